@@ -1,0 +1,118 @@
+/* ns2vc_b200 — C-ABI of the B200-native NS2VC denoiser hot path.
+ *
+ * The reference (adelacvg/NS2VC) is pure Python/PyTorch and defines no FFI; its boundary for this
+ * path is the Python object graph.  This header is the C boundary the Python
+ * drop-in modules (ns2vc_b200/unet.py, fused.py) bind with ctypes; each entry point names the
+ * reference interface it stands in for.  Plain C types, raw device pointers + cudaStream_t,
+ * int return (0 = ok, <0 = error; ns2vc_last_error() returns the message).  No exceptions or C++
+ * types cross the ABI; the caller owns every buffer, the handle owns only its packed weights.
+ * All calls are stream-ordered, allocation-free after ns2vc_unet_finalize() and capturable in a
+ * CUDA graph.  One handle per device; not thread-safe per handle.
+ */
+#ifndef NS2VC_B200_H
+#define NS2VC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ns2vc_unet ns2vc_unet;
+typedef void* ns2vc_stream;   /* cudaStream_t */
+
+#define NS2VC_MAX_LEVELS 8
+
+/* Constructor arguments of UNet1DConditionModel (reference unet1d/unet_1d_condition.py:151-203,
+ * as called from model.py:391-400). */
+typedef struct ns2vc_unet_cfg {
+  int in_channels;            /* conv_in input channels = latent + content (356)                 */
+  int latent_channels;        /* leading channels that change every step (100); the rest is the  */
+                              /* step-invariant content embedding whose conv_in share is hoisted  */
+  int out_channels;           /* 100                                                              */
+  int n_levels;
+  int block_out_channels[NS2VC_MAX_LEVELS];
+  int layers_per_block[NS2VC_MAX_LEVELS];
+  int down_has_attn[NS2VC_MAX_LEVELS];   /* CrossAttnDownBlock2D (1) / DownBlock2D (0)           */
+  int up_has_attn[NS2VC_MAX_LEVELS];     /* CrossAttnUpBlock2D (1) / UpBlock2D (0)               */
+  int num_heads;              /* reference: attention_head_dim reinterpreted as head count (:219) */
+  int cross_attention_dim;
+  int norm_num_groups;
+  float norm_eps;
+  int time_scale_shift;       /* resnet_time_scale_shift == 'scale_shift'                         */
+  int add_embed_text;         /* addition_embed_type == 'text'                                    */
+  int add_embed_heads;        /* addition_embed_type_num_heads (64)                               */
+  int flip_sin_to_cos;
+  float freq_shift;
+} ns2vc_unet_cfg;
+
+const char* ns2vc_last_error(void);
+
+/* Build the layer plan for cfg (reference ctor, unet_1d_condition.py:421-559). */
+int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out);
+void ns2vc_unet_destroy(ns2vc_unet* h);
+
+/* state_dict contract (reference key names and shapes). */
+int ns2vc_unet_num_weights(const ns2vc_unet* h);
+int ns2vc_unet_weight_info(const ns2vc_unet* h, int i, const char** name, int64_t shape[4], int* ndim);
+/* Copy one parameter (device fp32, contiguous) into the handle: load_state_dict per key. */
+int ns2vc_unet_load_weight(ns2vc_unet* h, const char* key, const float* dptr, const int64_t* shape, int ndim,
+                           ns2vc_stream stream);
+/* Pack every contraction weight into the tcgen05 operand layout (bf16 hi/lo, swizzled tiles);
+ * fails if any key is missing (strict load, reference inference/infer_tool.py:27). */
+int ns2vc_unet_finalize(ns2vc_unet* h, ns2vc_stream stream);
+
+int ns2vc_unet_workspace_bytes(const ns2vc_unet* h, int B, int T, int S, size_t* bytes);
+
+/* Step-invariant conditioning (the part of Diffusion_Encoder.forward / UNet forward that does not
+ * depend on x or t: model.py:406-411, unet_1d_condition.py:816-818, 869-870, cross-attention K/V
+ * attention_processor.py:1017-1020).
+ *   content : [B, in_channels-latent_channels, T] fp32, batch stride content_bstride floats (may be NULL if 0 ch)
+ *   prompt  : [B, S, cross_attention_dim] fp32 contiguous (encoder_hidden_states)
+ *   mask    : [B, S] uint8 (1 = attend), or NULL (no encoder_attention_mask)                    */
+int ns2vc_unet_prepare_cond(ns2vc_unet* h, const float* content, long long content_bstride, const float* prompt,
+                            const uint8_t* mask, int B, int T, int S, void* ws, ns2vc_stream stream);
+
+/* UNet1DConditionModel.forward (unet_1d_condition.py:743-1037) given prepared conditioning.
+ *   x [B, latent_channels, T] fp32 (batch stride x_bstride floats), t [B] fp32 -> out [B, out_channels, T] */
+int ns2vc_unet_forward(ns2vc_unet* h, const float* x, long long x_bstride, const float* t, float* out, int B, int T,
+                       int S, void* ws, ns2vc_stream stream);
+
+/* Per-step sampler math fused into one element-wise kernel (bit-exact fp32 op order).
+ * DPM-Solver++(2M): model_wrapper x_start->noise (sampler/dpm_solver.py:291-292), data_prediction_fn
+ * (:437-439), dpm_solver_first_update (:569-576), multistep_dpm_solver_second_update (:813-831). */
+typedef struct ns2vc_dpm_coef {
+  float alpha_s, sigma_s, c_x, c_m, c_d, inv_r0;
+  int order;                  /* 0: x0 round trip only; 1 / 2: + first / second order update       */
+} ns2vc_dpm_coef;
+int ns2vc_dpm_step(const float* x, const float* unet_out, const float* m_prev, const ns2vc_dpm_coef* c, float* m_cur,
+                   float* x_next, size_t n, ns2vc_stream stream);
+
+/* UniPC-bh2 (sampler/uni_pc.py:471-588): corrector at t and predictor to the next time. */
+typedef struct ns2vc_unipc_coef {
+  float alpha_t, sigma_t, c_x, c_m, ab, rk, rho0, rho1;
+  int corr_order;
+  float n_c_x, n_c_m, nab, nrk;
+  int pred_order;
+} ns2vc_unipc_coef;
+int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0, const float* m1,
+                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, ns2vc_stream stream);
+
+/* Bit-exact index helpers (host, no GPU): nearest-neighbour source index of F.interpolate(size=)
+ * (reference resnet.py:160) and the stride-2 conv length rule (resnet.py:200). */
+int ns2vc_nearest_index(int t_in, int t_out, int* idx /* [t_out] */);
+int ns2vc_down_length(int t);
+
+/* Diagnostics used by the parity tests. */
+int ns2vc_unet_num_taps(const ns2vc_unet* h);
+int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* level, int* channels);
+int ns2vc_unet_set_tap(ns2vc_unet* h, int i, float* dst /* device [B, T_level, C] token-major, or NULL */);
+const char* ns2vc_unet_plan_string(const ns2vc_unet* h);
+int ns2vc_unet_launch_count(const ns2vc_unet* h);  /* kernels launched by the last forward */
+const char* ns2vc_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NS2VC_B200_H */

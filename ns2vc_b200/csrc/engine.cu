@@ -1,0 +1,947 @@
+// Denoiser engine: layer plan, weight registry + packing, per-shape launch program, C-ABI.
+//
+// The plan restates the block structure of the reference UNet1DConditionModel
+// (unet1d/unet_1d_condition.py:421-559, forward :943-1032) — see ns2vc_b200/arch.py for the
+// Python twin that the oracle uses; tests compare the two plan strings.
+#include "common.cuh"
+#include "../../include/ns2vc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace ns2vc;
+
+namespace {
+
+struct PlanOp {
+  enum Kind { PUSH, POP_CAT, RESNET, XFORMER, DOWN, UP } kind;
+  std::string prefix;
+  int cin = 0, cout = 0, level = 0;
+  int c1 = 0, c2 = 0;       // RESNET: channels of the running tensor and of the concatenated skip
+};
+
+struct WSlot {
+  std::string name;
+  std::vector<int64_t> shape;
+  float* d = nullptr;       // owned fp32 copy
+  bool loaded = false;
+  size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+struct PackedB {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  float* f32 = nullptr;
+  int Npad = 0, nkb = 0, n_logical = 0;
+};
+
+inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+inline int nkb_of(int c) { return (c + 63) / 64; }
+
+struct ResnetSite {
+  std::string p;
+  int c1, c2, cin, cout;
+  bool shortcut;
+  PackedB conv1, conv2;      // conv2 also carries the 1x1 shortcut K-blocks
+  float* bias2 = nullptr;    // conv2.bias (+ conv_shortcut.bias)
+  int film_off = 0;
+};
+struct XformerSite {
+  std::string p;
+  int c;
+  PackedB proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
+  int kv_off = 0;            // column offset of this block's K|V in the cross K/V cache
+};
+struct ConvSite { std::string p; int c; PackedB w; };
+
+// One launch of the per-shape program.
+struct Launch {
+  enum Kind { GEMM, ATTN, GN, LN_STATS, LN_APPLY, LINEAR, NCT2TOK, POOL_CLS, POOL_ATT, MASKBIAS, TAP } kind;
+  GemmOp gemm;
+  AttnOp attn;
+  GnOp gn;
+  LinOp lin;
+  // generic small args
+  const float* a = nullptr; const float* b = nullptr; const float* c = nullptr; float* o = nullptr;
+  const uint8_t* mask = nullptr;
+  int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0; float f0 = 0; long long ll0 = 0;
+  int patch = 0;             // 1: a<-x (forward), 2: lin.x<-t, 3: gemm.out<-out, 4: a<-content, 5: gemm seg0 src<-prompt / a<-prompt, 6: mask
+  int tap_index = -1;
+};
+
+struct Arena {           // bump allocator over the caller's workspace (or a dry run when base == nullptr)
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <class T> T* get(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct ns2vc_unet {
+  ns2vc_unet_cfg cfg;
+  int ted = 0;                                   // time_embed_dim
+  std::vector<PlanOp> plan;
+  std::vector<WSlot> weights;
+  std::unordered_map<std::string, int> windex;
+  bool finalized = false;
+  bool simt = false;
+  std::string plan_str;
+
+  std::vector<ResnetSite> resnets;
+  std::vector<XformerSite> xformers;
+  std::vector<ConvSite> resamplers;
+  PackedB convin_lat, convin_content, conv_out, kv_all;
+  int kv_total = 0, film_total = 0;
+  float* film_W = nullptr; float* film_b = nullptr;       // concatenated time_emb_proj
+  float* pool_kv_W = nullptr; float* pool_kv_b = nullptr; // concatenated k_proj | v_proj
+  std::vector<void*> owned;                               // everything to cudaFree
+
+  // cached program
+  int pB = 0, pT = 0, pS = 0; void* pws = nullptr; bool has_mask = false; bool cond_ready = false;
+  std::vector<Launch> prog_cond, prog_fwd;
+  std::vector<int*> rowmaps;                              // device index tables owned by the program
+  std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch;
+  std::vector<float*> tap_dst;
+  int last_launches = 0;
+
+  const float* W(const std::string& n) const {
+    auto it = windex.find(n);
+    return it == windex.end() ? nullptr : weights[it->second].d;
+  }
+};
+
+namespace {
+
+int level_len(int T, int level) {
+  for (int i = 0; i < level; ++i) T = (T - 1) / 2 + 1;
+  return T;
+}
+
+void add_w(ns2vc_unet* h, const std::string& n, std::vector<int64_t> shape) {
+  h->windex[n] = (int)h->weights.size();
+  WSlot s; s.name = n; s.shape = std::move(shape);
+  h->weights.push_back(std::move(s));
+}
+void add_conv(ns2vc_unet* h, const std::string& p, int co, int ci, int k) { add_w(h, p + ".weight", {co, ci, k}); add_w(h, p + ".bias", {co}); }
+void add_lin(ns2vc_unet* h, const std::string& p, int co, int ci, bool bias = true) { add_w(h, p + ".weight", {co, ci}); if (bias) add_w(h, p + ".bias", {co}); }
+void add_norm(ns2vc_unet* h, const std::string& p, int c) { add_w(h, p + ".weight", {c}); add_w(h, p + ".bias", {c}); }
+
+void build_plan(ns2vc_unet* h) {
+  const ns2vc_unet_cfg& c = h->cfg;
+  const int n = c.n_levels;
+  std::vector<int> skip;
+  auto push = [&](int ch, int level) { PlanOp o; o.kind = PlanOp::PUSH; o.cout = ch; o.level = level; h->plan.push_back(o); skip.push_back(ch); };
+  int ch = c.block_out_channels[0], level = 0;
+  push(ch, 0);
+  for (int i = 0; i < n; ++i) {
+    const int cout = c.block_out_channels[i];
+    for (int j = 0; j < c.layers_per_block[i]; ++j) {
+      PlanOp r; r.kind = PlanOp::RESNET; r.prefix = "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+      r.cin = ch; r.cout = cout; r.level = level; r.c1 = ch; r.c2 = 0; h->plan.push_back(r);
+      ch = cout;
+      if (c.down_has_attn[i]) {
+        PlanOp x; x.kind = PlanOp::XFORMER; x.prefix = "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
+        x.cin = x.cout = ch; x.level = level; h->plan.push_back(x);
+      }
+      push(ch, level);
+    }
+    if (i != n - 1) {
+      ++level;
+      PlanOp d; d.kind = PlanOp::DOWN; d.prefix = "down_blocks." + std::to_string(i) + ".downsamplers.0"; d.cin = d.cout = ch; d.level = level;
+      h->plan.push_back(d);
+      push(ch, level);
+    }
+  }
+  auto res = [&](const std::string& p, int c1, int c2, int cout) {
+    PlanOp r; r.kind = PlanOp::RESNET; r.prefix = p; r.cin = c1 + c2; r.cout = cout; r.level = level; r.c1 = c1; r.c2 = c2; h->plan.push_back(r);
+  };
+  auto xf = [&](const std::string& p, int cc) {
+    PlanOp x; x.kind = PlanOp::XFORMER; x.prefix = p; x.cin = x.cout = cc; x.level = level; h->plan.push_back(x);
+  };
+  res("mid_block.resnets.0", ch, 0, ch);
+  xf("mid_block.attentions.0", ch);
+  res("mid_block.resnets.1", ch, 0, ch);
+  for (int i = 0; i < n; ++i) {
+    const int cout = c.block_out_channels[n - 1 - i];
+    const int layers = c.layers_per_block[n - 1 - i] + 1;
+    for (int j = 0; j < layers; ++j) {
+      const int sk = skip.back(); skip.pop_back();
+      PlanOp pc; pc.kind = PlanOp::POP_CAT; pc.cin = ch; pc.cout = ch + sk; pc.level = level; h->plan.push_back(pc);
+      res("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), ch, sk, cout);
+      ch = cout;
+      if (c.up_has_attn[i]) xf("up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), ch);
+    }
+    if (i != n - 1) {
+      --level;
+      PlanOp u; u.kind = PlanOp::UP; u.prefix = "up_blocks." + std::to_string(i) + ".upsamplers.0"; u.cin = u.cout = ch; u.level = level;
+      h->plan.push_back(u);
+    }
+  }
+  // plan string (compared with ns2vc_b200.arch.build_plan in tests)
+  static const char* kn[] = {"push", "pop_cat", "resnet", "xformer", "down", "up"};
+  for (auto& o : h->plan) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s|%s|%d|%d|%d\n", kn[o.kind], o.prefix.c_str(), o.cin, o.cout, o.level);
+    h->plan_str += buf;
+  }
+}
+
+void register_weights(ns2vc_unet* h) {
+  const ns2vc_unet_cfg& c = h->cfg;
+  const int c0 = c.block_out_channels[0], ted = h->ted, xd = c.cross_attention_dim;
+  add_conv(h, "conv_in", c0, c.in_channels, 3);
+  add_lin(h, "time_embedding.linear_1", ted, c0);
+  add_lin(h, "time_embedding.linear_2", ted, ted);
+  if (c.add_embed_text) {
+    add_norm(h, "add_embedding.norm1", xd);
+    add_w(h, "add_embedding.pool.positional_embedding", {1, xd});
+    add_lin(h, "add_embedding.pool.k_proj", xd, xd);
+    add_lin(h, "add_embedding.pool.q_proj", xd, xd);
+    add_lin(h, "add_embedding.pool.v_proj", xd, xd);
+    add_lin(h, "add_embedding.proj", ted, xd);
+    add_norm(h, "add_embedding.norm2", ted);
+  }
+  for (auto& o : h->plan) {
+    if (o.kind == PlanOp::RESNET) {
+      const std::string& p = o.prefix;
+      add_norm(h, p + ".norm1", o.cin);
+      add_conv(h, p + ".conv1", o.cout, o.cin, 3);
+      add_lin(h, p + ".time_emb_proj", c.time_scale_shift ? 2 * o.cout : o.cout, ted);
+      add_norm(h, p + ".norm2", o.cout);
+      add_conv(h, p + ".conv2", o.cout, o.cout, 3);
+      if (o.cin != o.cout) add_conv(h, p + ".conv_shortcut", o.cout, o.cin, 1);
+    } else if (o.kind == PlanOp::XFORMER) {
+      const std::string& p = o.prefix; const int cc = o.cout;
+      add_norm(h, p + ".norm", cc);
+      add_conv(h, p + ".proj_in", cc, cc, 1);
+      const std::string b = p + ".transformer_blocks.0";
+      add_norm(h, b + ".norm1", cc);
+      add_lin(h, b + ".attn1.to_q", cc, cc, false); add_lin(h, b + ".attn1.to_k", cc, cc, false); add_lin(h, b + ".attn1.to_v", cc, cc, false);
+      add_lin(h, b + ".attn1.to_out.0", cc, cc);
+      add_norm(h, b + ".norm2", cc);
+      add_lin(h, b + ".attn2.to_q", cc, cc, false); add_lin(h, b + ".attn2.to_k", cc, xd, false); add_lin(h, b + ".attn2.to_v", cc, xd, false);
+      add_lin(h, b + ".attn2.to_out.0", cc, cc);
+      add_norm(h, b + ".norm3", cc);
+      add_lin(h, b + ".ff.net.0.proj", 8 * cc, cc);
+      add_lin(h, b + ".ff.net.2", cc, 4 * cc);
+      add_conv(h, p + ".proj_out", cc, cc, 1);
+    } else if (o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) {
+      add_conv(h, o.prefix + ".conv", o.cout, o.cin, 3);
+    }
+  }
+  add_norm(h, "conv_norm_out", c0);
+  add_conv(h, "conv_out", c.out_channels, c0, 3);
+}
+
+template <class T>
+int dev_alloc(ns2vc_unet* h, T** p, size_t n, bool zero) {
+  void* q = nullptr;
+  NS_CHECK_CUDA(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) NS_CHECK_CUDA(cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+int alloc_packed(ns2vc_unet* h, PackedB& pb, int n_logical, int n_packed, int nkb) {
+  pb.n_logical = n_logical;
+  pb.Npad = pad_to(n_packed, 128);
+  pb.nkb = nkb;
+  const size_t elems = (size_t)nkb * pb.Npad * 64;
+  if (dev_alloc(h, &pb.hi, elems, true)) return -2;
+  if (dev_alloc(h, &pb.lo, elems, true)) return -2;
+  if (h->simt) { if (dev_alloc(h, &pb.f32, elems, true)) return -2; }
+  return 0;
+}
+
+// Pack `w` ([n_rows, cin_total, ktaps]) channels [cin0, cin0+ncin) of tap `tap` at k-block kb0, columns n_dst0..
+int pack_seg(ns2vc_unet* h, PackedB& pb, const std::string& wname, int n_rows, int cin_total, int ktaps, int tap, int cin0,
+             int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st) {
+  const float* w = h->W(wname);
+  NS_REQUIRE(w != nullptr, "pack: weight %s missing", wname.c_str());
+  PackSeg ps;
+  ps.w = w; ps.n_rows = n_rows; ps.cin_total = cin_total; ps.ktaps = ktaps; ps.tap = tap; ps.cin0 = cin0; ps.ncin = ncin;
+  ps.n_dst0 = n_dst0; ps.kb0 = kb0; ps.nkb = nkb_of(ncin); ps.geglu_half = geglu_half;
+  return launch_pack_b(ps, pb.hi, pb.lo, pb.f32, pb.Npad, st);
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+int pack_all(ns2vc_unet* h, cudaStream_t st) {
+  const ns2vc_unet_cfg& c = h->cfg;
+  const int c0 = c.block_out_channels[0];
+  const int Cl = c.latent_channels, Cc = c.in_channels - c.latent_channels;
+  int rc;
+  // conv_in: latent part and (hoisted) content part
+  {
+    const int nl = nkb_of(Cl);
+    if ((rc = alloc_packed(h, h->convin_lat, c0, c0, 3 * nl))) return rc;
+    for (int j = 0; j < 3; ++j)
+      if ((rc = pack_seg(h, h->convin_lat, "conv_in.weight", c0, c.in_channels, 3, j, 0, Cl, 0, j * nl, 0, st))) return rc;
+    if (Cc > 0) {
+      const int nc = nkb_of(Cc);
+      if ((rc = alloc_packed(h, h->convin_content, c0, c0, 3 * nc))) return rc;
+      for (int j = 0; j < 3; ++j)
+        if ((rc = pack_seg(h, h->convin_content, "conv_in.weight", c0, c.in_channels, 3, j, Cl, Cc, 0, j * nc, 0, st))) return rc;
+    }
+  }
+  // resnets / transformers / resamplers in plan order
+  int film_off = 0, kv_off = 0;
+  for (auto& o : h->plan) {
+    if (o.kind == PlanOp::RESNET) {
+      ResnetSite s; s.p = o.prefix; s.c1 = o.c1; s.c2 = o.c2; s.cin = o.cin; s.cout = o.cout; s.shortcut = o.cin != o.cout;
+      const int n1 = nkb_of(s.c1), n2 = s.c2 ? nkb_of(s.c2) : 0, no = nkb_of(s.cout);
+      if ((rc = alloc_packed(h, s.conv1, s.cout, s.cout, 3 * (n1 + n2)))) return rc;
+      for (int j = 0; j < 3; ++j) {
+        if ((rc = pack_seg(h, s.conv1, s.p + ".conv1.weight", s.cout, s.cin, 3, j, 0, s.c1, 0, j * (n1 + n2), 0, st))) return rc;
+        if (s.c2 && (rc = pack_seg(h, s.conv1, s.p + ".conv1.weight", s.cout, s.cin, 3, j, s.c1, s.c2, 0, j * (n1 + n2) + n1, 0, st))) return rc;
+      }
+      const int nsc = s.shortcut ? (n1 + n2) : 0;
+      if ((rc = alloc_packed(h, s.conv2, s.cout, s.cout, 3 * no + nsc))) return rc;
+      for (int j = 0; j < 3; ++j)
+        if ((rc = pack_seg(h, s.conv2, s.p + ".conv2.weight", s.cout, s.cout, 3, j, 0, s.cout, 0, j * no, 0, st))) return rc;
+      if (s.shortcut) {
+        if ((rc = pack_seg(h, s.conv2, s.p + ".conv_shortcut.weight", s.cout, s.cin, 1, 0, 0, s.c1, 0, 3 * no, 0, st))) return rc;
+        if (s.c2 && (rc = pack_seg(h, s.conv2, s.p + ".conv_shortcut.weight", s.cout, s.cin, 1, 0, s.c1, s.c2, 0, 3 * no + n1, 0, st))) return rc;
+      }
+      if (dev_alloc(h, &s.bias2, s.cout, false)) return -2;
+      add_vec_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(h->W(s.p + ".conv2.bias"), s.shortcut ? h->W(s.p + ".conv_shortcut.bias") : nullptr, s.bias2, s.cout);
+      s.film_off = film_off;
+      film_off += c.time_scale_shift ? 2 * s.cout : s.cout;
+      h->resnets.push_back(s);
+    } else if (o.kind == PlanOp::XFORMER) {
+      XformerSite x; x.p = o.prefix; x.c = o.cout;
+      const int C = x.c, nk = nkb_of(C);
+      const std::string b = x.p + ".transformer_blocks.0";
+      if ((rc = alloc_packed(h, x.proj_in, C, C, nk))) return rc;
+      if ((rc = pack_seg(h, x.proj_in, x.p + ".proj_in.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      if ((rc = alloc_packed(h, x.qkv, 3 * C, 3 * C, nk))) return rc;
+      const char* qkvn[3] = {".attn1.to_q.weight", ".attn1.to_k.weight", ".attn1.to_v.weight"};
+      for (int i = 0; i < 3; ++i)
+        if ((rc = pack_seg(h, x.qkv, b + qkvn[i], C, C, 1, 0, 0, C, i * C, 0, 0, st))) return rc;
+      if ((rc = alloc_packed(h, x.out1, C, C, nk))) return rc;
+      if ((rc = pack_seg(h, x.out1, b + ".attn1.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      if ((rc = alloc_packed(h, x.q2, C, C, nk))) return rc;
+      if ((rc = pack_seg(h, x.q2, b + ".attn2.to_q.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      if ((rc = alloc_packed(h, x.out2, C, C, nk))) return rc;
+      if ((rc = pack_seg(h, x.out2, b + ".attn2.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      NS_REQUIRE((4 * C) % 64 == 0, "transformer width %d: 4C must be a multiple of 64", C);
+      if ((rc = alloc_packed(h, x.ff1, 4 * C, 8 * C, nk))) return rc;
+      if ((rc = pack_seg(h, x.ff1, b + ".ff.net.0.proj.weight", 8 * C, C, 1, 0, 0, C, 0, 0, 4 * C, st))) return rc;
+      if ((rc = alloc_packed(h, x.ff2, C, C, nkb_of(4 * C)))) return rc;
+      if ((rc = pack_seg(h, x.ff2, b + ".ff.net.2.weight", C, 4 * C, 1, 0, 0, 4 * C, 0, 0, 0, st))) return rc;
+      if ((rc = alloc_packed(h, x.proj_out, C, C, nk))) return rc;
+      if ((rc = pack_seg(h, x.proj_out, x.p + ".proj_out.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      x.kv_off = kv_off;
+      kv_off += 2 * C;
+      h->xformers.push_back(x);
+    } else if (o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) {
+      ConvSite s; s.p = o.prefix; s.c = o.cout;
+      const int nk = nkb_of(s.c);
+      if ((rc = alloc_packed(h, s.w, s.c, s.c, 3 * nk))) return rc;
+      for (int j = 0; j < 3; ++j)
+        if ((rc = pack_seg(h, s.w, s.p + ".conv.weight", s.c, s.c, 3, j, 0, s.c, 0, j * nk, 0, st))) return rc;
+      h->resamplers.push_back(s);
+    }
+  }
+  h->film_total = film_off;
+  h->kv_total = kv_off;
+  // conv_out
+  {
+    const int nk = nkb_of(c0);
+    if ((rc = alloc_packed(h, h->conv_out, c.out_channels, c.out_channels, 3 * nk))) return rc;
+    for (int j = 0; j < 3; ++j)
+      if ((rc = pack_seg(h, h->conv_out, "conv_out.weight", c.out_channels, c0, 3, j, 0, c0, 0, j * nk, 0, st))) return rc;
+  }
+  // all cross-attention K|V projections as one GEMM over the prompt
+  if (h->kv_total > 0) {
+    const int xd = c.cross_attention_dim;
+    if ((rc = alloc_packed(h, h->kv_all, h->kv_total, h->kv_total, nkb_of(xd)))) return rc;
+    for (auto& x : h->xformers) {
+      const std::string b = x.p + ".transformer_blocks.0";
+      if ((rc = pack_seg(h, h->kv_all, b + ".attn2.to_k.weight", x.c, xd, 1, 0, 0, xd, x.kv_off, 0, 0, st))) return rc;
+      if ((rc = pack_seg(h, h->kv_all, b + ".attn2.to_v.weight", x.c, xd, 1, 0, 0, xd, x.kv_off + x.c, 0, 0, st))) return rc;
+    }
+  }
+  // concatenated FiLM projection [film_total, ted]
+  if (dev_alloc(h, &h->film_W, (size_t)h->film_total * h->ted, false)) return -2;
+  if (dev_alloc(h, &h->film_b, (size_t)h->film_total, false)) return -2;
+  for (auto& s : h->resnets) {
+    const int rows = c.time_scale_shift ? 2 * s.cout : s.cout;
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->film_W + (size_t)s.film_off * h->ted, h->W(s.p + ".time_emb_proj.weight"), (size_t)rows * h->ted * 4, cudaMemcpyDeviceToDevice, st));
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->film_b + s.film_off, h->W(s.p + ".time_emb_proj.bias"), (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (c.add_embed_text) {
+    const int xd = c.cross_attention_dim;
+    if (dev_alloc(h, &h->pool_kv_W, (size_t)2 * xd * xd, false)) return -2;
+    if (dev_alloc(h, &h->pool_kv_b, (size_t)2 * xd, false)) return -2;
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->pool_kv_W, h->W("add_embedding.pool.k_proj.weight"), (size_t)xd * xd * 4, cudaMemcpyDeviceToDevice, st));
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->pool_kv_W + (size_t)xd * xd, h->W("add_embedding.pool.v_proj.weight"), (size_t)xd * xd * 4, cudaMemcpyDeviceToDevice, st));
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->pool_kv_b, h->W("add_embedding.pool.k_proj.bias"), (size_t)xd * 4, cudaMemcpyDeviceToDevice, st));
+    NS_CHECK_CUDA(cudaMemcpyAsync(h->pool_kv_b + xd, h->W("add_embedding.pool.v_proj.bias"), (size_t)xd * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  NS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Program construction
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+  ns2vc_unet* h;
+  Arena ar;
+  int B, T, S;
+  std::vector<Launch>* out;
+  bool dry;
+  bool taps = false;
+
+  void seg(GemmOp& g, const float* src, int ld, int ch0, int nch, int tap, int mode, const float* p0 = nullptr,
+           const float* p1 = nullptr, const float* p2 = nullptr, int aoff = 0, int ald = 0) {
+    ASeg& s = g.seg[g.nseg++];
+    s.src = src; s.ld = ld; s.ch0 = ch0; s.nch = nch; s.nkb = nkb_of(nch); s.tap = tap; s.mode = mode;
+    s.p0 = p0; s.p1 = p1; s.p2 = p2; s.aoff = aoff; s.ald = ald;
+    g.nkb_total += s.nkb;
+  }
+  GemmOp gemm_base(const PackedB& w, int T_out, int T_src, int stride = 1) {
+    GemmOp g; memset(&g, 0, sizeof(g));
+    g.B = B; g.T_out = T_out; g.T_src = T_src; g.T_virt = T_src; g.stride = stride;
+    g.w_hi = w.hi; g.w_lo = w.lo; g.w_f32 = w.f32; g.N = w.Npad; g.n_valid = w.n_logical;
+    return g;
+  }
+  void emit_gemm(GemmOp& g, const PackedB& w, int patch = 0) {
+    Launch l; l.kind = Launch::GEMM; l.gemm = g; l.patch = patch;
+    if (!dry && g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
+    out->push_back(l);
+  }
+  void emit_gn(const float* s1, int ld1, int C1, const float* s2, int ld2, int C2, int Tl, float eps, const float* gamma,
+               const float* beta, const float* film, int film_ld, float* scale, float* shift, double* acc, unsigned* cnt) {
+    Launch l; l.kind = Launch::GN;
+    GnOp& g = l.gn; g.src1 = s1; g.ld1 = ld1; g.C1 = C1; g.src2 = s2; g.ld2 = ld2; g.C2 = C2; g.B = B; g.T = Tl;
+    g.G = h->cfg.norm_num_groups; g.eps = eps; g.gamma = gamma; g.beta = beta; g.film = film; g.film_ld = film_ld;
+    g.scale = scale; g.shift = shift; g.acc = acc; g.counter = cnt;
+    out->push_back(l);
+  }
+  void emit_ln_stats(const float* x, int ld, int M, int C, float* stats) {
+    Launch l; l.kind = Launch::LN_STATS; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.o = stats; out->push_back(l);
+  }
+  void emit_tap(const std::string& name, const float* src, int level, int C, int Tl) {
+    if (!dry && taps) {
+      Launch l; l.kind = Launch::TAP; l.a = src; l.i0 = B * Tl * C; l.tap_index = (int)h->tap_names.size(); out->push_back(l);
+      h->tap_names.push_back(name); h->tap_level.push_back(level); h->tap_ch.push_back(C);
+    }
+  }
+};
+
+int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_out) {
+  const ns2vc_unet_cfg& c = h->cfg;
+  const bool dry = (ws == nullptr);
+  const int nlev = c.n_levels;
+  const int G = c.norm_num_groups;
+  const int c0 = c.block_out_channels[0];
+  const int Cl = c.latent_channels, Cc = c.in_channels - Cl;
+  const int Clp = pad_to(Cl, 8);
+  const int xd = c.cross_attention_dim, ted = h->ted;
+  std::vector<int> Tl(nlev);
+  for (int l = 0; l < nlev; ++l) Tl[l] = level_len(T, l);
+  NS_REQUIRE(Tl[nlev - 1] >= 1 && T >= 1 && B >= 1 && S >= 1, "bad shape B=%d T=%d S=%d", B, T, S);
+
+  std::vector<Launch> cond, fwd;
+  if (!dry) {
+    for (int* p : h->rowmaps) cudaFree(p);
+    h->rowmaps.clear();
+    h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear();
+  }
+  Builder bc{h, Arena{(uint8_t*)ws, 0}, B, T, S, &cond, dry};
+  Arena& ar = bc.ar;
+
+  // ---- persistent conditioning buffers
+  float* P = (Cc > 0) ? ar.get<float>((size_t)B * T * c0) : nullptr;      // conv_in(content) + bias
+  float* kvc = ar.get<float>((size_t)B * S * std::max(h->kv_total, 1));
+  float* maskbias = ar.get<float>((size_t)B * S);
+  float* aug = ar.get<float>((size_t)B * ted);
+  // ---- conditioning scratch
+  float* ctok = (Cc > 0) ? ar.get<float>((size_t)B * T * Cc) : nullptr;
+  float* pn = ar.get<float>((size_t)B * S * xd);
+  float* ptok = ar.get<float>((size_t)B * (S + 1) * xd);
+  float* pq = ar.get<float>((size_t)B * xd);
+  float* pkv = ar.get<float>((size_t)B * (S + 1) * 2 * xd);
+  float* ppool = ar.get<float>((size_t)B * xd);
+  float* pproj = ar.get<float>((size_t)B * ted);
+
+  // ================= conditioning program =================
+  if (Cc > 0) {
+    Launch l; l.kind = Launch::NCT2TOK; l.patch = 4; l.i0 = Cc; l.i1 = T; l.o = ctok; l.i2 = Cc; l.i3 = Cc; cond.push_back(l);
+    GemmOp g = bc.gemm_base(h->convin_content, T, T);
+    for (int j = 0; j < 3; ++j) bc.seg(g, ctok, Cc, 0, Cc, j - 1, A_RAW);
+    g.flags = EPI_BIAS; g.bias = h->W("conv_in.bias"); g.out = P; g.out_ld = c0;
+    bc.emit_gemm(g, h->convin_content);
+  }
+  { Launch l; l.kind = Launch::MASKBIAS; l.patch = 6; l.i0 = B * S; l.o = maskbias; cond.push_back(l); }
+  if (h->kv_total > 0) {
+    GemmOp g = bc.gemm_base(h->kv_all, S, S);
+    bc.seg(g, nullptr, xd, 0, xd, 0, A_RAW);
+    g.out = kvc; g.out_ld = h->kv_total;
+    bc.emit_gemm(g, h->kv_all, 5);
+  }
+  if (c.add_embed_text) {
+    // TextTimeEmbedding (embeddings.py:421-434): LN -> AttentionPooling -> Linear -> LN
+    { Launch l; l.kind = Launch::LN_APPLY; l.patch = 5; l.i0 = xd; l.i1 = B * S; l.i2 = xd; l.f0 = 1e-5f;
+      l.b = h->W("add_embedding.norm1.weight"); l.c = h->W("add_embedding.norm1.bias"); l.o = pn; l.i3 = xd; cond.push_back(l); }
+    { Launch l; l.kind = Launch::POOL_CLS; l.a = pn; l.b = h->W("add_embedding.pool.positional_embedding"); l.i0 = S; l.i1 = xd; l.o = ptok; cond.push_back(l); }
+    { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+      o.x = ptok; o.x_ld = (S + 1) * xd; o.M = B; o.K = xd; o.W = h->W("add_embedding.pool.q_proj.weight"); o.bias = h->W("add_embedding.pool.q_proj.bias");
+      o.N = xd; o.out = pq; o.out_ld = xd; cond.push_back(l); }
+    { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+      o.x = ptok; o.x_ld = xd; o.M = B * (S + 1); o.K = xd; o.W = h->pool_kv_W; o.bias = h->pool_kv_b; o.N = 2 * xd; o.out = pkv; o.out_ld = 2 * xd; cond.push_back(l); }
+    { Launch l; l.kind = Launch::POOL_ATT; l.a = pq; l.b = pkv; l.i0 = S + 1; l.i1 = xd; l.i2 = c.add_embed_heads; l.o = ppool; cond.push_back(l); }
+    { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+      o.x = ppool; o.x_ld = xd; o.M = B; o.K = xd; o.W = h->W("add_embedding.proj.weight"); o.bias = h->W("add_embedding.proj.bias"); o.N = ted; o.out = pproj; o.out_ld = ted; cond.push_back(l); }
+    { Launch l; l.kind = Launch::LN_APPLY; l.a = pproj; l.i0 = ted; l.i1 = B; l.i2 = ted; l.f0 = 1e-5f;
+      l.b = h->W("add_embedding.norm2.weight"); l.c = h->W("add_embedding.norm2.bias"); l.o = aug; l.i3 = ted; cond.push_back(l); }
+  }
+
+  // ================= forward program =================
+  Builder bf{h, ar, B, T, S, &fwd, dry};
+  bf.taps = true;
+  Arena& fa = bf.ar;
+  // per-step small buffers
+  float* xtok = fa.get<float>((size_t)B * T * Clp);
+  float* temb1 = fa.get<float>((size_t)B * ted);
+  float* emb = fa.get<float>((size_t)B * ted);
+  float* film = fa.get<float>((size_t)B * std::max(h->film_total, 1));
+  double* gn_acc = fa.get<double>((size_t)B * G * 2);
+  unsigned* gn_cnt = fa.get<unsigned>((size_t)B * G);
+  // activation buffers
+  size_t max_act = 0, max_ff = 0, max_qkv = 0;
+  for (auto& o : h->plan) {
+    const size_t rows = (size_t)B * Tl[o.level];
+    if (o.kind == PlanOp::RESNET || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) max_act = std::max(max_act, rows * o.cout);
+    if (o.kind == PlanOp::XFORMER) { max_act = std::max(max_act, rows * o.cout); max_ff = std::max(max_ff, rows * 4 * o.cout); max_qkv = std::max(max_qkv, rows * 3 * o.cout); }
+  }
+  max_act = std::max(max_act, (size_t)B * T * c0);
+  float* rot[3]; for (int i = 0; i < 3; ++i) rot[i] = fa.get<float>(max_act);
+  float* H1 = fa.get<float>(max_act);
+  float* T0 = fa.get<float>(max_act);
+  float* T1 = fa.get<float>(max_act);
+  float* ATT = fa.get<float>(max_act);
+  float* QKV = fa.get<float>(std::max<size_t>(max_qkv, 1));
+  float* FF = fa.get<float>(std::max<size_t>(max_ff, 1));
+
+  // entry: x -> tokens, time path, conv_in
+  { Launch l; l.kind = Launch::NCT2TOK; l.patch = 1; l.i0 = Cl; l.i1 = T; l.o = xtok; l.i2 = Clp; l.i3 = Clp; fwd.push_back(l); }
+  { Launch l; l.kind = Launch::LINEAR; l.patch = 2; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+    o.x = nullptr; o.x_ld = 1; o.M = B; o.K = c0; o.W = h->W("time_embedding.linear_1.weight"); o.bias = h->W("time_embedding.linear_1.bias");
+    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; fwd.push_back(l); }
+  { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+    o.x = temb1; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->W("time_embedding.linear_2.weight"); o.bias = h->W("time_embedding.linear_2.bias");
+    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = aug; o.add_ld = ted; } fwd.push_back(l); }
+  if (h->film_total > 0) {
+    Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
+    o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; fwd.push_back(l);
+  }
+
+  std::vector<std::pair<float*, int>> skips;   // (ptr, channels)
+  int rot_i = 0;
+  auto next_out = [&](bool is_skip, size_t elems) -> float* {
+    if (is_skip) return fa.get<float>(elems);
+    float* p = rot[rot_i]; rot_i = (rot_i + 1) % 3; return p;
+  };
+  // is the op at plan index i followed (before the next compute op) by a PUSH?
+  auto followed_by_push = [&](size_t i) { return i + 1 < h->plan.size() && h->plan[i + 1].kind == PlanOp::PUSH; };
+
+  float* cur = nullptr; int cur_c = c0, cur_level = 0;
+  {
+    // conv_in output is the first skip
+    float* o = next_out(true, (size_t)B * T * c0);
+    GemmOp g = bf.gemm_base(h->convin_lat, T, T);
+    for (int j = 0; j < 3; ++j) bf.seg(g, xtok, Clp, 0, Clp, j - 1, A_RAW);
+    if (Cc > 0) { g.flags = EPI_RESIDUAL; g.res = P; g.res_ld = c0; }
+    else { g.flags = EPI_BIAS; g.bias = h->W("conv_in.bias"); }
+    g.out = o; g.out_ld = c0;
+    bf.emit_gemm(g, h->convin_lat);
+    cur = o;
+    bf.emit_tap("conv_in", cur, 0, c0, T);
+  }
+  const float* cat2 = nullptr; int cat2_c = 0;    // pending concat source
+  size_t ri = 0, xi = 0, si = 0;
+  for (size_t pi = 0; pi < h->plan.size(); ++pi) {
+    const PlanOp& o = h->plan[pi];
+    const int TL = Tl[o.level];
+    const size_t rows = (size_t)B * TL;
+    switch (o.kind) {
+      case PlanOp::PUSH: skips.push_back({cur, cur_c}); break;
+      case PlanOp::POP_CAT: cat2 = skips.back().first; cat2_c = skips.back().second; skips.pop_back(); break;
+      case PlanOp::RESNET: {
+        const ResnetSite& s = h->resnets[ri++];
+        const float* s1 = cur; const float* s2 = s.c2 ? cat2 : nullptr;
+        float* sc1 = fa.get<float>((size_t)B * s.cin); float* sh1 = fa.get<float>((size_t)B * s.cin);
+        float* sc2 = fa.get<float>((size_t)B * s.cout); float* sh2 = fa.get<float>((size_t)B * s.cout);
+        bf.emit_gn(s1, s.c1, s.c1, s2, s.c2, s.c2, TL, c.norm_eps, h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, sc1, sh1, gn_acc, gn_cnt);
+        {
+          GemmOp g = bf.gemm_base(s.conv1, TL, TL);
+          for (int j = 0; j < 3; ++j) {
+            bf.seg(g, s1, s.c1, 0, s.c1, j - 1, A_AFFINE_SILU, sc1, sh1, nullptr, 0, s.cin);
+            if (s.c2) bf.seg(g, s2, s.c2, 0, s.c2, j - 1, A_AFFINE_SILU, sc1, sh1, nullptr, s.c1, s.cin);
+          }
+          g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv1.bias");
+          if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
+          g.out = H1; g.out_ld = s.cout;
+          bf.emit_gemm(g, s.conv1);
+        }
+        bf.emit_gn(H1, s.cout, s.cout, nullptr, 0, 0, TL, c.norm_eps, h->W(s.p + ".norm2.weight"), h->W(s.p + ".norm2.bias"),
+                   c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, sc2, sh2, gn_acc, gn_cnt);
+        float* outp = next_out(followed_by_push(pi), rows * s.cout);
+        {
+          GemmOp g = bf.gemm_base(s.conv2, TL, TL);
+          for (int j = 0; j < 3; ++j) bf.seg(g, H1, s.cout, 0, s.cout, j - 1, A_AFFINE_SILU, sc2, sh2, nullptr, 0, s.cout);
+          g.flags = EPI_BIAS; g.bias = s.bias2;
+          if (s.shortcut) {
+            bf.seg(g, s1, s.c1, 0, s.c1, 0, A_RAW);
+            if (s.c2) bf.seg(g, s2, s.c2, 0, s.c2, 0, A_RAW);
+          } else {
+            g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1;
+          }
+          g.out = outp; g.out_ld = s.cout;
+          bf.emit_gemm(g, s.conv2);
+        }
+        cur = outp; cur_c = s.cout; cur_level = o.level; cat2 = nullptr; cat2_c = 0;
+        bf.emit_tap(s.p, cur, o.level, cur_c, TL);
+        break;
+      }
+      case PlanOp::XFORMER: {
+        const XformerSite& x = h->xformers[xi++];
+        const int C = x.c, H = c.num_heads, dh = C / H;
+        const std::string b = x.p + ".transformer_blocks.0";
+        float* sc = fa.get<float>((size_t)B * C); float* sh = fa.get<float>((size_t)B * C);
+        float* rs1 = fa.get<float>(rows * 2); float* rs2 = fa.get<float>(rows * 2); float* rs3 = fa.get<float>(rows * 2);
+        bf.emit_gn(cur, C, C, nullptr, 0, 0, TL, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
+        { GemmOp g = bf.gemm_base(x.proj_in, TL, TL); bf.seg(g, cur, C, 0, C, 0, A_AFFINE, sc, sh, nullptr, 0, C);
+          g.flags = EPI_BIAS; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bf.emit_gemm(g, x.proj_in); }
+        bf.emit_ln_stats(T0, C, (int)rows, C, rs1);
+        { GemmOp g = bf.gemm_base(x.qkv, TL, TL); bf.seg(g, T0, C, 0, C, 0, A_LN, rs1, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"));
+          g.out = QKV; g.out_ld = 3 * C; bf.emit_gemm(g, x.qkv); }
+        { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
+          a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C; a.out = ATT; a.out_ld = C;
+          a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); fwd.push_back(l); }
+        { GemmOp g = bf.gemm_base(x.out1, TL, TL); bf.seg(g, ATT, C, 0, C, 0, A_RAW);
+          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bf.emit_gemm(g, x.out1); }
+        bf.emit_ln_stats(T1, C, (int)rows, C, rs2);
+        { GemmOp g = bf.gemm_base(x.q2, TL, TL); bf.seg(g, T1, C, 0, C, 0, A_LN, rs2, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"));
+          g.out = QKV; g.out_ld = C; bf.emit_gemm(g, x.q2); }
+        { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
+          a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.kv_off + C; a.v_ld = h->kv_total; a.bias = maskbias;
+          a.out = ATT; a.out_ld = C; a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/; fwd.push_back(l); }
+        { GemmOp g = bf.gemm_base(x.out2, TL, TL); bf.seg(g, ATT, C, 0, C, 0, A_RAW);
+          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bf.emit_gemm(g, x.out2); }
+        bf.emit_ln_stats(T0, C, (int)rows, C, rs3);
+        { GemmOp g = bf.gemm_base(x.ff1, TL, TL); bf.seg(g, T0, C, 0, C, 0, A_LN, rs3, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"));
+          g.flags = EPI_GEGLU; g.bias = h->W(b + ".ff.net.0.proj.bias"); g.out = FF; g.out_ld = 4 * C; bf.emit_gemm(g, x.ff1); }
+        { GemmOp g = bf.gemm_base(x.ff2, TL, TL); bf.seg(g, FF, 4 * C, 0, 4 * C, 0, A_RAW);
+          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bf.emit_gemm(g, x.ff2); }
+        float* outp = next_out(followed_by_push(pi), rows * C);
+        { GemmOp g = bf.gemm_base(x.proj_out, TL, TL); bf.seg(g, T1, C, 0, C, 0, A_RAW);
+          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C; bf.emit_gemm(g, x.proj_out); }
+        cur = outp;
+        bf.emit_tap(x.p, cur, o.level, C, TL);
+        break;
+      }
+      case PlanOp::DOWN: {
+        const ConvSite& s = h->resamplers[si++];
+        const int Tin = Tl[o.level - 1];
+        float* outp = next_out(followed_by_push(pi), rows * s.c);
+        GemmOp g = bf.gemm_base(s.w, TL, Tin, 2);
+        for (int j = 0; j < 3; ++j) bf.seg(g, cur, s.c, 0, s.c, j - 1, A_RAW);
+        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        bf.emit_gemm(g, s.w);
+        cur = outp; cur_level = o.level;
+        bf.emit_tap(s.p, cur, o.level, s.c, TL);
+        break;
+      }
+      case PlanOp::UP: {
+        const ConvSite& s = h->resamplers[si++];
+        const int Tin = Tl[o.level + 1];
+        int* map_d = nullptr;
+        if (!dry) {
+          std::vector<int> idx(TL);
+          ns2vc_nearest_index(Tin, TL, idx.data());
+          NS_CHECK_CUDA(cudaMalloc(&map_d, (size_t)TL * sizeof(int)));
+          NS_CHECK_CUDA(cudaMemcpy(map_d, idx.data(), (size_t)TL * sizeof(int), cudaMemcpyHostToDevice));
+          h->rowmaps.push_back(map_d);
+        }
+        float* outp = next_out(followed_by_push(pi), rows * s.c);
+        GemmOp g = bf.gemm_base(s.w, TL, Tin, 1);
+        g.T_virt = TL; g.rowmap = map_d;
+        for (int j = 0; j < 3; ++j) bf.seg(g, cur, s.c, 0, s.c, j - 1, A_RAW);
+        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        bf.emit_gemm(g, s.w);
+        cur = outp; cur_level = o.level;
+        bf.emit_tap(s.p, cur, o.level, s.c, TL);
+        break;
+      }
+    }
+  }
+  (void)cur_level; (void)cat2_c;
+  // output head: GN -> SiLU -> conv_out, stored channel-major [B, out_channels, T]
+  {
+    float* sc = fa.get<float>((size_t)B * c0); float* sh = fa.get<float>((size_t)B * c0);
+    bf.emit_gn(cur, c0, c0, nullptr, 0, 0, T, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
+    GemmOp g = bf.gemm_base(h->conv_out, T, T);
+    for (int j = 0; j < 3; ++j) bf.seg(g, cur, c0, 0, c0, j - 1, A_AFFINE_SILU, sc, sh, nullptr, 0, c0);
+    g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr; g.out_ld = 0;
+    bf.emit_gemm(g, h->conv_out, 3);
+  }
+  if (bytes_out) *bytes_out = fa.off + 256;
+  if (!dry) {
+    h->prog_cond = std::move(cond);
+    h->prog_fwd = std::move(fwd);
+    h->tap_dst.assign(h->tap_names.size(), nullptr);
+    h->pB = B; h->pT = T; h->pS = S; h->pws = ws; h->cond_ready = false;
+  }
+  return 0;
+}
+
+int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long long x_bstride, const float* t, float* out,
+                const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
+  int rc = 0, count = 0;
+  for (auto& l : prog) {
+    switch (l.kind) {
+      case Launch::GEMM: {
+        GemmOp g = l.gemm;
+        if (l.patch == 3) g.out = out;
+        if (l.patch == 5) g.seg[0].src = prompt;
+        rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
+        break;
+      }
+      case Launch::ATTN: {
+        AttnOp a = l.attn;
+        if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
+        rc = launch_attention(a, st);
+        break;
+      }
+      case Launch::GN: rc = launch_gn_affine(l.gn, st); break;
+      case Launch::LN_STATS: rc = launch_ln_stats(l.a, l.i0, l.i1, l.i2, l.f0, l.o, st); break;
+      case Launch::LN_APPLY: {
+        const float* src = (l.patch == 5) ? prompt : l.a;
+        rc = launch_ln_apply(src, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.o, l.i3, st);
+        break;
+      }
+      case Launch::LINEAR: {
+        LinOp o = l.lin;
+        if (l.patch == 2) o.x = t;
+        rc = launch_small_linear(o, st);
+        break;
+      }
+      case Launch::NCT2TOK: {
+        const float* src = (l.patch == 1) ? x : content;
+        const long long bs = (l.patch == 1) ? x_bstride : content_bstride;
+        rc = launch_nct_to_tokens(src, bs, h->pB, l.i0, l.i1, l.o, l.i2, l.i3, st);
+        break;
+      }
+      case Launch::POOL_CLS: rc = launch_pool_class_token(l.a, l.b, h->pB, l.i0, l.i1, l.o, st); break;
+      case Launch::POOL_ATT: rc = launch_pool_attend(l.a, l.b, h->pB, l.i0, l.i1, l.i2, l.o, st); break;
+      case Launch::MASKBIAS:
+        if (mask) rc = launch_mask_bias(mask, l.i0, l.o, st); else --count;
+        break;
+      case Launch::TAP:
+        --count;
+        if (l.tap_index >= 0 && l.tap_index < (int)h->tap_dst.size() && h->tap_dst[l.tap_index]) {
+          cudaError_t e = cudaMemcpyAsync(h->tap_dst[l.tap_index], l.a, (size_t)l.i0 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+          if (e != cudaSuccess) { set_error("tap copy failed: %s", cudaGetErrorString(e)); rc = -2; }
+        }
+        break;
+    }
+    if (rc) return rc;
+    ++count;
+  }
+  h->last_launches = count;
+  return 0;
+}
+
+int ensure_program(ns2vc_unet* h, int B, int T, int S, void* ws) {
+  NS_REQUIRE(h->finalized, "ns2vc_unet_finalize() has not been called");
+  NS_REQUIRE(ws != nullptr, "workspace is NULL");
+  if (h->pB == B && h->pT == T && h->pS == S && h->pws == ws) return 0;
+  return build_programs(h, B, T, S, ws, nullptr);
+}
+
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char* ns2vc_last_error(void) { return ns2vc::get_error(); }
+
+const char* ns2vc_build_info(void) { return "ns2vc_b200 sm_100a tcgen05/3xBF16 engine, built " __DATE__ " " __TIME__; }
+
+int ns2vc_down_length(int t) { return (t - 1) / 2 + 1; }
+
+int ns2vc_nearest_index(int t_in, int t_out, int* idx) {
+  // ATen nearest_idx (UpSample.h): identity if sizes match, >>1 for exact 2x, else
+  // min(int(floorf(dst * (float)in/out)), in-1) with the scale held in fp32.
+  if (t_in <= 0 || t_out <= 0 || !idx) { ns2vc::set_error("nearest_index: bad sizes %d -> %d", t_in, t_out); return -1; }
+  const float scale = (float)t_in / (float)t_out;
+  for (int i = 0; i < t_out; ++i) {
+    int s;
+    if (t_out == t_in) s = i;
+    else if (t_out == 2 * t_in) s = i >> 1;
+    else s = std::min((int)floorf((float)i * scale), t_in - 1);
+    idx[i] = s;
+  }
+  return 0;
+}
+
+int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
+  NS_REQUIRE(cfg && out, "null argument");
+  NS_REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= NS2VC_MAX_LEVELS, "n_levels %d out of range", cfg->n_levels);
+  NS_REQUIRE(cfg->latent_channels >= 1 && cfg->latent_channels <= cfg->in_channels, "latent_channels %d invalid", cfg->latent_channels);
+  for (int i = 0; i < cfg->n_levels; ++i) {
+    const int c = cfg->block_out_channels[i];
+    NS_REQUIRE(c % cfg->norm_num_groups == 0 && c % cfg->num_heads == 0 && c % 16 == 0,
+               "block width %d must be divisible by groups %d, heads %d and 16", c, cfg->norm_num_groups, cfg->num_heads);
+    NS_REQUIRE(cfg->layers_per_block[i] >= 1, "layers_per_block must be >= 1");
+  }
+  NS_REQUIRE(cfg->cross_attention_dim % 8 == 0, "cross_attention_dim must be a multiple of 8");
+  if (cfg->add_embed_text)
+    NS_REQUIRE(cfg->cross_attention_dim % cfg->add_embed_heads == 0 && cfg->cross_attention_dim / cfg->add_embed_heads <= 16,
+               "addition_embed heads %d unsupported for dim %d", cfg->add_embed_heads, cfg->cross_attention_dim);
+  ns2vc_unet* h = new ns2vc_unet();
+  h->cfg = *cfg;
+  h->ted = 4 * cfg->block_out_channels[0];
+  const char* be = getenv("NS2VC_GEMM_BACKEND");
+  h->simt = be && strcmp(be, "simt") == 0;
+  build_plan(h);
+  register_weights(h);
+  *out = h;
+  return 0;
+}
+
+void ns2vc_unet_destroy(ns2vc_unet* h) {
+  if (!h) return;
+  for (auto& w : h->weights) if (w.d) cudaFree(w.d);
+  for (void* p : h->owned) cudaFree(p);
+  for (int* p : h->rowmaps) cudaFree(p);
+  delete h;
+}
+
+int ns2vc_unet_num_weights(const ns2vc_unet* h) { return h ? (int)h->weights.size() : -1; }
+
+int ns2vc_unet_weight_info(const ns2vc_unet* h, int i, const char** name, int64_t shape[4], int* ndim) {
+  NS_REQUIRE(h && i >= 0 && i < (int)h->weights.size(), "weight index %d out of range", i);
+  const WSlot& w = h->weights[i];
+  if (name) *name = w.name.c_str();
+  if (ndim) *ndim = (int)w.shape.size();
+  if (shape) for (size_t k = 0; k < w.shape.size() && k < 4; ++k) shape[k] = w.shape[k];
+  return 0;
+}
+
+int ns2vc_unet_load_weight(ns2vc_unet* h, const char* key, const float* dptr, const int64_t* shape, int ndim, ns2vc_stream stream) {
+  NS_REQUIRE(h && key && dptr, "null argument");
+  auto it = h->windex.find(key);
+  NS_REQUIRE(it != h->windex.end(), "Unexpected key in state_dict: %s", key);
+  WSlot& w = h->weights[it->second];
+  NS_REQUIRE(ndim == (int)w.shape.size(), "size mismatch for %s: expected %d dims, got %d", key, (int)w.shape.size(), ndim);
+  for (int k = 0; k < ndim; ++k) NS_REQUIRE(shape[k] == w.shape[k], "size mismatch for %s at dim %d: expected %lld, got %lld", key, k, (long long)w.shape[k], (long long)shape[k]);
+  if (!w.d) NS_CHECK_CUDA(cudaMalloc(&w.d, w.numel() * sizeof(float)));
+  NS_CHECK_CUDA(cudaMemcpyAsync(w.d, dptr, w.numel() * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  w.loaded = true;
+  h->finalized = false;
+  return 0;
+}
+
+int ns2vc_unet_finalize(ns2vc_unet* h, ns2vc_stream stream) {
+  NS_REQUIRE(h, "null handle");
+  for (auto& w : h->weights) NS_REQUIRE(w.loaded, "Missing key in state_dict: %s", w.name.c_str());
+  // (re)pack: drop previous packed buffers
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear(); h->resnets.clear(); h->xformers.clear(); h->resamplers.clear();
+  h->pB = h->pT = h->pS = 0; h->pws = nullptr;
+  int rc = pack_all(h, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->finalized = true;
+  return 0;
+}
+
+int ns2vc_unet_workspace_bytes(const ns2vc_unet* h, int B, int T, int S, size_t* bytes) {
+  NS_REQUIRE(h && bytes, "null argument");
+  NS_REQUIRE(h->finalized, "ns2vc_unet_finalize() has not been called");
+  return build_programs(const_cast<ns2vc_unet*>(h), B, T, S, nullptr, bytes);
+}
+
+int ns2vc_unet_prepare_cond(ns2vc_unet* h, const float* content, long long content_bstride, const float* prompt, const uint8_t* mask,
+                            int B, int T, int S, void* ws, ns2vc_stream stream) {
+  NS_REQUIRE(h && prompt, "null argument");
+  int rc = ensure_program(h, B, T, S, ws);
+  if (rc) return rc;
+  const int Cc = h->cfg.in_channels - h->cfg.latent_channels;
+  NS_REQUIRE(Cc == 0 || content != nullptr, "content is NULL but the model has %d content channels", Cc);
+  h->has_mask = mask != nullptr;
+  rc = run_program(h, h->prog_cond, nullptr, 0, nullptr, nullptr, content, content_bstride, prompt, mask, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->cond_ready = true;
+  return 0;
+}
+
+int ns2vc_unet_forward(ns2vc_unet* h, const float* x, long long x_bstride, const float* t, float* out, int B, int T, int S, void* ws,
+                       ns2vc_stream stream) {
+  NS_REQUIRE(h && x && t && out, "null argument");
+  NS_REQUIRE(h->pB == B && h->pT == T && h->pS == S && h->pws == ws && h->cond_ready,
+             "ns2vc_unet_prepare_cond() must be called with the same (B,T,S,workspace) before forward");
+  return run_program(h, h->prog_fwd, x, x_bstride, t, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ns2vc_dpm_step(const float* x, const float* unet_out, const float* m_prev, const ns2vc_dpm_coef* c, float* m_cur, float* x_next,
+                   size_t n, ns2vc_stream stream) {
+  NS_REQUIRE(x && unet_out && c && m_cur, "null argument");
+  NS_REQUIRE(c->order == 0 || x_next, "x_next is NULL");
+  NS_REQUIRE(c->order < 2 || m_prev, "m_prev is NULL for a second-order step");
+  DpmStepCoef k; k.alpha_s = c->alpha_s; k.sigma_s = c->sigma_s; k.c_x = c->c_x; k.c_m = c->c_m; k.c_d = c->c_d; k.inv_r0 = c->inv_r0; k.order = c->order;
+  return launch_dpm_step(x, unet_out, m_prev, k, m_cur, x_next, n, (cudaStream_t)stream);
+}
+
+int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0, const float* m1,
+                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, ns2vc_stream stream) {
+  NS_REQUIRE(x_eval && unet_out && c && m_t, "null argument");
+  NS_REQUIRE(c->corr_order == 0 || (x_prev && m0 && x_t), "corrector inputs missing");
+  NS_REQUIRE(c->corr_order < 2 || m1, "m1 is NULL for an order-2 corrector");
+  NS_REQUIRE(c->pred_order == 0 || x_pred, "x_pred is NULL");
+  NS_REQUIRE(c->pred_order < 2 || c->corr_order > 0, "order-2 predictor needs the previous model output");
+  UniPcStepCoef k;
+  k.alpha_t = c->alpha_t; k.sigma_t = c->sigma_t; k.c_x = c->c_x; k.c_m = c->c_m; k.ab = c->ab; k.rk = c->rk; k.rho0 = c->rho0; k.rho1 = c->rho1;
+  k.corr_order = c->corr_order; k.n_c_x = c->n_c_x; k.n_c_m = c->n_c_m; k.nab = c->nab; k.nrk = c->nrk; k.pred_order = c->pred_order;
+  return launch_unipc_step(x_prev, x_eval, unet_out, m0, m1, k, m_t, x_t, x_pred, n, (cudaStream_t)stream);
+}
+
+int ns2vc_unet_num_taps(const ns2vc_unet* h) { return h ? (int)h->tap_names.size() : -1; }
+int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* level, int* channels) {
+  NS_REQUIRE(h && i >= 0 && i < (int)h->tap_names.size(), "tap index %d out of range", i);
+  if (name) *name = h->tap_names[i].c_str();
+  if (level) *level = h->tap_level[i];
+  if (channels) *channels = h->tap_ch[i];
+  return 0;
+}
+int ns2vc_unet_set_tap(ns2vc_unet* h, int i, float* dst) {
+  NS_REQUIRE(h && i >= 0 && i < (int)h->tap_dst.size(), "tap index %d out of range", i);
+  h->tap_dst[i] = dst;
+  return 0;
+}
+const char* ns2vc_unet_plan_string(const ns2vc_unet* h) { return h ? h->plan_str.c_str() : ""; }
+int ns2vc_unet_launch_count(const ns2vc_unet* h) { return h ? h->last_launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""Fused sampling loops: UNet forward (C-ABI) + one fused sampler-step kernel per step.
+
+``DenoiserSession`` is the explicit fast API (device-resident x, content, prompt):
+conditioning prepared once per utterance batch, per-step scalars precomputed on the host
+(``coefs.py``), no host synchronisation inside the loop (the reference syncs every step on
+``assert torch.isnan(x).any() == False``, model.py:404).
+
+``try_fused_dpm`` / ``try_fused_unipc`` let the drop-in ``DPM_Solver`` / ``UniPC`` classes
+take this path when the model closure they were given turns out to wrap our UNet (detected by
+tracing the first model call), so ``model.py:621-686`` benefits unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib, coefs
+from .unet import UNet1DConditionModel, trace_calls
+
+
+class DenoiserSession:
+    """One utterance batch on one GPU: UNet engine + prepared conditioning + sampler buffers."""
+
+    def __init__(self, unet: UNet1DConditionModel, content_BCT: Optional[torch.Tensor], prompt_BSC: torch.Tensor,
+                 prompt_mask: Optional[torch.Tensor], T: Optional[int] = None):
+        if not prompt_BSC.is_cuda:
+            raise RuntimeError("DenoiserSession needs CUDA tensors (no CPU path)")
+        self.unet = unet
+        self.dev = prompt_BSC.device
+        self.B, self.S = prompt_BSC.shape[0], prompt_BSC.shape[1]
+        Cc = unet.cfg.in_channels - unet.latent_channels
+        if Cc > 0:
+            if content_BCT is None or content_BCT.shape[1] != Cc:
+                raise ValueError(f"content must be [B, {Cc}, T]")
+            self.T = content_BCT.shape[2]
+            self.content = content_BCT.to(torch.float32).contiguous()
+        else:
+            if T is None:
+                raise ValueError("T is required when the model has no content channels")
+            self.T = T
+            self.content = None
+        self.prompt = prompt_BSC.to(torch.float32).contiguous()
+        self.mask = prompt_mask.to(torch.bool).to(torch.uint8).contiguous() if prompt_mask is not None else None
+        self.L = _lib.lib()
+        self.h = unet.engine(self.dev)
+        self.ws = unet.workspace(self.B, self.T, self.S, self.dev)
+        self.Cl, self.Co = unet.latent_channels, unet.cfg.out_channels
+        self._prepared = False
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def prepare(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ns2vc_unet_prepare_cond(
+                self.h, self.content.data_ptr() if self.content is not None else None,
+                (self.content.shape[1] * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
+                self.mask.data_ptr() if self.mask is not None else None, self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+        self._prepared = True
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor):
+        """x [B,Cl,T] fp32 contiguous, t [B] fp32, out [B,Co,T] fp32 — all on the session device."""
+        if not self._prepared:
+            self.prepare()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
+                                                 self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+
+    # ------------------------------------------------------------------ DPM-Solver++(2M)
+    def sample_dpmpp_2m(self, x_T: torch.Tensor, ns, ts: torch.Tensor, lower_order_final: bool = True,
+                        first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """DPM-Solver++ multistep order 2 over time points ``ts`` (N+1 values), x_start model.
+        Equivalent to reference DPM_Solver.sample(method='multistep', order=2) (dpm_solver.py:1171-1213)."""
+        assert self.Cl == self.Co, "x_start parameterisation needs out_channels == latent channels"
+        table = coefs.dpmpp_2m_table(ns, ts, lower_order_final)
+        B, dev = self.B, self.dev
+        tvals = torch.tensor([[st.t_input] * B for st in table], dtype=torch.float32).to(dev, non_blocking=True)
+        x = x_T.to(torch.float32).clone(memory_format=torch.contiguous_format)   # never write the caller's tensor
+        n = x.numel()
+        x_next = torch.empty_like(x)
+        out = torch.empty_like(x)
+        m_a, m_b = torch.empty_like(x), torch.empty_like(x)
+        if not self._prepared:
+            self.prepare()
+        stream = self._stream()
+        for k, st in enumerate(table):
+            if k == 0 and first_out is not None:
+                out.copy_(first_out)
+            else:
+                self.forward(x, tvals[k], out)
+            c = _lib.DpmCoef(st.alpha_s, st.sigma_s, st.c_x, st.c_m, st.c_d, st.inv_r0, st.order)
+            with torch.cuda.device(dev):
+                _lib.check(self.L.ns2vc_dpm_step(x.data_ptr(), out.data_ptr(), m_b.data_ptr(), C.byref(c), m_a.data_ptr(),
+                                                 x_next.data_ptr(), n, stream))
+            x, x_next = x_next, x
+            m_a, m_b = m_b, m_a
+        return x
+
+    # ------------------------------------------------------------------ UniPC-bh2
+    def sample_unipc(self, x_T: torch.Tensor, ns, ts: torch.Tensor, variant: str = "bh2",
+                     first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """UniPC multistep order 2, data prediction, lower_order_final (uni_pc.py:606-658)."""
+        assert self.Cl == self.Co
+        table = coefs.unipc_bh2_table(ns, ts, variant)
+        B, dev = self.B, self.dev
+        tvals = torch.tensor([[st.t_input] * B for st in table], dtype=torch.float32).to(dev, non_blocking=True)
+        n = x_T.numel()
+        x_prev = x_T.to(torch.float32).contiguous()      # x at the previous time point (corrector base); never written
+        x_eval = x_prev                                   # where the model is evaluated
+        out = torch.empty_like(x_prev)
+        m0 = m1 = None
+        if not self._prepared:
+            self.prepare()
+        stream = self._stream()
+        for k, st in enumerate(table):
+            if k == 0 and first_out is not None:
+                out.copy_(first_out)
+            else:
+                self.forward(x_eval, tvals[k], out)
+            # fresh outputs every step (caching allocator: no sync, stream-ordered reuse)
+            m_t = torch.empty_like(x_prev)
+            x_t = torch.empty_like(x_prev) if st.corr_order > 0 else None
+            x_pred = torch.empty_like(x_prev)
+            c = _lib.UniPcCoef(st.alpha_t, st.sigma_t, st.c_x, st.c_m, st.ab, st.rk, st.rho0, st.rho1, st.corr_order,
+                               st.n_c_x, st.n_c_m, st.nab, st.nrk, st.pred_order)
+            with torch.cuda.device(dev):
+                _lib.check(self.L.ns2vc_unipc_step(
+                    x_prev.data_ptr(), x_eval.data_ptr(), out.data_ptr(), m0.data_ptr() if m0 is not None else None,
+                    m1.data_ptr() if m1 is not None else None, C.byref(c), m_t.data_ptr(),
+                    x_t.data_ptr() if x_t is not None else None, x_pred.data_ptr(), n, stream))
+            # history m1 <- m0 <- m_t ; corrector base <- corrected x_t (x_eval itself at k = 0)
+            m1, m0 = m0, m_t
+            x_prev = x_t if x_t is not None else x_eval
+            x_eval = x_pred
+        return x_eval
+
+
+def _fast_path_enabled() -> bool:
+    return os.environ.get("NS2VC_B200_FUSED", "1") != "0"
+
+
+def _trace_first_call(solver, x: torch.Tensor, t0: torch.Tensor):
+    """Run the solver's first model evaluation through the user's closure while recording which
+    denoiser calls it makes.  Returns (record, noise) if the closure is exactly one call of our
+    UNet whose output is returned unchanged (x_start model, no guidance), else (None, noise)."""
+    wrapped = getattr(solver, "_wrapped", None)
+    from .schedule import WrappedModel
+    with trace_calls() as recs:
+        noise = solver.model(x, t0)
+    if not isinstance(wrapped, WrappedModel) or wrapped.model_type != "x_start" or wrapped.guidance_type != "uncond":
+        return None, noise
+    if len(recs) != 1:
+        return None, noise
+    r = recs[0]
+    u = r.unet
+    Cl = u.latent_channels
+    if u.cfg.out_channels != Cl or r.sample.shape[1] != u.cfg.in_channels or tuple(r.sample.shape[::2]) != tuple(x.shape[::2]):
+        return None, noise
+    if x.shape[1] != Cl or x.dtype != torch.float32:
+        return None, noise
+    if not torch.equal(r.sample[:, :Cl], x):
+        return None, noise
+    # the closure must hand back the UNet output itself: noise == (x - alpha*out)/sigma
+    ns = wrapped.noise_schedule
+    tt = t0.expand(x.shape[0])
+    a, s = ns.marginal_alpha(tt), ns.marginal_std(tt)
+    expect = (x - a[:, None, None] * r.output) / s[:, None, None]
+    if not torch.equal(expect, noise):
+        return None, noise
+    return r, noise
+
+
+def _session_from_record(r) -> DenoiserSession:
+    u = r.unet
+    Cl = u.latent_channels
+    content = r.sample[:, Cl:] if r.sample.shape[1] > Cl else None
+    return DenoiserSession(u, content, r.ehs, r.mask, T=r.sample.shape[2])
+
+
+def try_fused_dpm(solver, x, steps, skip_type, t_T, t_0):
+    if not (_fast_path_enabled() and x.is_cuda and skip_type in ("time_uniform", "time_quadratic", "logSNR")):
+        return None
+    ns = solver.noise_schedule
+    ts = solver.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device="cpu")
+    with torch.no_grad():
+        rec, _ = _trace_first_call(solver, x, ts[0].to(x.device))
+        if rec is None:
+            return None
+        sess = _session_from_record(rec)
+        return sess.sample_dpmpp_2m(x, ns, ts, lower_order_final=True, first_out=rec.output)
+
+
+def try_fused_unipc(solver, x, steps, skip_type, t_T, t_0):
+    if not (_fast_path_enabled() and x.is_cuda and skip_type in ("time_uniform", "time_quadratic", "logSNR")):
+        return None
+    ns = solver.noise_schedule
+    ts = solver.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device="cpu")
+    with torch.no_grad():
+        rec, _ = _trace_first_call(solver, x, ts[0].to(x.device))
+        if rec is None:
+            return None
+        sess = _session_from_record(rec)
+        return sess.sample_unipc(x, ns, ts, variant=solver.variant, first_out=rec.output)
