@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the NS2VC denoiser hot path (BASELINE.json metric).
+
+metric: denoiser-steps/s = B x (UNet forwards) per second over full 50-NFE DPM-Solver++(2M)
+sampling runs at [B=8, C=100, T=1024], prompt S=256 (BASELINE.json configs[1]).
+
+A bench "step" = ONE complete 50-step sampling run of one batch of 8 utterances per GPU
+(prepare_cond + 50 x (UNet forward + fused sampler step); multi-GPU: + one all-gather of the final
+latents).  `value` times device-resident inputs; `e2e` times the public API
+(ns2vc_b200.api.sample_latents) from pinned host tensors to a host result, copies inside the timed
+region.  Weak scaling over GPUs (independent utterances per rank).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+B, T, S, NFE = 8, 1024, 256, 50
+METRIC = "denoiser-steps/s"
+UNIT = "denoiser-steps/s"
+
+
+def workload_cfg(n_gpus):
+    return {"workload": f"cfg2: B={B}/GPU, C=100, T={T}, S={S}, {NFE}-step DPM-Solver++(2M) multistep time_uniform, x_start UNet1D (66.08M params)",
+            "global_batch": B * n_gpus, "nfe": NFE, "parallelism": f"utterance-shard x{n_gpus} (one all-gather of latents)" if n_gpus > 1 else "single GPU",
+            "l2_policy": "per-forward weight stream (264 MB packed bf16 hi/lo + 2.9 GB activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+def flops_per_forward(cfg, Bn, Tn, Sn, gemm_only=False):
+    """Algorithmic FLOPs of one UNet forward (SURVEY.md Appendix E work model), from the layer plan."""
+    from ns2vc_b200.arch import build_plan, level_lengths
+    Tl = level_lengths(Tn, len(cfg.block_out_channels))
+    gemm = 2 * Tn * cfg.in_channels * cfg.block_out_channels[0] * 3 + 2 * Tn * cfg.block_out_channels[0] * cfg.out_channels * 3
+    attn = 0
+    for op in build_plan(cfg):
+        t = Tl[op.level]
+        if op.kind == "resnet":
+            gemm += 2 * t * (3 * op.cin * op.cout + 3 * op.cout ** 2 + (op.cin != op.cout) * op.cin * op.cout)
+        elif op.kind == "xformer":
+            c = op.cout
+            gemm += 2 * t * c * c * (1 + 3 + 1 + 1 + 1 + 8 + 4 + 1)
+            attn += 4 * t * t * c + 4 * t * Sn * c
+        elif op.kind in ("down", "up"):
+            gemm += 2 * t * op.cout ** 2 * 3
+    return Bn * (gemm if gemm_only else gemm + attn), Bn * attn
+
+
+def read_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (recipe's clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for i, n in enumerate(names):
+                    if "Active" in r[3 + i] and "Not" not in r[3 + i]:
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_inputs(seed):
+    from ns2vc_b200.synth import make_inputs
+    inp = make_inputs(B, T, S, seed=seed)
+    return {k: (v.pin_memory() if torch.cuda.is_available() else v) for k, v in inp.items()}
+
+
+def cpu_oracle_rate(n_forwards, threads):
+    """The reference's CPU path for one denoiser call at the cfg2 shape, timed on the host cores through
+    the oracle port (bit-identical restatement of the reference's ATen call sequence)."""
+    from ns2vc_b200.arch import ns2vc_denoiser_config
+    from ns2vc_b200.synth import make_inputs, make_state_dict
+    from oracle import unet_oracle
+    torch.set_num_threads(threads)
+    cfg = ns2vc_denoiser_config()
+    sd = make_state_dict(cfg, 0)
+    inp = make_inputs(B, T, S, seed=0)
+    t = torch.full((B,), 500.0)
+    with torch.no_grad():
+        unet_oracle.denoiser_forward(sd, cfg, inp["x"], inp["content"], inp["prompt"], inp["refer_lengths"], t)   # warm-up
+        t0 = time.perf_counter()
+        for _ in range(n_forwards):
+            unet_oracle.denoiser_forward(sd, cfg, inp["x"], inp["content"], inp["prompt"], inp["refer_lengths"], t)
+        dt = time.perf_counter() - t0
+    return B * n_forwards / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = 2                                     # bounded sample: 2 of the 50 denoiser calls per "step"
+    from ns2vc_b200.arch import ns2vc_denoiser_config
+    from ns2vc_b200.synth import make_inputs, make_state_dict, linear_betas
+    from oracle import unet_oracle, sampler_oracle
+    torch.set_num_threads(threads)
+    cfg = ns2vc_denoiser_config()
+    sd = make_state_dict(cfg, 0)
+    inp = make_inputs(B, T, S, seed=0)
+    sch = sampler_oracle.OracleSchedule(linear_betas(1000))
+    fn = lambda x, tt: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], tt)
+    ts = torch.linspace(1.0, 1e-3, NFE + 1)
+
+    def step():
+        x = inp["x"]
+        with torch.no_grad():
+            for k in range(per_step):               # model call + x0 round trip, as the sampler does per NFE
+                x = sampler_oracle.x0_model(fn, sch, x, ts[k])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * per_step * args.steps / dt
+    sample = f"{per_step} of {NFE} denoiser calls (UNet forward + x0 round trip) per step at B={B},T={T},S={S}; reference CPU path via the oracle port (reference is pure PyTorch; /root/reference is absent on the GPU box)"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args.gpus),
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nfe", type=int, default=NFE, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert args.warmup >= 3, "timing rules: W >= 3"
+    import torch.distributed as dist
+    from ns2vc_b200 import _lib, api
+    from ns2vc_b200.arch import ns2vc_denoiser_config
+    from ns2vc_b200.debug import profile_forward
+    from ns2vc_b200.fused import DenoiserSession
+    from ns2vc_b200.synth import make_state_dict
+    from ns2vc_b200.unet import UNet1DConditionModel
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nfe = args.nfe
+    cfg = ns2vc_denoiser_config()
+    unet = UNet1DConditionModel(in_channels=356, out_channels=100, block_out_channels=(128, 256, 384, 512), norm_num_groups=8,
+                                cross_attention_dim=256, attention_head_dim=8, addition_embed_type="text",
+                                resnet_time_scale_shift="scale_shift")
+    unet.load_state_dict(make_state_dict(cfg, 0))
+    unet = unet.to(dev).eval()
+    hin = host_inputs(seed=1000 * rank)
+    ns = api.default_schedule()
+    ts = torch.linspace(1.0, 1e-3, nfe + 1)
+    x_d = hin["x"].to(dev)
+    content_d = hin["content"].to(dev).permute(1, 2, 0).contiguous()
+    prompt_d = hin["prompt"].to(dev).permute(1, 0, 2).contiguous()
+    mask_d = api.sequence_mask(hin["refer_lengths"].to(dev), S)
+    gathered = torch.empty((world * B, 100, T), device=dev) if world > 1 else None
+    L = _lib.lib()
+    h = unet.engine(dev)
+
+    def run_device():
+        sess = DenoiserSession(unet, content_d, prompt_d, mask_d)
+        sess.prepare()
+        out = sess.sample_dpmpp_2m(x_d, ns, ts)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+
+    def run_e2e():
+        out = api.sample_latents(unet, hin["x"], hin["content"], hin["prompt"], hin["refer_lengths"], steps=nfe, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+            return gathered.to("cpu", non_blocking=False) if rank == 0 else out[:1, :1, :1].cpu()
+        return out.cpu()
+
+    def timed(fn, K, W, sample_clocks=False):
+        for _ in range(W):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        cs = ClockSampler(local) if sample_clocks else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        clocks = cs.stop() if cs else None
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    ms, clocks = timed(run_device, args.steps, args.warmup, sample_clocks=True)
+    launches_fwd = L.ns2vc_unet_launch_count(h)
+    units = world * B * nfe * args.steps
+    value = units / (ms / 1e3)
+    ms_e2e, _ = timed(run_e2e, args.steps, 1)
+    e2e_val = units / (ms_e2e / 1e3)
+    h2d = sum(hin[k].numel() * hin[k].element_size() for k in ("x", "content", "prompt", "refer_lengths"))
+    d2h = (world if rank == 0 else 1) * B * 100 * T * 4
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xBF16-split tensor-core contractions, fp32 accumulate)",
+           "data": "synthetic", "config": workload_cfg(world), "clocks": clocks,
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": (launches_fwd + 1) * nfe * args.steps + 40 * args.steps,
+           "ms_per_unet_forward": ms / args.steps / nfe}
+
+    if rank == 0:
+        # ---- per-kernel timing of 3 forwards (CUDA events around every launch, on the launch stream)
+        sess = DenoiserSession(unet, content_d, prompt_d, mask_d)
+        sess.prepare()
+        tv = torch.full((B,), 500.0, device=dev)
+        o = torch.empty_like(x_d)
+        nprof = 3
+        prof = profile_forward(unet, lambda: [sess.forward(x_d, tv, o) for _ in range(nprof)], dev)
+        total = sum(v[0] for v in prof.values())
+        kernels = {k: {"ms_per_forward": v[0] / nprof, "launches_per_forward": v[1] // nprof, "share": v[0] / total} for k, v in prof.items()}
+        peaks = read_peaks()
+        fl_gemm, fl_attn = flops_per_forward(cfg, B, T, S, gemm_only=True)
+        dom = max(prof, key=lambda k: prof[k][0])
+        if dom == "attention":
+            ach = fl_attn / (prof[dom][0] / nprof * 1e-3) / 1e12
+            alg = f"{fl_attn / 1e9:.1f} GFLOP QK^T+PV per forward"
+        else:
+            dom = "gemm_tc"
+            ach = fl_gemm / (prof[dom][0] / nprof * 1e-3) / 1e12
+            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic; the 3xBF16 split issues 3x this on the tensor pipe)"
+        out["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                           "traffic": None, "algorithmic": alg, "peak_source": peaks["src"],
+                           "launch_avg_us": 1e3 * prof[dom][0] / prof[dom][1], "timing": f"CUDA events around each launch, {nprof} forwards, profiling pass outside the timed region"}
+        out["kernels"] = kernels
+        whole = flops_per_forward(cfg, B, T, S)[0]
+        out["step_roofline"] = {"achieved_tflops": whole / (ms / args.steps / nfe * 1e-3) / 1e12, "algorithmic_gflop_per_forward": whole / 1e9,
+                                "t_hbm_ms_ideal_fusion": 3.20e9 / (peaks["hbm_gbs"] * 1e9) * 1e3, "t_tc_ms_3xbf16": 3 * whole / (peaks["tflops"] * 1e12) * 1e3}
+        if world == 1:
+            threads = os.cpu_count() or 1
+            nf = 3
+            rate, dt = cpu_oracle_rate(nf, threads)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{nf} UNet forwards at B={B},T={T},S={S} ({dt:.1f} s) through the oracle port of the reference's CPU PyTorch path, torch threads={threads}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,14 @@ const char* ns2vc_unet_plan_string(const ns2vc_unet* h);
 int ns2vc_unet_launch_count(const ns2vc_unet* h);  /* kernels launched by the last forward */
 const char* ns2vc_build_info(void);
 
+/* Per-kernel-kind device timing (CUDA events around every launch on the caller's stream); used by
+ * bench.py for the roofline line.  Off by default; never enable inside a timed region. */
+int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
+int ns2vc_profile_num_kinds(void);
+const char* ns2vc_profile_kind_name(int kind);
+int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches);
+int ns2vc_unet_profile_reset(ns2vc_unet* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,37 @@
+"""ns2vc_b200 — B200-native (sm_100a) implementation of the NS2VC diffusion-denoiser hot path.
+
+Drop-in surface (same names as the reference):
+    ns2vc_b200.unet.UNet1DConditionModel          <- unet1d/unet_1d_condition.py
+    ns2vc_b200.dpm_solver.{NoiseScheduleVP, model_wrapper, DPM_Solver}   <- sampler/dpm_solver.py
+    ns2vc_b200.uni_pc.{NoiseScheduleVP, model_wrapper, UniPC}            <- sampler/uni_pc.py
+``ns2vc_b200.install()`` aliases those module paths so the reference's model.py / infer.py import
+them unchanged.
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+__version__ = "0.1.0"
+
+
+def install() -> None:
+    """Make ``unet1d.unet_1d_condition``, ``sampler.dpm_solver`` and ``sampler.uni_pc`` resolve to
+    the B200 implementations (call before ``import model`` in the reference tree)."""
+    from . import dpm_solver, uni_pc, unet
+
+    def pkg(name):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        return m
+
+    u = pkg("unet1d")
+    sys.modules["unet1d.unet_1d_condition"] = unet
+    u.unet_1d_condition = unet
+    s = pkg("sampler")
+    sys.modules["sampler.dpm_solver"] = dpm_solver
+    sys.modules["sampler.uni_pc"] = uni_pc
+    s.dpm_solver, s.uni_pc = dpm_solver, uni_pc

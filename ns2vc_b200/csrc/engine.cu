@@ -115,6 +115,9 @@ struct ns2vc_unet {
   std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch;
   std::vector<float*> tap_dst;
   int last_launches = 0;
+  bool profiling = false;
+  struct ProfRec { int kind; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
 
   const float* W(const std::string& n) const {
     auto it = windex.find(n);
@@ -719,6 +722,12 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
                 const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
   int rc = 0, count = 0;
   for (auto& l : prog) {
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    const bool prof = h->profiling && l.kind != Launch::TAP;
+    if (prof) {
+      cudaEventCreate(&ev_a); cudaEventCreate(&ev_b);
+      cudaEventRecord(ev_a, st);
+    }
     switch (l.kind) {
       case Launch::GEMM: {
         GemmOp g = l.gemm;
@@ -764,6 +773,10 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
           if (e != cudaSuccess) { set_error("tap copy failed: %s", cudaGetErrorString(e)); rc = -2; }
         }
         break;
+    }
+    if (prof) {
+      cudaEventRecord(ev_b, st);
+      h->prof.push_back({(int)l.kind, ev_a, ev_b});
     }
     if (rc) return rc;
     ++count;
@@ -939,6 +952,36 @@ int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* leve
 int ns2vc_unet_set_tap(ns2vc_unet* h, int i, float* dst) {
   NS_REQUIRE(h && i >= 0 && i < (int)h->tap_dst.size(), "tap index %d out of range", i);
   h->tap_dst[i] = dst;
+  return 0;
+}
+int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {
+  NS_REQUIRE(h, "null handle");
+  h->profiling = on != 0;
+  return 0;
+}
+int ns2vc_profile_num_kinds(void) { return 10; }
+const char* ns2vc_profile_kind_name(int k) {
+  static const char* names[] = {"gemm_tc", "attention", "gn_affine", "ln_stats", "ln_apply", "small_linear", "nct_to_tokens",
+                               "pool_class_token", "pool_attend", "mask_bias"};
+  return (k >= 0 && k < 10) ? names[k] : "";
+}
+int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches) {
+  NS_REQUIRE(h && ms_total && launches, "null argument");
+  double ms = 0; long long n = 0;
+  for (auto& r : h->prof) {
+    if (r.kind != kind) continue;
+    NS_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float e = 0;
+    NS_CHECK_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    ms += e; ++n;
+  }
+  *ms_total = ms; *launches = n;
+  return 0;
+}
+int ns2vc_unet_profile_reset(ns2vc_unet* h) {
+  NS_REQUIRE(h, "null handle");
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
   return 0;
 }
 const char* ns2vc_unet_plan_string(const ns2vc_unet* h) { return h ? h->plan_str.c_str() : ""; }

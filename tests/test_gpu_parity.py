@@ -1,0 +1,304 @@
+"""Parity of the CUDA path against the oracle / reference fixtures.  All tests call through the
+C-ABI (via the drop-in Python modules).  Tolerance for floating-point results is the north-star's
+rtol=1e-3 / atol=1e-4 (fp32 outputs vs the reference's CPU fp32 path); element-wise sampler kernels
+and index/mask ops are bit-exact."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from conftest import tiny_config, tiny_inputs
+from ns2vc_b200 import _lib, coefs, dpm_solver as our_dpm, uni_pc as our_upc
+from ns2vc_b200.arch import ns2vc_denoiser_config
+from ns2vc_b200.debug import forward_with_taps
+from ns2vc_b200.fused import DenoiserSession
+from ns2vc_b200.schedule import NoiseScheduleVP
+from ns2vc_b200.synth import linear_betas, make_inputs, make_state_dict
+from ns2vc_b200.unet import UNet1DConditionModel
+from oracle import sampler_oracle, unet_oracle
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs()
+    viol = (err > atol + rtol * b.abs()).float().mean().item()
+    return viol == 0.0, f"max_abs={err.max().item():.3e} violations={viol:.3%} ref_rms={b.pow(2).mean().sqrt().item():.3e}"
+
+
+def make_unet(cfg, seed=0, backend=None):
+    kw = dict(in_channels=cfg.in_channels, out_channels=cfg.out_channels, block_out_channels=cfg.block_out_channels,
+              layers_per_block=list(cfg.layers_per_block), norm_num_groups=cfg.norm_num_groups, cross_attention_dim=cfg.cross_attention_dim,
+              attention_head_dim=cfg.num_heads, addition_embed_type=cfg.addition_embed_type,
+              addition_embed_type_num_heads=cfg.addition_embed_type_num_heads, resnet_time_scale_shift=cfg.resnet_time_scale_shift)
+    m = UNet1DConditionModel(**kw)
+    sd = make_state_dict(cfg, seed)
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda").eval()
+    old = os.environ.get("NS2VC_GEMM_BACKEND")
+    if backend:
+        os.environ["NS2VC_GEMM_BACKEND"] = backend
+    else:
+        os.environ.pop("NS2VC_GEMM_BACKEND", None)
+    try:
+        m.engine(torch.device("cuda", 0))          # the backend is fixed when the engine is created
+    finally:
+        if old is None:
+            os.environ.pop("NS2VC_GEMM_BACKEND", None)
+        else:
+            os.environ["NS2VC_GEMM_BACKEND"] = old
+    return m, sd
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    return make_unet(ns2vc_denoiser_config())
+
+
+def unet_inputs(inp, dev="cuda"):
+    x = torch.cat([inp["x"], inp["content"].permute(1, 2, 0)], 1).to(dev)
+    ehs = inp["prompt"].permute(1, 0, 2).contiguous().to(dev)
+    mask = unet_oracle.sequence_mask(inp["refer_lengths"], inp["prompt"].shape[0]).to(dev)
+    return x, ehs, mask
+
+
+def test_native_library_is_the_in_tree_build():
+    assert os.path.isfile(_lib.LIB_PATH) and "ns2vc_b200/_C" in _lib.LIB_PATH
+    assert torch.cuda.get_device_capability(0)[0] == 10, "these kernels are sm_100a only"
+
+
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_tiny_forward_every_op(gold, backend):
+    """Every op output of the tiny UNet against the reference's activations: localises any defect."""
+    g = gold("tiny_forward.pt")
+    m, _ = make_unet(tiny_config(), backend=None if backend == "tc" else "simt")
+    x, ehs, mask = unet_inputs(tiny_inputs())
+    out, taps = forward_with_taps(m, x, g["t"].cuda(), ehs, mask)
+    bad = []
+    for name, ref in g["taps"].items():
+        if name in ("emb", "aug_emb"):
+            continue
+        assert name in taps, f"engine has no tap {name}"
+        ok, msg = close(taps[name], ref)
+        if not ok:
+            bad.append(f"{name}: {msg}")
+    assert not bad, "first failing ops:\n" + "\n".join(bad[:8])
+    ok, msg = close(out, g["out"])
+    assert ok, msg
+    # integer timesteps, no mask (p_sample-style call)
+    out2 = m(x, torch.tensor([999, 0], device="cuda"), ehs).sample
+    ok, msg = close(out2, g["out_nomask"])
+    assert ok, msg
+
+
+def test_full_forward_matches_reference_fixture(gold, full_model):
+    g = gold("full_forward.pt")
+    m, _ = full_model
+    x, ehs, mask = unet_inputs(make_inputs(2, 131, 48, ragged=True, seed=20))
+    with torch.no_grad():
+        out = m(x, g["t"].cuda(), ehs, encoder_attention_mask=mask).sample
+    ok, msg = close(out, g["out"])
+    assert ok, msg
+
+
+@pytest.mark.parametrize("B,T,S", [(2, 1024, 256), (1, 1000, 100), (1, 1023, 7), (3, 8, 1)])
+def test_full_forward_vs_oracle_shapes(full_model, B, T, S):
+    """config-2 sequence length, lengths that are not multiples of 8 (forced-size upsample), T=8 minimum."""
+    m, sd = full_model
+    inp = make_inputs(B, T, S, ragged=True, seed=40 + T)
+    x, ehs, mask = unet_inputs(inp)
+    t = torch.linspace(3.5, 990.25, B)
+    with torch.no_grad():
+        out = m(x, t.cuda(), ehs, encoder_attention_mask=mask).sample
+        ref = unet_oracle.denoiser_forward(sd, ns2vc_denoiser_config(), inp["x"], inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    ok, msg = close(out, ref)
+    assert ok, msg
+
+
+def test_forward_is_deterministic_and_batch_independent(full_model):
+    m, _ = full_model
+    inp = make_inputs(8, 1024, 256, seed=77)
+    x, ehs, mask = unet_inputs(inp)
+    t = torch.full((8,), 421.5, device="cuda")
+    with torch.no_grad():
+        a = m(x, t, ehs, encoder_attention_mask=mask).sample
+        b = m(x, t, ehs, encoder_attention_mask=mask).sample
+        assert torch.equal(a, b)
+        x2 = x.clone()
+        x2[0] = torch.randn_like(x2[0])
+        c = m(x2, t, ehs, encoder_attention_mask=mask).sample
+    assert torch.equal(a[1:], c[1:]), "samples of a batch must not influence each other"
+    assert not torch.equal(a[0], c[0])
+    assert torch.isfinite(a).all()
+
+
+# ------------------------------------------------------------------ sampler kernels: bit-exact
+def _rt(x, o, a, s):
+    noise = (x - a * o) / s
+    return (x - s * noise) / a
+
+
+def test_dpm_step_kernel_bit_exact():
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x, o, mp = (torch.randn(3, 100, 257, device="cuda", generator=g) for _ in range(3))
+    f = lambda v: torch.tensor(v, dtype=torch.float32, device="cuda")
+    for order in (0, 1, 2):
+        c = _lib.DpmCoef(0.37, 0.929, 0.9571, -0.0123, -0.00615, 1.0231, order)
+        mc, xn = torch.empty_like(x), torch.zeros_like(x)
+        _lib.check(L.ns2vc_dpm_step(x.data_ptr(), o.data_ptr(), mp.data_ptr(), C.byref(c), mc.data_ptr(), xn.data_ptr(), x.numel(), None))
+        torch.cuda.synchronize()
+        m0 = _rt(x, o, f(c.alpha_s), f(c.sigma_s))
+        assert torch.equal(mc, m0)
+        if order >= 1:
+            r = f(c.c_x) * x - f(c.c_m) * m0
+            if order == 2:
+                r = r - f(c.c_d) * (f(c.inv_r0) * (m0 - mp))
+            assert torch.equal(xn, r)
+
+
+def test_unipc_step_kernel_bit_exact():
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xp, xe, o, m0, m1 = (torch.randn(2, 100, 131, device="cuda", generator=g) for _ in range(5))
+    f = lambda v: torch.tensor(v, dtype=torch.float32, device="cuda")
+    for corr, pred in ((0, 1), (1, 2), (2, 2), (2, 1)):
+        c = _lib.UniPcCoef(0.41, 0.912, 0.961, -0.0131, -0.0127, -1.07, 0.4931, 0.5069, corr, 0.957, -0.0141, -0.0139, -0.97, pred)
+        mt, xt, xq = torch.empty_like(xp), torch.empty_like(xp), torch.empty_like(xp)
+        _lib.check(L.ns2vc_unipc_step(xp.data_ptr(), xe.data_ptr(), o.data_ptr(), m0.data_ptr(), m1.data_ptr(), C.byref(c),
+                                      mt.data_ptr(), xt.data_ptr(), xq.data_ptr(), xp.numel(), None))
+        torch.cuda.synchronize()
+        mt_ref = _rt(xe, o, f(c.alpha_t), f(c.sigma_t))
+        assert torch.equal(mt, mt_ref)
+        xt_ref = xe
+        if corr:
+            xbar = f(c.c_x) * xp - f(c.c_m) * m0
+            inner = f(c.rho1) * (mt_ref - m0)
+            if corr == 2:
+                inner = f(c.rho0) * ((m1 - m0) / f(c.rk)) + f(c.rho1) * (mt_ref - m0)
+            xt_ref = xbar - f(c.ab) * inner
+            assert torch.equal(xt, xt_ref)
+        nbar = f(c.n_c_x) * xt_ref - f(c.n_c_m) * mt_ref
+        if pred == 2:
+            nbar = nbar - f(c.nab) * (f(0.5) * ((m0 - mt_ref) / f(c.nrk)))
+        assert torch.equal(xq, nbar)
+
+
+# ------------------------------------------------------------------ full sampling loops
+def _session(m, inp):
+    content = inp["content"].permute(1, 2, 0).contiguous().cuda()
+    prompt = inp["prompt"].permute(1, 0, 2).contiguous().cuda()
+    mask = unet_oracle.sequence_mask(inp["refer_lengths"], inp["prompt"].shape[0]).cuda()
+    return DenoiserSession(m, content, prompt, mask)
+
+
+def test_fused_samplers_tiny_vs_reference_fixture(gold):
+    g = gold("tiny_samplers.pt")
+    m, _ = make_unet(tiny_config())
+    inp = tiny_inputs()
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 13))
+    ok, msg = close(out, g["dpmpp2m_12"])
+    assert ok, msg
+    out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 9))
+    ok, msg = close(out, g["unipc_bh2_8"])
+    assert ok, msg
+
+
+def test_fused_dpm_50_steps_full_model_vs_oracle(full_model):
+    """The metric path (50-step DPM-Solver++ 2M) end to end, small T so the CPU oracle stays fast."""
+    m, sd = full_model
+    cfg = ns2vc_denoiser_config()
+    inp = make_inputs(2, 64, 32, ragged=True, seed=3)
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 51))
+    sch = sampler_oracle.OracleSchedule(linear_betas(1000))
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    with torch.no_grad():
+        ref = sampler_oracle.dpmpp_2m(fn, sch, inp["x"], 50)
+    ok, msg = close(out, ref)
+    assert ok, msg
+
+
+def _closure(m, inp):
+    """Same call chain as NaturalSpeech2.sample_fun -> Diffusion_Encoder.forward (model.py:520, 403-415)."""
+    content, prompt, plen = inp["content"].cuda(), inp["prompt"].cuda(), inp["refer_lengths"].cuda()
+
+    def fn(x, t, **kw):
+        assert torch.isnan(x).any() == False  # noqa: E712
+        p = prompt.permute(1, 0, 2)
+        c = content.permute(1, 2, 0)
+        xin = torch.cat([x, c], dim=1)
+        mask = unet_oracle.sequence_mask(plen, p.size(1)).to(torch.bool)
+        return m(xin, t, p, encoder_attention_mask=mask).sample
+    return fn
+
+
+def test_dropin_sampler_classes_take_the_fused_path(gold, monkeypatch):
+    """model.py:621-652 / 655-686 style usage with our classes: fused path == explicit session, and the
+    generic Python path (NS2VC_B200_FUSED=0) agrees with both."""
+    g = gold("tiny_samplers.pt")
+    m, _ = make_unet(tiny_config())
+    inp = tiny_inputs()
+    betas = linear_betas(1000).cuda()
+    x0 = inp["x"].cuda()
+    with torch.no_grad():
+        ns = our_dpm.NoiseScheduleVP("discrete", betas=betas)
+        mf = our_dpm.model_wrapper(_closure(m, inp), ns, model_type="x_start", model_kwargs={})
+        fast = our_dpm.DPM_Solver(mf, ns, algorithm_type="dpmsolver++").sample(x0, steps=12, order=2, skip_type="time_uniform", method="multistep")
+        monkeypatch.setenv("NS2VC_B200_FUSED", "0")
+        slow = our_dpm.DPM_Solver(mf, ns, algorithm_type="dpmsolver++").sample(x0, steps=12, order=2, skip_type="time_uniform", method="multistep")
+        monkeypatch.delenv("NS2VC_B200_FUSED")
+    ok, msg = close(fast, g["dpmpp2m_12"])
+    assert ok, "fused: " + msg
+    ok, msg = close(slow, g["dpmpp2m_12"])
+    assert ok, "generic: " + msg
+    ok, msg = close(fast, slow, rtol=1e-4, atol=2e-5)
+    assert ok, "fused vs generic: " + msg
+    with torch.no_grad():
+        ns = our_upc.NoiseScheduleVP("discrete", betas=betas)
+        mf = our_upc.model_wrapper(_closure(m, inp), ns, model_type="x_start", model_kwargs={})
+        fast = our_upc.UniPC(mf, ns, variant="bh2").sample(x0, steps=8, order=2, skip_type="time_uniform", method="multistep")
+    ok, msg = close(fast, g["unipc_bh2_8"])
+    assert ok, "unipc fused: " + msg
+
+
+def test_p_sample_chain_through_generic_forward(gold, full_model):
+    """DDPM p_sample (model.py:535-542) with injected noise: integer timesteps through UNet.forward."""
+    g = gold("p_sample.pt")
+    m, _ = full_model
+    inp = make_inputs(1, 64, 32, seed=30)
+    fn = _closure(m, inp)
+    ddpm = sampler_oracle.OracleDDPM(1000)
+    x = inp["x"].cuda()
+    with torch.no_grad():
+        for i, t in enumerate((999, 998, 997)):
+            noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i)).cuda()
+            bt = torch.full((1,), t, dtype=torch.long, device="cuda")
+            x0 = fn(x, bt)
+            mean = ddpm.coef1.cuda()[bt][:, None, None] * x0 + ddpm.coef2.cuda()[bt][:, None, None] * x
+            x = mean + (0.5 * ddpm.log_var.cuda()[bt][:, None, None]).exp() * noise
+            ok, msg = close(x, g["xs"][i])
+            assert ok, f"step {i}: {msg}"
+
+
+def test_weights_repack_after_update(full_model):
+    """load_state_dict / optimizer-style in-place updates must reach the packed tensor-core weights."""
+    cfg = tiny_config()
+    m, sd = make_unet(cfg)
+    x, ehs, mask = unet_inputs(tiny_inputs())
+    t = torch.tensor([10.0, 20.0], device="cuda")
+    with torch.no_grad():
+        a = m(x, t, ehs, encoder_attention_mask=mask).sample
+        sd2 = make_state_dict(cfg, seed=1)
+        m.load_state_dict(sd2)
+        b = m(x, t, ehs, encoder_attention_mask=mask).sample
+    ref = unet_oracle.unet_forward(sd2, cfg, x.cpu(), t.cpu(), ehs.cpu(), mask.cpu())
+    ok, msg = close(b, ref)
+    assert ok, msg
+    assert not torch.allclose(a, b)
