@@ -118,6 +118,7 @@ int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
 int ns2vc_profile_num_kinds(void);
 const char* ns2vc_profile_kind_name(int kind);
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches);
+int ns2vc_unet_profile_dump(ns2vc_unet* h, const char* csv_path);   /* one row per launch */
 int ns2vc_unet_profile_reset(ns2vc_unet* h);
 
 #ifdef __cplusplus

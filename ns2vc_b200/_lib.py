@@ -63,6 +63,7 @@ SIGNATURES = {
     "ns2vc_profile_num_kinds": (C.c_int, []),
     "ns2vc_profile_kind_name": (C.c_char_p, [C.c_int]),
     "ns2vc_unet_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "ns2vc_unet_profile_dump": (C.c_int, [_P, C.c_char_p]),
     "ns2vc_unet_profile_reset": (C.c_int, [_P]),
 }
 

@@ -116,7 +116,7 @@ struct ns2vc_unet {
   std::vector<float*> tap_dst;
   int last_launches = 0;
   bool profiling = false;
-  struct ProfRec { int kind; cudaEvent_t a, b; };
+  struct ProfRec { int kind; cudaEvent_t a, b; int M, N, K, nseg, ctas; };
   std::vector<ProfRec> prof;
 
   const float* W(const std::string& n) const {
@@ -450,7 +450,7 @@ struct Builder {
   }
 };
 
-int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_out) {
+int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_out, cudaStream_t st = nullptr) {
   const ns2vc_unet_cfg& c = h->cfg;
   const bool dry = (ws == nullptr);
   const int nlev = c.n_levels;
@@ -529,6 +529,12 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   float* film = fa.get<float>((size_t)B * std::max(h->film_total, 1));
   double* gn_acc = fa.get<double>((size_t)B * G * 2);
   unsigned* gn_cnt = fa.get<unsigned>((size_t)B * G);
+  if (!dry) {
+    // the GroupNorm kernels keep these accumulators zero between launches; they start from
+    // whatever the caller's workspace held
+    NS_CHECK_CUDA(cudaMemsetAsync(gn_acc, 0, (size_t)B * G * 2 * sizeof(double), st));
+    NS_CHECK_CUDA(cudaMemsetAsync(gn_cnt, 0, (size_t)B * G * sizeof(unsigned), st));
+  }
   // activation buffers
   size_t max_act = 0, max_ff = 0, max_qkv = 0;
   for (auto& o : h->plan) {
@@ -776,7 +782,10 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
     }
     if (prof) {
       cudaEventRecord(ev_b, st);
-      h->prof.push_back({(int)l.kind, ev_a, ev_b});
+      ns2vc_unet::ProfRec pr{(int)l.kind, ev_a, ev_b, 0, 0, 0, 0, 0};
+      if (l.kind == Launch::GEMM) { pr.M = l.gemm.B * l.gemm.T_out; pr.N = l.gemm.n_valid; pr.K = l.gemm.nkb_total * 64; pr.nseg = l.gemm.nseg; }
+      if (l.kind == Launch::ATTN) { pr.M = l.attn.Tq; pr.N = l.attn.Tk; pr.K = l.attn.dh; }
+      h->prof.push_back(pr);
     }
     if (rc) return rc;
     ++count;
@@ -785,11 +794,11 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
   return 0;
 }
 
-int ensure_program(ns2vc_unet* h, int B, int T, int S, void* ws) {
+int ensure_program(ns2vc_unet* h, int B, int T, int S, void* ws, cudaStream_t st) {
   NS_REQUIRE(h->finalized, "ns2vc_unet_finalize() has not been called");
   NS_REQUIRE(ws != nullptr, "workspace is NULL");
   if (h->pB == B && h->pT == T && h->pS == S && h->pws == ws) return 0;
-  return build_programs(h, B, T, S, ws, nullptr);
+  return build_programs(h, B, T, S, ws, nullptr, st);
 }
 
 }  // namespace
@@ -900,7 +909,7 @@ int ns2vc_unet_workspace_bytes(const ns2vc_unet* h, int B, int T, int S, size_t*
 int ns2vc_unet_prepare_cond(ns2vc_unet* h, const float* content, long long content_bstride, const float* prompt, const uint8_t* mask,
                             int B, int T, int S, void* ws, ns2vc_stream stream) {
   NS_REQUIRE(h && prompt, "null argument");
-  int rc = ensure_program(h, B, T, S, ws);
+  int rc = ensure_program(h, B, T, S, ws, (cudaStream_t)stream);
   if (rc) return rc;
   const int Cc = h->cfg.in_channels - h->cfg.latent_channels;
   NS_REQUIRE(Cc == 0 || content != nullptr, "content is NULL but the model has %d content channels", Cc);
@@ -976,6 +985,20 @@ int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long
     ms += e; ++n;
   }
   *ms_total = ms; *launches = n;
+  return 0;
+}
+int ns2vc_unet_profile_dump(ns2vc_unet* h, const char* path) {
+  NS_REQUIRE(h && path, "null argument");
+  FILE* f = fopen(path, "w");
+  NS_REQUIRE(f, "cannot open %s", path);
+  fprintf(f, "idx,kind,us,M,N,K,nseg\n");
+  int i = 0;
+  for (auto& r : h->prof) {
+    cudaEventSynchronize(r.b);
+    float e = 0; cudaEventElapsedTime(&e, r.a, r.b);
+    fprintf(f, "%d,%s,%.2f,%d,%d,%d,%d\n", i++, ns2vc_profile_kind_name(r.kind), e * 1e3f, r.M, r.N, r.K, r.nseg);
+  }
+  fclose(f);
   return 0;
 }
 int ns2vc_unet_profile_reset(ns2vc_unet* h) {

@@ -24,15 +24,22 @@
 namespace ns2vc {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 64;
-constexpr int kStages = 3;
 constexpr int kProdWarps = 8;
 constexpr int kThreads = (kProdWarps + 2) * 32;
-constexpr int kTileBytes = BM * BK * 2;                 // 16 KB: one bf16 [128 x 64] operand tile
-constexpr int kStageBytes = 4 * kTileBytes;             // A_hi, A_lo, B_hi, B_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
-constexpr uint32_t kTmemCols = 128;
+constexpr int kATileBytes = BM * BK * 2;                // 16 KB: one bf16 [128 x 64] A tile (hi or lo)
+
+template <int BN_> struct TileCfg {
+  static constexpr int BN = BN_;
+  static constexpr int kBTileBytes = BN_ * BK * 2;      // one bf16 [BN x 64] B tile (hi or lo)
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+  static constexpr int kStages = (BN_ == 128) ? 3 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr uint32_t kTmemCols = BN_;
+  // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
+  // B=bf16 [10,13)=1, A/B K-major, N>>3 at [17,23), M>>4 at [24,29).
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -84,16 +91,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
-// B=bf16 [10,13)=1, A/B K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accum)
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -120,59 +123,50 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// Load + transform 8 consecutive channels [c0, c0+8) of one A row.  Must agree with a_fetch().
-__device__ __forceinline__ void a_load8(const GemmOp& op, const ASeg& s, int b, long long srow, int c0, float* v) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (srow < 0 || c0 >= s.nch) return;
+// ---- A-producer helpers.  One thread owns 8 consecutive channels (one 16-byte bf16 chunk) of 4 rows.
+// Must agree element-for-element with a_fetch() in gemm_common.cuh.
+struct Row8 { float v[8]; };
+
+__device__ __forceinline__ void load_raw8(const ASeg& s, long long srow, int c0, bool vec, Row8& r) {
   const float* px = s.src + srow * s.ld + s.ch0 + c0;
-  const bool full = (c0 + 8 <= s.nch);
-  const bool vec = full && (((s.ld | s.ch0) & 3) == 0);
   if (vec) {
     const float4 x0 = __ldg(reinterpret_cast<const float4*>(px));
     const float4 x1 = __ldg(reinterpret_cast<const float4*>(px) + 1);
-    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    r.v[0] = x0.x; r.v[1] = x0.y; r.v[2] = x0.z; r.v[3] = x0.w; r.v[4] = x1.x; r.v[5] = x1.y; r.v[6] = x1.z; r.v[7] = x1.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (c0 + j < s.nch) v[j] = __ldg(px + j);
-  }
-  if (s.mode == A_AFFINE || s.mode == A_AFFINE_SILU) {
-    const float* ps = s.p0 + (long long)b * s.ald + s.aoff + c0;
-    const float* pb = s.p1 + (long long)b * s.ald + s.aoff + c0;
-    float sc[8], sh[8];
-    if (full && (((s.ald | s.aoff) & 3) == 0)) {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(ps)), a1 = __ldg(reinterpret_cast<const float4*>(ps) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(pb)), b1 = __ldg(reinterpret_cast<const float4*>(pb) + 1);
-      sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
-      sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = c0 + j < s.nch;
-        sc[j] = ok ? __ldg(ps + j) : 0.f;
-        sh[j] = ok ? __ldg(pb + j) : 0.f;
-      }
-    }
-    if (s.mode == A_AFFINE_SILU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], sc[j], sh[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-    }
-  } else if (s.mode == A_LN) {
-    const float mean = __ldg(s.p0 + 2 * srow), rstd = __ldg(s.p0 + 2 * srow + 1);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c0 + j < s.nch) v[j] = (v[j] - mean) * rstd * __ldg(s.p1 + s.ch0 + c0 + j) + __ldg(s.p2 + s.ch0 + c0 + j);
-  }
-  if (!full) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (c0 + j >= s.nch) v[j] = 0.f;
+    for (int j = 0; j < 8; ++j) r.v[j] = (c0 + j < s.nch) ? __ldg(px + j) : 0.f;
   }
 }
+__device__ __forceinline__ void load_vec8(const float* p, int c0, int nch, bool vec, float* o) {
+  if (vec) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p)), a1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = a0.x; o[1] = a0.y; o[2] = a0.z; o[3] = a0.w; o[4] = a1.x; o[5] = a1.y; o[6] = a1.z; o[7] = a1.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (c0 + j < nch) ? __ldg(p + j) : 0.f;
+  }
+}
+__device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, int r, int chunk, const float* v) {
+  float h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+  uint4 hi, lo;
+  hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
+  hi.z = pack_bf16x2(h[4], h[5]); hi.w = pack_bf16x2(h[6], h[7]);
+  lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
+  lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
+  const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(a_hi + off) = hi;
+  *reinterpret_cast<uint4*>(a_lo + off) = lo;
+}
 
+template <int BN_>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
+  using Cfg = TileCfg<BN_>;
+  constexpr int BN = Cfg::BN;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kStageBytes = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // SWIZZLE_128B atoms need 1024 B alignment
@@ -199,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"(kTmemCols)
+                 "r"(Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -221,32 +215,82 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       rb[p] = rv[p] ? m / op.T_out : 0;
       rt[p] = rv[p] ? m % op.T_out : 0;
     }
+    const bool same_b = (rb[0] == rb[1]) && (rb[0] == rb[2]) && (rb[0] == rb[3]);
     int si = 0, kbl = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int stage = kb % kStages;
       const uint32_t parity = (uint32_t)((kb / kStages) & 1);
-      mbar_wait(empty_bar(stage), parity ^ 1u);
       const ASeg& s = op.seg[si];
-      uint8_t* a_hi = smem + stage * kStageBytes;
-      uint8_t* a_lo = a_hi + kTileBytes;
       const int c0 = kbl * 64 + chunk * 8;
+      const bool chan_ok = c0 < s.nch;
+      const bool full = c0 + 8 <= s.nch;
+      const bool vec = full && (((s.ld | s.ch0) & 3) == 0);
+      // ---- phase 1: issue every global load of this k-block before touching the data
+      long long srow[4];
+      Row8 x[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        srow[p] = (rv[p] && chan_ok) ? a_src_row(op, rb[p], rt[p], s.tap) : -1;
+        if (srow[p] >= 0) load_raw8(s, srow[p], c0, vec, x[p]);
+      }
+      float pa[8], pb[8];                                   // affine scale/shift or LN gamma/beta
+      float2 st[4];
+      const int mode = s.mode;
+      if (chan_ok) {
+        if (mode == A_AFFINE || mode == A_AFFINE_SILU) {
+          const bool pvec = full && (((s.ald | s.aoff) & 3) == 0);
+          load_vec8(s.p0 + (long long)rb[0] * s.ald + s.aoff + c0, c0, s.nch, pvec, pa);
+          load_vec8(s.p1 + (long long)rb[0] * s.ald + s.aoff + c0, c0, s.nch, pvec, pb);
+        } else if (mode == A_LN) {
+          const bool pvec = full && ((s.ch0 & 3) == 0);
+          load_vec8(s.p1 + s.ch0 + c0, c0, s.nch, pvec, pa);
+          load_vec8(s.p2 + s.ch0 + c0, c0, s.nch, pvec, pb);
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (srow[p] >= 0) st[p] = __ldg(reinterpret_cast<const float2*>(s.p0) + srow[p]);
+        }
+      }
+      mbar_wait(empty_bar(stage), parity ^ 1u);
+      uint8_t* a_hi = smem + stage * kStageBytes;
+      uint8_t* a_lo = a_hi + kATileBytes;
+      // ---- phase 2: transform, split, store
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int r = p * 32 + rsub;
         float v[8];
-        const long long srow = rv[p] ? a_src_row(op, rb[p], rt[p], s.tap) : -1;
-        a_load8(op, s, rb[p], srow, c0, v);
-        uint4 hi, lo;
-        float h[8];
+        if (srow[p] < 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-        hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
-        hi.z = pack_bf16x2(h[4], h[5]); hi.w = pack_bf16x2(h[6], h[7]);
-        lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
-        lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
-        const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = x[p].v[j];
+          if (mode == A_AFFINE || mode == A_AFFINE_SILU) {
+            float sc[8], sh[8];
+            if (same_b || rb[p] == rb[0]) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sc[j] = pa[j]; sh[j] = pb[j]; }
+            } else {
+              const bool pvec = full && (((s.ald | s.aoff) & 3) == 0);
+              load_vec8(s.p0 + (long long)rb[p] * s.ald + s.aoff + c0, c0, s.nch, pvec, sc);
+              load_vec8(s.p1 + (long long)rb[p] * s.ald + s.aoff + c0, c0, s.nch, pvec, sh);
+            }
+            if (mode == A_AFFINE_SILU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], sc[j], sh[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            }
+          } else if (mode == A_LN) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (v[j] - st[p].x) * st[p].y * pa[j] + pb[j];
+          }
+          if (!full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (c0 + j >= s.nch) v[j] = 0.f;
+          }
+        }
+        store_split8(a_hi, a_lo, r, chunk, v);
       }
       fence_proxy_async();                                  // generic-proxy stores -> visible to UMMA (async proxy)
       __syncwarp();
@@ -266,27 +310,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int t = mv ? (int)(m % op.T_out) : 0;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     if (op.flags & EPI_GEGLU) {
-      float val[32], gate[32];
-      tmem_ld32(trow + (uint32_t)(hh * 32), val);
-      tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
-      const int nbase = blockIdx.y * 64 + hh * 32;          // logical output column
-      if (mv) {
-        float* po = op.out + m * op.out_ld + nbase;
+      if (BN == 128) {
+        float val[32], gate[32];
+        tmem_ld32(trow + (uint32_t)(hh * 32), val);
+        tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
+        const int nbase = blockIdx.y * 64 + hh * 32;        // logical output column
+        if (mv) {
+          float* po = op.out + m * op.out_ld + nbase;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          o.x = epi_value(op, b, m, nbase + j + 0, val[j + 0], gate[j + 0]);
-          o.y = epi_value(op, b, m, nbase + j + 1, val[j + 1], gate[j + 1]);
-          o.z = epi_value(op, b, m, nbase + j + 2, val[j + 2], gate[j + 2]);
-          o.w = epi_value(op, b, m, nbase + j + 3, val[j + 3], gate[j + 3]);
-          *reinterpret_cast<float4*>(po + j) = o;
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = epi_value(op, b, m, nbase + j + 0, val[j + 0], gate[j + 0]);
+            o.y = epi_value(op, b, m, nbase + j + 1, val[j + 1], gate[j + 1]);
+            o.z = epi_value(op, b, m, nbase + j + 2, val[j + 2], gate[j + 2]);
+            o.w = epi_value(op, b, m, nbase + j + 3, val[j + 3], gate[j + 3]);
+            *reinterpret_cast<float4*>(po + j) = o;
+          }
         }
       }
     } else {
+      constexpr int kChunks = BN / 64;                      // 32-column chunks per warp
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < kChunks; ++cc) {
         float acc[32];
-        const int col = hh * 64 + cc * 32;
+        const int col = hh * (BN / 2) + cc * 32;
         tmem_ld32(trow + (uint32_t)col, acc);
         const int nbase = n0 + col;
         if (!mv || nbase >= op.n_valid) continue;
@@ -296,16 +343,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int n = nbase + j;
             if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = epi_value(op, b, m, n, acc[j], 0.f);
           }
-        } else if (nbase + 32 <= op.n_valid && ((op.out_ld & 3) == 0)) {
+        } else if (nbase + 32 <= op.n_valid && ((op.out_ld & 3) == 0) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0) &&
+                   !(op.flags & EPI_ROWBIAS)) {
           float* po = op.out + m * op.out_ld + nbase;
+          const float4* pr = (op.flags & EPI_RESIDUAL) ? reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase) : nullptr;
+          const float4* pbias = (op.flags & EPI_BIAS) ? reinterpret_cast<const float4*>(op.bias + nbase) : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = epi_value(op, b, m, nbase + j + 0, acc[j + 0], 0.f);
-            o.y = epi_value(op, b, m, nbase + j + 1, acc[j + 1], 0.f);
-            o.z = epi_value(op, b, m, nbase + j + 2, acc[j + 2], 0.f);
-            o.w = epi_value(op, b, m, nbase + j + 3, acc[j + 3], 0.f);
-            *reinterpret_cast<float4*>(po + j) = o;
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if (pbias) { const float4 bv = __ldg(pbias + j); o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w; }
+            if (pr) { const float4 rv4 = __ldg(pr + j); o.x += rv4.x; o.y += rv4.y; o.z += rv4.z; o.w += rv4.w; }
+            *reinterpret_cast<float4*>(po + 4 * j) = o;
           }
         } else {
 #pragma unroll
@@ -323,12 +371,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int stage = kb % kStages;
         const uint32_t parity = (uint32_t)((kb / kStages) & 1);
         mbar_wait(empty_bar(stage), parity ^ 1u);
-        const uint32_t b_hi = base + stage * kStageBytes + 2 * kTileBytes;
-        const uint32_t b_lo = b_hi + kTileBytes;
-        mbar_arrive_expect_tx(full_bar(stage), 2u * BN * 128u);
+        const uint32_t b_hi = base + stage * kStageBytes + 2 * kATileBytes;
+        const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
+        mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kBTileBytes);
         const size_t eoff = ((size_t)kb * op.N + n0) * 64;
-        bulk_g2s(b_hi, op.w_hi + eoff, BN * 128u, full_bar(stage));
-        bulk_g2s(b_lo, op.w_lo + eoff, BN * 128u, full_bar(stage));
+        bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
+        bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
       }
     }
   } else {
@@ -340,16 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(full_bar(stage), parity);
         tc_fence_after();
         const uint32_t a_hi = base + stage * kStageBytes;
-        const uint32_t a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = a_hi + 2 * kTileBytes;
-        const uint32_t b_lo = a_hi + 3 * kTileBytes;
+        const uint32_t a_lo = a_hi + kATileBytes;
+        const uint32_t b_hi = a_hi + 2 * kATileBytes;
+        const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
           const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
-          umma_bf16(tmem_base, dah, dbh, (kb | k) != 0 ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, 1u);
-          umma_bf16(tmem_base, dal, dbh, 1u);
+          umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
+          umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
         }
         umma_commit(empty_bar(stage));                      // frees this smem stage when the MMAs retire
       }
@@ -360,25 +408,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
-int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
+template <int BN_>
+static int launch_bn(const GemmOp& op, cudaStream_t st) {
+  using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", kSmemBytes, cudaGetErrorString(e)); return -2; }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
-  if (op.N % BN) { set_error("gemm_tc: packed N=%d is not a multiple of %d", op.N, BN); return -1; }
-  if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
   const int M = op.B * op.T_out;
-  dim3 grid(ceil_div(M, BM), op.N / BN);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(op);
+  dim3 grid(ceil_div(M, BM), op.N / BN_);
+  gemm_tc_kernel<BN_><<<grid, kThreads, Cfg::kSmemBytes, st>>>(op);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
+  if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
+  if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
+  const int M = op.B * op.T_out;
+  // N-tile: 128 wide when that already fills the 148 SMs, else 64 wide (twice the CTAs; the
+  // GEGLU epilogue pairs value|gate inside a 128-column block and needs BN = 128).
+  const int ctas128 = ceil_div(M, BM) * (op.N / 128);
+  if ((op.flags & EPI_GEGLU) || ctas128 >= 120) return launch_bn<128>(op, st);
+  return launch_bn<64>(op, st);
 }
 
 }  // namespace ns2vc

@@ -92,27 +92,38 @@ int launch_tokens_to_nct(const float* x, int ld, int B, int C, int T, float* out
 // then restores acc/counter to zero so the buffers are reusable without a memset.
 // Reference: nn.GroupNorm (biased variance) resnet.py:536,557, transformer_1d.py:134.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_affine_kernel(GnOp op, int nsplit) {
+__global__ void __launch_bounds__(128) gn_affine_kernel(GnOp op, int nsplit) {
   const int bg = blockIdx.x;
   const int b = bg / op.G, g = bg % op.G;
   const int C = op.C1 + op.C2;
   const int cpg = C / op.G;
   const int c_lo = g * cpg;
-  // T-slice of this block
+  // T-slice of this block; one row (cpg contiguous channels) per thread per iteration
   const int tper = (op.T + nsplit - 1) / nsplit;
   const int t_lo = blockIdx.y * tper;
   const int t_hi = min(op.T, t_lo + tper);
   float s = 0.f, ss = 0.f;
-  const int n = (t_hi > t_lo) ? (t_hi - t_lo) * cpg : 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int t = t_lo + i / cpg;
-    int c = c_lo + i % cpg;
-    float v = (c < op.C1) ? op.src1[((long long)b * op.T + t) * op.ld1 + c]
-                          : op.src2[((long long)b * op.T + t) * op.ld2 + (c - op.C1)];
-    s += v;
-    ss += v * v;
+  const bool vec = ((cpg | op.C1 | op.ld1 | (op.C2 ? op.ld2 : 0)) & 3) == 0;
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += blockDim.x) {
+    const float* r1 = op.src1 + ((long long)b * op.T + t) * op.ld1;
+    const float* r2 = op.C2 ? op.src2 + ((long long)b * op.T + t) * op.ld2 : nullptr;
+    if (vec) {
+#pragma unroll 4
+      for (int c = c_lo; c < c_lo + cpg; c += 4) {
+        const float4 v = (c < op.C1) ? __ldg(reinterpret_cast<const float4*>(r1 + c))
+                                     : __ldg(reinterpret_cast<const float4*>(r2 + (c - op.C1)));
+        s += (v.x + v.y) + (v.z + v.w);
+        ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      for (int c = c_lo; c < c_lo + cpg; ++c) {
+        const float v = (c < op.C1) ? r1[c] : r2[c - op.C1];
+        s += v;
+        ss += v * v;
+      }
+    }
   }
-  __shared__ double sh[2][8];
+  __shared__ double sh[2][4];
   __shared__ bool is_last;
   double ds = (double)warp_sum(s), dss = (double)warp_sum(ss);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -160,12 +171,11 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(GnOp op, int nsplit) {
 int launch_gn_affine(const GnOp& op, cudaStream_t st) {
   const int C = op.C1 + op.C2;
   if (C % op.G) { set_error("gn: %d channels not divisible by %d groups", C, op.G); return -1; }
-  const long long per_group = (long long)op.T * (C / op.G);
-  int nsplit = (int)((per_group + 8191) / 8192);
+  int nsplit = (op.T + 127) / 128;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 64) nsplit = 64;
   dim3 grid(op.B * op.G, nsplit);
-  gn_affine_kernel<<<grid, 256, 0, st>>>(op, nsplit);
+  gn_affine_kernel<<<grid, 128, 0, st>>>(op, nsplit);
   NS_LAUNCH_CHECK();
   return 0;
 }

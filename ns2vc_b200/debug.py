@@ -39,7 +39,7 @@ def forward_with_taps(unet, sample: torch.Tensor, timestep, ehs: torch.Tensor,
     return out, {k: v.permute(0, 2, 1).contiguous() for k, v in zip(names, bufs)}
 
 
-def profile_forward(unet, steps_fn, device) -> Dict[str, Tuple[float, int]]:
+def profile_forward(unet, steps_fn, device, dump_csv: Optional[str] = None) -> Dict[str, Tuple[float, int]]:
     """Run ``steps_fn()`` with per-launch CUDA-event timing on; returns {kind: (total ms, launches)}."""
     L = _lib.lib()
     h = unet.engine(device)
@@ -56,5 +56,7 @@ def profile_forward(unet, steps_fn, device) -> Dict[str, Tuple[float, int]]:
         _lib.check(L.ns2vc_unet_profile_read(h, k, C.byref(ms), C.byref(n)))
         if n.value:
             out[L.ns2vc_profile_kind_name(k).decode()] = (ms.value, n.value)
+    if dump_csv:
+        _lib.check(L.ns2vc_unet_profile_dump(h, dump_csv.encode()))
     _lib.check(L.ns2vc_unet_profile_reset(h))
     return out

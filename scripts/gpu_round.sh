@@ -1,13 +1,14 @@
 #!/usr/bin/env bash
 # One GPU-box visit: staged parity tests (separate processes so a trapped kernel cannot poison the
-# rest), smoke, short bench.  Logs land in gpurun_out/.
+# rest), smoke, short bench, ncu launch list + one full capture.  Logs land in gpurun_out/.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-600}" "$@" > "gpurun_out/$name.log" 2>&1; echo "exit $?" >> "gpurun_out/$name.log"; tail -${TAILN:-15} "gpurun_out/$name.log"; }
-run t1_simt python -m pytest tests/test_gpu_parity.py -q -k "simt or in_tree" -p no:cacheprovider
-run t2_steps python -m pytest tests/test_gpu_parity.py -q -k "kernel_bit_exact" -p no:cacheprovider
-run t3_tc python -m pytest tests/test_gpu_parity.py -q -k "tiny_forward_every_op and tc" -p no:cacheprovider
-TMO=1200 run t4_rest python -m pytest tests/test_gpu_parity.py -q -k "not tiny_forward_every_op and not kernel_bit_exact and not in_tree" -p no:cacheprovider
+run() { name=$1; shift; echo "=== $name"; timeout "${TMO:-600}" "$@" > "gpurun_out/$name.log" 2>&1; echo "exit $?" >> "gpurun_out/$name.log"; tail -${TAILN:-12} "gpurun_out/$name.log"; }
+run t1_tiny python -m pytest tests/test_gpu_parity.py -q -k "tiny_forward_every_op or in_tree or kernel_bit_exact" -p no:cacheprovider
+TMO=1200 run t2_rest python -m pytest tests/test_gpu_parity.py -q -k "not tiny_forward_every_op and not kernel_bit_exact and not in_tree" -p no:cacheprovider
 run smoke python -c "import __graft_entry__ as g; g.smoke()"
-TMO=900 run bench python bench.py --steps ${BENCH_STEPS:-1} --warmup 3
+TMO=900 TAILN=3 run bench python bench.py --steps ${BENCH_STEPS:-1} --warmup 3
+if [ "${NCU:-1}" = "1" ]; then
+  TMO=600 TAILN=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python scripts/ncu_target.py 2
+  TMO=900 TAILN=3 run ncu_full ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 100 -c 4 -f -o gpurun_out/prof_gemm python scripts/ncu_target.py 1
+fi
