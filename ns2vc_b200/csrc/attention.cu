@@ -79,9 +79,22 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnOp op) {
   }
   if (qv) {
     const float inv = 1.0f / lrun;
-    float* po = op.out + ((long long)b * op.Tq + tq) * op.out_ld + h * DH;
+    if (op.out) {
+      float* po = op.out + ((long long)b * op.Tq + tq) * op.out_ld + h * DH;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) po[d] = o[d] * inv;
+      for (int d = 0; d < DH; ++d) po[d] = o[d] * inv;
+    }
+    if (op.out_hi) {
+      __nv_bfloat16* ph = op.out_hi + ((long long)b * op.Tq + tq) * op.out_split_ld + h * DH;
+      __nv_bfloat16* pl = op.out_lo + ((long long)b * op.Tq + tq) * op.out_split_ld + h * DH;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) {
+        const float v = o[d] * inv;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        ph[d] = hi;
+        pl[d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+    }
   }
 }
 

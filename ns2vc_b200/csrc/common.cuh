@@ -37,60 +37,63 @@ const char* get_error();
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// GEMM / implicit-conv operator descriptor (shared by the tcgen05 kernel and the SIMT debug
-// kernel so both see byte-identical problem statements).
-//
-//   out[m, n] = epilogue( sum_seg sum_{c < nch} A_seg(m, c) * W[kofs_seg + c, n] )
-//
-// A_seg(m, c): m -> (b, t);  u = t*stride + tap;  zero if u outside [0, T_virt);
-//              r = rowmap ? rowmap[u] : u;  x = src[(b*T_src + r)*ld + ch0 + c];
-//              then the segment's transform (zero padding is applied AFTER the transform,
-//              as a conv pads the normalised activations: reference resnet.py:597-612).
+// "Split" activations: every GEMM A operand is stored as two bf16 tensors hi = bf16(x),
+// lo = bf16(x - hi), token-major [B, T, ld].  They are written ONCE by the op that produces or
+// normalises the activation (prep kernels below, or a GEMM/attention epilogue) and then read by
+// TMA straight into the swizzled shared-memory image the UMMA wants — for every conv tap and
+// every N tile — instead of re-running GroupNorm/SiLU in the GEMM's load path.
 // ---------------------------------------------------------------------------------------------
-enum AMode : int {
-  A_RAW = 0,          // x
-  A_AFFINE = 1,       // x * p0[b, aoff+c] + p1[b, aoff+c]              (GroupNorm folded)
-  A_AFFINE_SILU = 2,  // silu(x * p0 + p1)                              (GroupNorm[+FiLM] + SiLU)
-  A_LN = 3,           // (x - mean_m) * rstd_m * p1[c] + p2[c];  p0 = rowstats [M_src, 2]
+struct SplitBuf {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  int T;              // rows per batch entry
+  int C;              // valid channels
+  int ld;             // row pitch in elements (multiple of 8)
 };
 
-struct ASeg {
-  const float* src;   // token-major [B, T_src, ld]
-  const float* p0;
-  const float* p1;
-  const float* p2;
-  int ld;             // floats per source row
-  int ch0;            // first source channel of this segment
-  int nch;            // valid channels (k >= nch inside the segment's k-blocks reads as 0)
-  int nkb;            // number of 64-wide k-blocks this segment occupies
-  int tap;            // row offset (-1, 0, +1)
-  int mode;           // AMode
-  int aoff;           // channel offset into the affine arrays (second concat source)
-  int ald;            // row pitch of the affine arrays (floats per batch entry)
+struct alignas(128) TMap { unsigned long long v[16]; };   // CUtensorMap storage (driver-encoded)
+
+// GEMM / implicit-conv operator (shared by the tcgen05 kernel and the SIMT debug kernel):
+//
+//   out[b, t, n] = epilogue( sum_seg sum_{c < 64*nkb} A_seg[b, t + tap, c0 + c] * W[kofs_seg + c, n] )
+//
+// A_seg rows outside [0, src.T) and channels >= src.C read as zero (TMA out-of-bounds fill), which
+// is exactly a conv's zero padding of the already-normalised activations (reference resnet.py:597-612).
+// Strided (downsample) and nearest-upsample convs get their row mapping from the prep kernel, so
+// every segment here is a unit-stride window.
+constexpr int kMaxSrc = 4;
+constexpr int kMaxSeg = 8;
+
+struct GSeg {
+  int src;            // index into GemmOp::src
+  int c0;             // first channel
+  int nkb;            // 64-wide k-blocks
+  int tap;            // row offset
 };
 
 enum EpiFlags : int {
   EPI_BIAS = 1,       // + bias[n]
   EPI_RESIDUAL = 2,   // + res[m*res_ld + n]
   EPI_GEGLU = 4,      // packed N pairs 64 value | 64 gate columns: out = (v+bv) * gelu_erf(g+bg)
-  EPI_OUT_NCT = 8,    // store out[b, n, t] (channel-major, n < n_valid) instead of token-major
+  EPI_OUT_NCT = 8,    // store fp32 out[b, n, t] (channel-major, n < n_valid)
   EPI_ROWBIAS = 16,   // + rowbias[b*rowbias_ld + n]   (per-sample bias, time_embedding 'default')
+  EPI_OUT_F32 = 32,   // store fp32 token-major out[m*out_ld + n]
+  EPI_OUT_SPLIT = 64, // store bf16 hi/lo token-major (feeds the next GEMM's TMA)
 };
 
-constexpr int kMaxSeg = 8;
-
 struct GemmOp {
-  ASeg seg[kMaxSeg];
+  TMap tmap[2 * kMaxSrc];      // [2*i] = hi, [2*i+1] = lo of src[i]; box = {64 ch, 128 rows, 1}
+  SplitBuf src[kMaxSrc];
+  int nsrc;
+  GSeg seg[kMaxSeg];
   int nseg;
-  int nkb_total;      // sum of seg[i].nkb
-  int B, T_out, T_src, T_virt;
-  int stride;
-  const int* rowmap;  // nearest-upsample index table [T_virt] or nullptr
+  int nkb_total;
+  int B, T_out;
   // B operand
   const __nv_bfloat16* w_hi;   // packed [kb][Npad][64] (128B-swizzled rows)
   const __nv_bfloat16* w_lo;
   const float* w_f32;          // debug SIMT backend: [K_pad][Npad] fp32 (nullptr unless enabled)
-  int N;                       // packed output columns (multiple of 64)
+  int N;                       // packed output columns (multiple of 128)
   // epilogue
   int flags;
   const float* bias;           // [N] (GEGLU: [2*N_out] in the reference's value|gate order)
@@ -99,13 +102,18 @@ struct GemmOp {
   const float* res;
   int res_ld;
   float* out;
-  int out_ld;                  // token-major pitch, or (EPI_OUT_NCT) unused
+  int out_ld;
+  __nv_bfloat16* out_hi;       // EPI_OUT_SPLIT
+  __nv_bfloat16* out_lo;
+  int out_split_ld;
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
 };
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st);
 int launch_gemm_simt(const GemmOp& op, cudaStream_t st);
+// Encode the TMA descriptors of op.src[] into op.tmap[] (host; needs a CUDA context).
+int encode_tmaps(GemmOp& op);
 
 // Weight packing (device side, load time).  Source W is the reference parameter layout
 // [n_rows, cin_total, ktaps] fp32 (ktaps = 1 for nn.Linear / 1x1 conv).
@@ -125,6 +133,27 @@ int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, f
                   cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
+// Activation prep: (concat of up to two fp32 sources) -> [GroupNorm affine (+FiLM) (+SiLU)] -> split
+// ---------------------------------------------------------------------------------------------
+enum PrepMode : int { PREP_RAW = 0, PREP_AFFINE = 1, PREP_AFFINE_SILU = 2 };
+struct PrepOp {
+  const float* src1; int ld1; int C1;
+  const float* src2; int ld2; int C2;     // nullptr / 0 when there is no concat
+  int B, T_src, T_dst;
+  int row_mul, row_add;                   // src row = rowmap ? rowmap[t] : t*row_mul + row_add
+  const int* rowmap;                      // nearest-upsample index table [T_dst] or nullptr
+  int mode;
+  const float* scale; const float* shift; // [B, C1+C2]
+  SplitBuf out;                           // transformed
+  SplitBuf raw;                           // optional second output without the transform (hi == nullptr: none)
+};
+int launch_prep_split(const PrepOp& op, cudaStream_t st);
+
+// LayerNorm + split in one pass (one warp per row): out = ((x-mean)*rstd*gamma + beta) as bf16 hi/lo
+int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta,
+                    SplitBuf out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
 // Attention
 // ---------------------------------------------------------------------------------------------
 struct AttnOp {
@@ -132,7 +161,10 @@ struct AttnOp {
   const float* k; int k_ld;       // [B, Tk, k_ld]
   const float* v; int v_ld;
   const float* bias;              // additive [B, Tk] or nullptr      (reference: 0 / -10000)
-  float* out; int out_ld;         // [B, Tq, out_ld]
+  float* out; int out_ld;         // [B, Tq, out_ld] fp32 (may be nullptr when out_hi is set)
+  __nv_bfloat16* out_hi;          // optional split output (feeds the out-projection GEMM)
+  __nv_bfloat16* out_lo;
+  int out_split_ld;
   int B, H, Tq, Tk, dh;
   float scale;                    // dh^-0.5
 };
@@ -163,6 +195,8 @@ int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float
 // [B, C, T] (batch stride bstride) -> token-major [B, T, ldo] (channels >= C zero-filled up to Cpad)
 int launch_nct_to_tokens(const float* x, long long bstride, int B, int C, int T, float* out, int ldo, int Cpad,
                          cudaStream_t st);
+// [B, C, T] fp32 -> split token-major [B, T, out.ld] (channels >= C zero-filled up to out.ld)
+int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st);
 // token-major [B, T, ld] -> [B, C, T]
 int launch_tokens_to_nct(const float* x, int ld, int B, int C, int T, float* out, cudaStream_t st);
 

@@ -63,16 +63,17 @@ struct ConvSite { std::string p; int c; PackedB w; };
 
 // One launch of the per-shape program.
 struct Launch {
-  enum Kind { GEMM, ATTN, GN, LN_STATS, LN_APPLY, LINEAR, NCT2TOK, POOL_CLS, POOL_ATT, MASKBIAS, TAP } kind;
+  enum Kind { GEMM, ATTN, GN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, TAP } kind;
   GemmOp gemm;
   AttnOp attn;
   GnOp gn;
   LinOp lin;
+  PrepOp prep;
+  SplitBuf split;
   // generic small args
   const float* a = nullptr; const float* b = nullptr; const float* c = nullptr; float* o = nullptr;
-  const uint8_t* mask = nullptr;
-  int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0; float f0 = 0; long long ll0 = 0;
-  int patch = 0;             // 1: a<-x (forward), 2: lin.x<-t, 3: gemm.out<-out, 4: a<-content, 5: gemm seg0 src<-prompt / a<-prompt, 6: mask
+  int i0 = 0, i1 = 0, i2 = 0, i3 = 0; float f0 = 0;
+  int patch = 0;             // 1: x (forward)  2: t  3: out  4: content  5: prompt  6: mask
   int tap_index = -1;
 };
 
@@ -308,20 +309,16 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) {
       ResnetSite s; s.p = o.prefix; s.c1 = o.c1; s.c2 = o.c2; s.cin = o.cin; s.cout = o.cout; s.shortcut = o.cin != o.cout;
-      const int n1 = nkb_of(s.c1), n2 = s.c2 ? nkb_of(s.c2) : 0, no = nkb_of(s.cout);
-      if ((rc = alloc_packed(h, s.conv1, s.cout, s.cout, 3 * (n1 + n2)))) return rc;
-      for (int j = 0; j < 3; ++j) {
-        if ((rc = pack_seg(h, s.conv1, s.p + ".conv1.weight", s.cout, s.cin, 3, j, 0, s.c1, 0, j * (n1 + n2), 0, st))) return rc;
-        if (s.c2 && (rc = pack_seg(h, s.conv1, s.p + ".conv1.weight", s.cout, s.cin, 3, j, s.c1, s.c2, 0, j * (n1 + n2) + n1, 0, st))) return rc;
-      }
-      const int nsc = s.shortcut ? (n1 + n2) : 0;
+      const int ni = nkb_of(s.cin), no = nkb_of(s.cout);
+      if ((rc = alloc_packed(h, s.conv1, s.cout, s.cout, 3 * ni))) return rc;
+      for (int j = 0; j < 3; ++j)
+        if ((rc = pack_seg(h, s.conv1, s.p + ".conv1.weight", s.cout, s.cin, 3, j, 0, s.cin, 0, j * ni, 0, st))) return rc;
+      const int nsc = s.shortcut ? ni : 0;
       if ((rc = alloc_packed(h, s.conv2, s.cout, s.cout, 3 * no + nsc))) return rc;
       for (int j = 0; j < 3; ++j)
         if ((rc = pack_seg(h, s.conv2, s.p + ".conv2.weight", s.cout, s.cout, 3, j, 0, s.cout, 0, j * no, 0, st))) return rc;
-      if (s.shortcut) {
-        if ((rc = pack_seg(h, s.conv2, s.p + ".conv_shortcut.weight", s.cout, s.cin, 1, 0, 0, s.c1, 0, 3 * no, 0, st))) return rc;
-        if (s.c2 && (rc = pack_seg(h, s.conv2, s.p + ".conv_shortcut.weight", s.cout, s.cin, 1, 0, s.c1, s.c2, 0, 3 * no + n1, 0, st))) return rc;
-      }
+      if (s.shortcut)
+        if ((rc = pack_seg(h, s.conv2, s.p + ".conv_shortcut.weight", s.cout, s.cin, 1, 0, 0, s.cin, 0, 3 * no, 0, st))) return rc;
       if (dev_alloc(h, &s.bias2, s.cout, false)) return -2;
       add_vec_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(h->W(s.p + ".conv2.bias"), s.shortcut ? h->W(s.p + ".conv_shortcut.bias") : nullptr, s.bias2, s.cout);
       s.film_off = film_off;
@@ -412,23 +409,41 @@ struct Builder {
   std::vector<Launch>* out;
   bool dry;
   bool taps = false;
+  int err = 0;
 
-  void seg(GemmOp& g, const float* src, int ld, int ch0, int nch, int tap, int mode, const float* p0 = nullptr,
-           const float* p1 = nullptr, const float* p2 = nullptr, int aoff = 0, int ald = 0) {
-    ASeg& s = g.seg[g.nseg++];
-    s.src = src; s.ld = ld; s.ch0 = ch0; s.nch = nch; s.nkb = nkb_of(nch); s.tap = tap; s.mode = mode;
-    s.p0 = p0; s.p1 = p1; s.p2 = p2; s.aoff = aoff; s.ald = ald;
-    g.nkb_total += s.nkb;
+  SplitBuf split(int Tn, int C) {
+    SplitBuf s; s.T = Tn; s.C = C; s.ld = pad_to(C, 8);
+    s.hi = ar.get<__nv_bfloat16>((size_t)B * Tn * s.ld);
+    s.lo = ar.get<__nv_bfloat16>((size_t)B * Tn * s.ld);
+    return s;
   }
-  GemmOp gemm_base(const PackedB& w, int T_out, int T_src, int stride = 1) {
+  // view of a (larger) scratch split as [B, Tn, C]
+  static SplitBuf view(const SplitBuf& base, int Tn, int C) {
+    SplitBuf s = base; s.T = Tn; s.C = C; s.ld = pad_to(C, 8); return s;
+  }
+  GemmOp gemm_base(const PackedB& w, int T_out) {
     GemmOp g; memset(&g, 0, sizeof(g));
-    g.B = B; g.T_out = T_out; g.T_src = T_src; g.T_virt = T_src; g.stride = stride;
+    g.B = B; g.T_out = T_out;
     g.w_hi = w.hi; g.w_lo = w.lo; g.w_f32 = w.f32; g.N = w.Npad; g.n_valid = w.n_logical;
     return g;
   }
+  int add_src(GemmOp& g, const SplitBuf& s) { g.src[g.nsrc] = s; return g.nsrc++; }
+  void seg(GemmOp& g, int src, int c0, int nch, int tap) {
+    GSeg& s = g.seg[g.nseg++];
+    s.src = src; s.c0 = c0; s.nkb = nkb_of(nch); s.tap = tap;
+    g.nkb_total += s.nkb;
+  }
+  void conv3(GemmOp& g, const SplitBuf& s) {           // k=3, stride 1, pad 1 over one split source
+    const int i = add_src(g, s);
+    for (int j = 0; j < 3; ++j) seg(g, i, 0, s.C, j - 1);
+  }
   void emit_gemm(GemmOp& g, const PackedB& w, int patch = 0) {
-    Launch l; l.kind = Launch::GEMM; l.gemm = g; l.patch = patch;
-    if (!dry && g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
+    Launch l; l.kind = Launch::GEMM; l.patch = patch;
+    if (!dry) {
+      if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
+      if (!h->simt) { int rc = encode_tmaps(g); if (rc) err = rc; }
+    }
+    l.gemm = g;
     out->push_back(l);
   }
   void emit_gn(const float* s1, int ld1, int C1, const float* s2, int ld2, int C2, int Tl, float eps, const float* gamma,
@@ -439,8 +454,19 @@ struct Builder {
     g.scale = scale; g.shift = shift; g.acc = acc; g.counter = cnt;
     out->push_back(l);
   }
-  void emit_ln_stats(const float* x, int ld, int M, int C, float* stats) {
-    Launch l; l.kind = Launch::LN_STATS; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.o = stats; out->push_back(l);
+  void emit_prep(const float* s1, int C1, const float* s2, int C2, int T_src, int T_dst, int mode, const float* scale,
+                 const float* shift, const SplitBuf& o, const SplitBuf* raw = nullptr, int row_mul = 1, int row_add = 0,
+                 const int* rowmap = nullptr, int patch = 0) {
+    Launch l; l.kind = Launch::PREP; l.patch = patch;
+    PrepOp& p = l.prep; memset(&p, 0, sizeof(p));
+    p.src1 = s1; p.ld1 = C1; p.C1 = C1; p.src2 = s2; p.ld2 = C2; p.C2 = C2; p.B = B; p.T_src = T_src; p.T_dst = T_dst;
+    p.row_mul = row_mul; p.row_add = row_add; p.rowmap = rowmap; p.mode = mode; p.scale = scale; p.shift = shift; p.out = o;
+    if (raw) p.raw = *raw;
+    out->push_back(l);
+  }
+  void emit_ln_split(const float* x, int ld, int M, int C, const float* gamma, const float* beta, const SplitBuf& o) {
+    Launch l; l.kind = Launch::LN_SPLIT; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.b = gamma; l.c = beta; l.split = o;
+    out->push_back(l);
   }
   void emit_tap(const std::string& name, const float* src, int level, int C, int Tl) {
     if (!dry && taps) {
@@ -457,7 +483,6 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   const int G = c.norm_num_groups;
   const int c0 = c.block_out_channels[0];
   const int Cl = c.latent_channels, Cc = c.in_channels - Cl;
-  const int Clp = pad_to(Cl, 8);
   const int xd = c.cross_attention_dim, ted = h->ted;
   std::vector<int> Tl(nlev);
   for (int l = 0; l < nlev; ++l) Tl[l] = level_len(T, l);
@@ -469,8 +494,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     h->rowmaps.clear();
     h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear();
   }
-  Builder bc{h, Arena{(uint8_t*)ws, 0}, B, T, S, &cond, dry};
-  Arena& ar = bc.ar;
+  Builder bld{h, Arena{(uint8_t*)ws, 0}, B, T, S, &cond, dry};
+  Arena& ar = bld.ar;
 
   // ---- persistent conditioning buffers
   float* P = (Cc > 0) ? ar.get<float>((size_t)B * T * c0) : nullptr;      // conv_in(content) + bias
@@ -478,7 +503,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   float* maskbias = ar.get<float>((size_t)B * S);
   float* aug = ar.get<float>((size_t)B * ted);
   // ---- conditioning scratch
-  float* ctok = (Cc > 0) ? ar.get<float>((size_t)B * T * Cc) : nullptr;
+  SplitBuf s_content = (Cc > 0) ? bld.split(T, Cc) : SplitBuf{};
+  SplitBuf s_prompt = bld.split(S, xd);
   float* pn = ar.get<float>((size_t)B * S * xd);
   float* ptok = ar.get<float>((size_t)B * (S + 1) * xd);
   float* pq = ar.get<float>((size_t)B * xd);
@@ -488,18 +514,20 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 
   // ================= conditioning program =================
   if (Cc > 0) {
-    Launch l; l.kind = Launch::NCT2TOK; l.patch = 4; l.i0 = Cc; l.i1 = T; l.o = ctok; l.i2 = Cc; l.i3 = Cc; cond.push_back(l);
-    GemmOp g = bc.gemm_base(h->convin_content, T, T);
-    for (int j = 0; j < 3; ++j) bc.seg(g, ctok, Cc, 0, Cc, j - 1, A_RAW);
-    g.flags = EPI_BIAS; g.bias = h->W("conv_in.bias"); g.out = P; g.out_ld = c0;
-    bc.emit_gemm(g, h->convin_content);
+    { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 4; l.i0 = Cc; l.i1 = T; l.split = s_content; cond.push_back(l); }
+    GemmOp g = bld.gemm_base(h->convin_content, T);
+    bld.conv3(g, s_content);
+    g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W("conv_in.bias"); g.out = P; g.out_ld = c0;
+    bld.emit_gemm(g, h->convin_content);
   }
   { Launch l; l.kind = Launch::MASKBIAS; l.patch = 6; l.i0 = B * S; l.o = maskbias; cond.push_back(l); }
   if (h->kv_total > 0) {
-    GemmOp g = bc.gemm_base(h->kv_all, S, S);
-    bc.seg(g, nullptr, xd, 0, xd, 0, A_RAW);
-    g.out = kvc; g.out_ld = h->kv_total;
-    bc.emit_gemm(g, h->kv_all, 5);
+    bld.emit_prep(nullptr, xd, nullptr, 0, S, S, PREP_RAW, nullptr, nullptr, s_prompt, nullptr, 1, 0, nullptr, 5);
+    GemmOp g = bld.gemm_base(h->kv_all, S);
+    const int i = bld.add_src(g, s_prompt);
+    bld.seg(g, i, 0, xd, 0);
+    g.flags = EPI_OUT_F32; g.out = kvc; g.out_ld = h->kv_total;
+    bld.emit_gemm(g, h->kv_all);
   }
   if (c.add_embed_text) {
     // TextTimeEmbedding (embeddings.py:421-434): LN -> AttentionPooling -> Linear -> LN
@@ -519,16 +547,15 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   }
 
   // ================= forward program =================
-  Builder bf{h, ar, B, T, S, &fwd, dry};
-  bf.taps = true;
-  Arena& fa = bf.ar;
+  bld.out = &fwd;
+  bld.taps = true;
   // per-step small buffers
-  float* xtok = fa.get<float>((size_t)B * T * Clp);
-  float* temb1 = fa.get<float>((size_t)B * ted);
-  float* emb = fa.get<float>((size_t)B * ted);
-  float* film = fa.get<float>((size_t)B * std::max(h->film_total, 1));
-  double* gn_acc = fa.get<double>((size_t)B * G * 2);
-  unsigned* gn_cnt = fa.get<unsigned>((size_t)B * G);
+  SplitBuf s_xin = bld.split(T, Cl);
+  float* temb1 = ar.get<float>((size_t)B * ted);
+  float* emb = ar.get<float>((size_t)B * ted);
+  float* film = ar.get<float>((size_t)B * std::max(h->film_total, 1));
+  double* gn_acc = ar.get<double>((size_t)B * G * 2);
+  unsigned* gn_cnt = ar.get<unsigned>((size_t)B * G);
   if (!dry) {
     // the GroupNorm kernels keep these accumulators zero between launches; they start from
     // whatever the caller's workspace held
@@ -536,23 +563,29 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     NS_CHECK_CUDA(cudaMemsetAsync(gn_cnt, 0, (size_t)B * G * sizeof(unsigned), st));
   }
   // activation buffers
-  size_t max_act = 0, max_ff = 0, max_qkv = 0;
+  size_t max_act = (size_t)B * T * c0, max_cat = 0, max_ff = 1, max_qkv = 1;
   for (auto& o : h->plan) {
     const size_t rows = (size_t)B * Tl[o.level];
-    if (o.kind == PlanOp::RESNET || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) max_act = std::max(max_act, rows * o.cout);
+    if (o.kind == PlanOp::RESNET) { max_act = std::max(max_act, rows * o.cout); max_cat = std::max(max_cat, rows * o.cin); }
+    if (o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) { max_act = std::max(max_act, rows * o.cout); max_cat = std::max(max_cat, rows * o.cout); }
     if (o.kind == PlanOp::XFORMER) { max_act = std::max(max_act, rows * o.cout); max_ff = std::max(max_ff, rows * 4 * o.cout); max_qkv = std::max(max_qkv, rows * 3 * o.cout); }
   }
-  max_act = std::max(max_act, (size_t)B * T * c0);
-  float* rot[3]; for (int i = 0; i < 3; ++i) rot[i] = fa.get<float>(max_act);
-  float* H1 = fa.get<float>(max_act);
-  float* T0 = fa.get<float>(max_act);
-  float* T1 = fa.get<float>(max_act);
-  float* ATT = fa.get<float>(max_act);
-  float* QKV = fa.get<float>(std::max<size_t>(max_qkv, 1));
-  float* FF = fa.get<float>(std::max<size_t>(max_ff, 1));
+  max_cat = std::max(max_cat, max_act);
+  float* rot[3]; for (int i = 0; i < 3; ++i) rot[i] = ar.get<float>(max_act);
+  float* H1 = ar.get<float>(max_act);
+  float* T0 = ar.get<float>(max_act);
+  float* T1 = ar.get<float>(max_act);
+  float* QKV = ar.get<float>(max_qkv);
+  auto scratch_split = [&](size_t elems) { SplitBuf s{}; s.hi = ar.get<__nv_bfloat16>(elems); s.lo = ar.get<__nv_bfloat16>(elems); return s; };
+  const SplitBuf SP_A = scratch_split(max_cat);      // conv1 / resample input
+  const SplitBuf SP_R = scratch_split(max_cat);      // raw shortcut operand / odd rows of a stride-2 conv
+  const SplitBuf SP_H = scratch_split(max_act);      // conv2 input, ff2 output, out-head input
+  const SplitBuf SP_X = scratch_split(max_act);      // GN / LN normalised transformer activations
+  const SplitBuf SP_ATT = scratch_split(max_act);    // attention output
+  const SplitBuf SP_FF = scratch_split(max_ff);      // GEGLU output
 
-  // entry: x -> tokens, time path, conv_in
-  { Launch l; l.kind = Launch::NCT2TOK; l.patch = 1; l.i0 = Cl; l.i1 = T; l.o = xtok; l.i2 = Clp; l.i3 = Clp; fwd.push_back(l); }
+  // entry: x -> split tokens, time path, conv_in
+  { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 1; l.i0 = Cl; l.i1 = T; l.split = s_xin; fwd.push_back(l); }
   { Launch l; l.kind = Launch::LINEAR; l.patch = 2; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = nullptr; o.x_ld = 1; o.M = B; o.K = c0; o.W = h->W("time_embedding.linear_1.weight"); o.bias = h->W("time_embedding.linear_1.bias");
     o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; fwd.push_back(l); }
@@ -567,26 +600,25 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   std::vector<std::pair<float*, int>> skips;   // (ptr, channels)
   int rot_i = 0;
   auto next_out = [&](bool is_skip, size_t elems) -> float* {
-    if (is_skip) return fa.get<float>(elems);
+    if (is_skip) return ar.get<float>(elems);
     float* p = rot[rot_i]; rot_i = (rot_i + 1) % 3; return p;
   };
-  // is the op at plan index i followed (before the next compute op) by a PUSH?
   auto followed_by_push = [&](size_t i) { return i + 1 < h->plan.size() && h->plan[i + 1].kind == PlanOp::PUSH; };
 
-  float* cur = nullptr; int cur_c = c0, cur_level = 0;
+  float* cur = nullptr; int cur_c = c0;
   {
-    // conv_in output is the first skip
-    float* o = next_out(true, (size_t)B * T * c0);
-    GemmOp g = bf.gemm_base(h->convin_lat, T, T);
-    for (int j = 0; j < 3; ++j) bf.seg(g, xtok, Clp, 0, Clp, j - 1, A_RAW);
-    if (Cc > 0) { g.flags = EPI_RESIDUAL; g.res = P; g.res_ld = c0; }
-    else { g.flags = EPI_BIAS; g.bias = h->W("conv_in.bias"); }
+    float* o = next_out(true, (size_t)B * T * c0);      // conv_in output is the first skip
+    GemmOp g = bld.gemm_base(h->convin_lat, T);
+    bld.conv3(g, s_xin);
+    g.flags = EPI_OUT_F32;
+    if (Cc > 0) { g.flags |= EPI_RESIDUAL; g.res = P; g.res_ld = c0; }
+    else { g.flags |= EPI_BIAS; g.bias = h->W("conv_in.bias"); }
     g.out = o; g.out_ld = c0;
-    bf.emit_gemm(g, h->convin_lat);
+    bld.emit_gemm(g, h->convin_lat);
     cur = o;
-    bf.emit_tap("conv_in", cur, 0, c0, T);
+    bld.emit_tap("conv_in", cur, 0, c0, T);
   }
-  const float* cat2 = nullptr; int cat2_c = 0;    // pending concat source
+  const float* cat2 = nullptr;                    // pending concat source
   size_t ri = 0, xi = 0, si = 0;
   for (size_t pi = 0; pi < h->plan.size(); ++pi) {
     const PlanOp& o = h->plan[pi];
@@ -594,91 +626,93 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     const size_t rows = (size_t)B * TL;
     switch (o.kind) {
       case PlanOp::PUSH: skips.push_back({cur, cur_c}); break;
-      case PlanOp::POP_CAT: cat2 = skips.back().first; cat2_c = skips.back().second; skips.pop_back(); break;
+      case PlanOp::POP_CAT: cat2 = skips.back().first; skips.pop_back(); break;
       case PlanOp::RESNET: {
         const ResnetSite& s = h->resnets[ri++];
         const float* s1 = cur; const float* s2 = s.c2 ? cat2 : nullptr;
-        float* sc1 = fa.get<float>((size_t)B * s.cin); float* sh1 = fa.get<float>((size_t)B * s.cin);
-        float* sc2 = fa.get<float>((size_t)B * s.cout); float* sh2 = fa.get<float>((size_t)B * s.cout);
-        bf.emit_gn(s1, s.c1, s.c1, s2, s.c2, s.c2, TL, c.norm_eps, h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, sc1, sh1, gn_acc, gn_cnt);
+        float* sc1 = ar.get<float>((size_t)B * s.cin); float* sh1 = ar.get<float>((size_t)B * s.cin);
+        float* sc2 = ar.get<float>((size_t)B * s.cout); float* sh2 = ar.get<float>((size_t)B * s.cout);
+        const SplitBuf a_in = Builder::view(SP_A, TL, s.cin), a_raw = Builder::view(SP_R, TL, s.cin), a_h = Builder::view(SP_H, TL, s.cout);
+        bld.emit_gn(s1, s.c1, s.c1, s2, s.c2, s.c2, TL, c.norm_eps, h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, sc1, sh1, gn_acc, gn_cnt);
+        bld.emit_prep(s1, s.c1, s2, s.c2, TL, TL, PREP_AFFINE_SILU, sc1, sh1, a_in, s.shortcut ? &a_raw : nullptr);
         {
-          GemmOp g = bf.gemm_base(s.conv1, TL, TL);
-          for (int j = 0; j < 3; ++j) {
-            bf.seg(g, s1, s.c1, 0, s.c1, j - 1, A_AFFINE_SILU, sc1, sh1, nullptr, 0, s.cin);
-            if (s.c2) bf.seg(g, s2, s.c2, 0, s.c2, j - 1, A_AFFINE_SILU, sc1, sh1, nullptr, s.c1, s.cin);
-          }
-          g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv1.bias");
+          GemmOp g = bld.gemm_base(s.conv1, TL);
+          bld.conv3(g, a_in);
+          g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv1.bias");
           if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
           g.out = H1; g.out_ld = s.cout;
-          bf.emit_gemm(g, s.conv1);
+          bld.emit_gemm(g, s.conv1);
         }
-        bf.emit_gn(H1, s.cout, s.cout, nullptr, 0, 0, TL, c.norm_eps, h->W(s.p + ".norm2.weight"), h->W(s.p + ".norm2.bias"),
-                   c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, sc2, sh2, gn_acc, gn_cnt);
+        bld.emit_gn(H1, s.cout, s.cout, nullptr, 0, 0, TL, c.norm_eps, h->W(s.p + ".norm2.weight"), h->W(s.p + ".norm2.bias"),
+                    c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, sc2, sh2, gn_acc, gn_cnt);
+        bld.emit_prep(H1, s.cout, nullptr, 0, TL, TL, PREP_AFFINE_SILU, sc2, sh2, a_h);
         float* outp = next_out(followed_by_push(pi), rows * s.cout);
         {
-          GemmOp g = bf.gemm_base(s.conv2, TL, TL);
-          for (int j = 0; j < 3; ++j) bf.seg(g, H1, s.cout, 0, s.cout, j - 1, A_AFFINE_SILU, sc2, sh2, nullptr, 0, s.cout);
-          g.flags = EPI_BIAS; g.bias = s.bias2;
-          if (s.shortcut) {
-            bf.seg(g, s1, s.c1, 0, s.c1, 0, A_RAW);
-            if (s.c2) bf.seg(g, s2, s.c2, 0, s.c2, 0, A_RAW);
-          } else {
-            g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1;
-          }
+          GemmOp g = bld.gemm_base(s.conv2, TL);
+          bld.conv3(g, a_h);
+          g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = s.bias2;
+          if (s.shortcut) { const int i = bld.add_src(g, a_raw); bld.seg(g, i, 0, s.cin, 0); }
+          else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
           g.out = outp; g.out_ld = s.cout;
-          bf.emit_gemm(g, s.conv2);
+          bld.emit_gemm(g, s.conv2);
         }
-        cur = outp; cur_c = s.cout; cur_level = o.level; cat2 = nullptr; cat2_c = 0;
-        bf.emit_tap(s.p, cur, o.level, cur_c, TL);
+        cur = outp; cur_c = s.cout; cat2 = nullptr;
+        bld.emit_tap(s.p, cur, o.level, cur_c, TL);
         break;
       }
       case PlanOp::XFORMER: {
         const XformerSite& x = h->xformers[xi++];
         const int C = x.c, H = c.num_heads, dh = C / H;
         const std::string b = x.p + ".transformer_blocks.0";
-        float* sc = fa.get<float>((size_t)B * C); float* sh = fa.get<float>((size_t)B * C);
-        float* rs1 = fa.get<float>(rows * 2); float* rs2 = fa.get<float>(rows * 2); float* rs3 = fa.get<float>(rows * 2);
-        bf.emit_gn(cur, C, C, nullptr, 0, 0, TL, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
-        { GemmOp g = bf.gemm_base(x.proj_in, TL, TL); bf.seg(g, cur, C, 0, C, 0, A_AFFINE, sc, sh, nullptr, 0, C);
-          g.flags = EPI_BIAS; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bf.emit_gemm(g, x.proj_in); }
-        bf.emit_ln_stats(T0, C, (int)rows, C, rs1);
-        { GemmOp g = bf.gemm_base(x.qkv, TL, TL); bf.seg(g, T0, C, 0, C, 0, A_LN, rs1, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"));
-          g.out = QKV; g.out_ld = 3 * C; bf.emit_gemm(g, x.qkv); }
+        float* sc = ar.get<float>((size_t)B * C); float* sh = ar.get<float>((size_t)B * C);
+        const SplitBuf sx = Builder::view(SP_X, TL, C), satt = Builder::view(SP_ATT, TL, C), sff = Builder::view(SP_FF, TL, 4 * C),
+                       sh2 = Builder::view(SP_H, TL, C);
+        auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
+        bld.emit_gn(cur, C, C, nullptr, 0, 0, TL, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
+        bld.emit_prep(cur, C, nullptr, 0, TL, TL, PREP_AFFINE, sc, sh, sx);
+        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.proj_in); }
+        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
+        { GemmOp g = lin(x.qkv, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
-          a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C; a.out = ATT; a.out_ld = C;
+          a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C;
+          a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
           a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); fwd.push_back(l); }
-        { GemmOp g = bf.gemm_base(x.out1, TL, TL); bf.seg(g, ATT, C, 0, C, 0, A_RAW);
-          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bf.emit_gemm(g, x.out1); }
-        bf.emit_ln_stats(T1, C, (int)rows, C, rs2);
-        { GemmOp g = bf.gemm_base(x.q2, TL, TL); bf.seg(g, T1, C, 0, C, 0, A_LN, rs2, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"));
-          g.out = QKV; g.out_ld = C; bf.emit_gemm(g, x.q2); }
+        { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bld.emit_gemm(g, x.out1); }
+        bld.emit_ln_split(T1, C, (int)rows, C, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"), sx);
+        { GemmOp g = lin(x.q2, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; bld.emit_gemm(g, x.q2); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.kv_off + C; a.v_ld = h->kv_total; a.bias = maskbias;
-          a.out = ATT; a.out_ld = C; a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/; fwd.push_back(l); }
-        { GemmOp g = bf.gemm_base(x.out2, TL, TL); bf.seg(g, ATT, C, 0, C, 0, A_RAW);
-          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bf.emit_gemm(g, x.out2); }
-        bf.emit_ln_stats(T0, C, (int)rows, C, rs3);
-        { GemmOp g = bf.gemm_base(x.ff1, TL, TL); bf.seg(g, T0, C, 0, C, 0, A_LN, rs3, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"));
-          g.flags = EPI_GEGLU; g.bias = h->W(b + ".ff.net.0.proj.bias"); g.out = FF; g.out_ld = 4 * C; bf.emit_gemm(g, x.ff1); }
-        { GemmOp g = bf.gemm_base(x.ff2, TL, TL); bf.seg(g, FF, 4 * C, 0, 4 * C, 0, A_RAW);
-          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bf.emit_gemm(g, x.ff2); }
+          a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
+          a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/; fwd.push_back(l); }
+        { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.out2); }
+        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"), sx);
+        { GemmOp g = lin(x.ff1, sx, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.0.proj.bias");
+          g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld; bld.emit_gemm(g, x.ff1); }
+        { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
+          g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
         float* outp = next_out(followed_by_push(pi), rows * C);
-        { GemmOp g = bf.gemm_base(x.proj_out, TL, TL); bf.seg(g, T1, C, 0, C, 0, A_RAW);
-          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C; bf.emit_gemm(g, x.proj_out); }
+        { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C; bld.emit_gemm(g, x.proj_out); }
         cur = outp;
-        bf.emit_tap(x.p, cur, o.level, C, TL);
+        bld.emit_tap(x.p, cur, o.level, C, TL);
         break;
       }
       case PlanOp::DOWN: {
+        // conv k3 s2 p1:  out[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1] = W0 O[t-1] + W1 E[t] + W2 O[t]
+        // with E[t] = x[2t], O[t] = x[2t+1] decimated by the prep kernel (unit-stride TMA windows).
         const ConvSite& s = h->resamplers[si++];
         const int Tin = Tl[o.level - 1];
+        const int To = Tin / 2;                                  // odd-row count
+        const SplitBuf ev = Builder::view(SP_A, TL, s.c), od = Builder::view(SP_R, std::max(To, 1), s.c);
+        bld.emit_prep(cur, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, ev, nullptr, 2, 0);
+        bld.emit_prep(cur, s.c, nullptr, 0, Tin, std::max(To, 1), PREP_RAW, nullptr, nullptr, od, nullptr, 2, 1);
         float* outp = next_out(followed_by_push(pi), rows * s.c);
-        GemmOp g = bf.gemm_base(s.w, TL, Tin, 2);
-        for (int j = 0; j < 3; ++j) bf.seg(g, cur, s.c, 0, s.c, j - 1, A_RAW);
-        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
-        bf.emit_gemm(g, s.w);
-        cur = outp; cur_level = o.level;
-        bf.emit_tap(s.p, cur, o.level, s.c, TL);
+        GemmOp g = bld.gemm_base(s.w, TL);
+        const int ie = bld.add_src(g, ev), io = bld.add_src(g, od);
+        bld.seg(g, io, 0, s.c, -1); bld.seg(g, ie, 0, s.c, 0); bld.seg(g, io, 0, s.c, 0);
+        g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        bld.emit_gemm(g, s.w);
+        cur = outp;
+        bld.emit_tap(s.p, cur, o.level, s.c, TL);
         break;
       }
       case PlanOp::UP: {
@@ -689,32 +723,36 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           std::vector<int> idx(TL);
           ns2vc_nearest_index(Tin, TL, idx.data());
           NS_CHECK_CUDA(cudaMalloc(&map_d, (size_t)TL * sizeof(int)));
-          NS_CHECK_CUDA(cudaMemcpy(map_d, idx.data(), (size_t)TL * sizeof(int), cudaMemcpyHostToDevice));
+          NS_CHECK_CUDA(cudaMemcpyAsync(map_d, idx.data(), (size_t)TL * sizeof(int), cudaMemcpyHostToDevice, st));
+          NS_CHECK_CUDA(cudaStreamSynchronize(st));
           h->rowmaps.push_back(map_d);
         }
+        const SplitBuf up = Builder::view(SP_A, TL, s.c);
+        bld.emit_prep(cur, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, up, nullptr, 1, 0, map_d);
         float* outp = next_out(followed_by_push(pi), rows * s.c);
-        GemmOp g = bf.gemm_base(s.w, TL, Tin, 1);
-        g.T_virt = TL; g.rowmap = map_d;
-        for (int j = 0; j < 3; ++j) bf.seg(g, cur, s.c, 0, s.c, j - 1, A_RAW);
-        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
-        bf.emit_gemm(g, s.w);
-        cur = outp; cur_level = o.level;
-        bf.emit_tap(s.p, cur, o.level, s.c, TL);
+        GemmOp g = bld.gemm_base(s.w, TL);
+        bld.conv3(g, up);
+        g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        bld.emit_gemm(g, s.w);
+        cur = outp;
+        bld.emit_tap(s.p, cur, o.level, s.c, TL);
         break;
       }
     }
   }
-  (void)cur_level; (void)cat2_c;
   // output head: GN -> SiLU -> conv_out, stored channel-major [B, out_channels, T]
   {
-    float* sc = fa.get<float>((size_t)B * c0); float* sh = fa.get<float>((size_t)B * c0);
-    bf.emit_gn(cur, c0, c0, nullptr, 0, 0, T, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
-    GemmOp g = bf.gemm_base(h->conv_out, T, T);
-    for (int j = 0; j < 3; ++j) bf.seg(g, cur, c0, 0, c0, j - 1, A_AFFINE_SILU, sc, sh, nullptr, 0, c0);
-    g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr; g.out_ld = 0;
-    bf.emit_gemm(g, h->conv_out, 3);
+    float* sc = ar.get<float>((size_t)B * c0); float* sh = ar.get<float>((size_t)B * c0);
+    const SplitBuf a_h = Builder::view(SP_H, T, c0);
+    bld.emit_gn(cur, c0, c0, nullptr, 0, 0, T, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
+    bld.emit_prep(cur, c0, nullptr, 0, T, T, PREP_AFFINE_SILU, sc, sh, a_h);
+    GemmOp g = bld.gemm_base(h->conv_out, T);
+    bld.conv3(g, a_h);
+    g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
+    bld.emit_gemm(g, h->conv_out, 3);
   }
-  if (bytes_out) *bytes_out = fa.off + 256;
+  if (bld.err) return bld.err;
+  if (bytes_out) *bytes_out = ar.off + 256;
   if (!dry) {
     h->prog_cond = std::move(cond);
     h->prog_fwd = std::move(fwd);
@@ -736,10 +774,12 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
     }
     switch (l.kind) {
       case Launch::GEMM: {
-        GemmOp g = l.gemm;
-        if (l.patch == 3) g.out = out;
-        if (l.patch == 5) g.seg[0].src = prompt;
-        rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
+        if (l.patch == 3) {
+          GemmOp g = l.gemm; g.out = out;
+          rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
+        } else {
+          rc = h->simt ? launch_gemm_simt(l.gemm, st) : launch_gemm_tc(l.gemm, st);
+        }
         break;
       }
       case Launch::ATTN: {
@@ -749,7 +789,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         break;
       }
       case Launch::GN: rc = launch_gn_affine(l.gn, st); break;
-      case Launch::LN_STATS: rc = launch_ln_stats(l.a, l.i0, l.i1, l.i2, l.f0, l.o, st); break;
+      case Launch::LN_SPLIT: rc = launch_ln_split(l.a, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.split, st); break;
       case Launch::LN_APPLY: {
         const float* src = (l.patch == 5) ? prompt : l.a;
         rc = launch_ln_apply(src, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.o, l.i3, st);
@@ -761,10 +801,16 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         rc = launch_small_linear(o, st);
         break;
       }
-      case Launch::NCT2TOK: {
+      case Launch::NCT2SPLIT: {
         const float* src = (l.patch == 1) ? x : content;
         const long long bs = (l.patch == 1) ? x_bstride : content_bstride;
-        rc = launch_nct_to_tokens(src, bs, h->pB, l.i0, l.i1, l.o, l.i2, l.i3, st);
+        rc = launch_nct_to_split(src, bs, h->pB, l.i0, l.i1, l.split, st);
+        break;
+      }
+      case Launch::PREP: {
+        PrepOp p = l.prep;
+        if (l.patch == 5) p.src1 = prompt;
+        rc = launch_prep_split(p, st);
         break;
       }
       case Launch::POOL_CLS: rc = launch_pool_class_token(l.a, l.b, h->pB, l.i0, l.i1, l.o, st); break;
@@ -784,6 +830,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       cudaEventRecord(ev_b, st);
       ns2vc_unet::ProfRec pr{(int)l.kind, ev_a, ev_b, 0, 0, 0, 0, 0};
       if (l.kind == Launch::GEMM) { pr.M = l.gemm.B * l.gemm.T_out; pr.N = l.gemm.n_valid; pr.K = l.gemm.nkb_total * 64; pr.nseg = l.gemm.nseg; }
+      if (l.kind == Launch::PREP) { pr.M = l.prep.B * l.prep.T_dst; pr.N = l.prep.C1 + l.prep.C2; }
       if (l.kind == Launch::ATTN) { pr.M = l.attn.Tq; pr.N = l.attn.Tk; pr.K = l.attn.dh; }
       h->prof.push_back(pr);
     }
@@ -968,11 +1015,11 @@ int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {
   h->profiling = on != 0;
   return 0;
 }
-int ns2vc_profile_num_kinds(void) { return 10; }
+int ns2vc_profile_num_kinds(void) { return 11; }
 const char* ns2vc_profile_kind_name(int k) {
-  static const char* names[] = {"gemm_tc", "attention", "gn_affine", "ln_stats", "ln_apply", "small_linear", "nct_to_tokens",
-                               "pool_class_token", "pool_attend", "mask_bias"};
-  return (k >= 0 && k < 10) ? names[k] : "";
+  static const char* names[] = {"gemm_tc", "attention", "gn_affine", "ln_split", "ln_apply", "small_linear", "nct_to_split",
+                               "pool_class_token", "pool_attend", "mask_bias", "prep_split"};
+  return (k >= 0 && k < 11) ? names[k] : "";
 }
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches) {
   NS_REQUIRE(h && ms_total && launches, "null argument");

@@ -1,5 +1,4 @@
-// Device helpers shared by the tcgen05 GEMM and the SIMT debug GEMM: A-operand row mapping,
-// the fused normalisation/activation transforms, and the epilogue math.
+// Device helpers shared by the tcgen05 GEMM, the SIMT debug GEMM and the prep kernels.
 #pragma once
 #include "common.cuh"
 
@@ -10,39 +9,33 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 // erf-GELU, as F.gelu default (reference attention.py:295)
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
-// Source row for output row (b, t) and a segment tap; returns -1 for a zero-padded row.
-__device__ __forceinline__ long long a_src_row(const GemmOp& op, int b, int t, int tap) {
-  const int u = t * op.stride + tap;
-  if (u < 0 || u >= op.T_virt) return -1;
-  const int r = op.rowmap ? __ldg(op.rowmap + u) : u;
-  return (long long)b * op.T_src + r;
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// One A element (used by the SIMT kernel and as the definition the vector paths must match).
-__device__ __forceinline__ float a_fetch(const GemmOp& op, const ASeg& s, int b, long long srow, int c) {
-  if (srow < 0 || c >= s.nch) return 0.f;
-  float x = __ldg(s.src + srow * s.ld + s.ch0 + c);
-  switch (s.mode) {
-    case A_AFFINE:
-      x = fmaf(x, __ldg(s.p0 + (long long)b * s.ald + s.aoff + c), __ldg(s.p1 + (long long)b * s.ald + s.aoff + c));
-      break;
-    case A_AFFINE_SILU:
-      x = fmaf(x, __ldg(s.p0 + (long long)b * s.ald + s.aoff + c), __ldg(s.p1 + (long long)b * s.ald + s.aoff + c));
-      x = silu_f(x);
-      break;
-    case A_LN: {
-      const float mean = __ldg(s.p0 + 2 * srow), rstd = __ldg(s.p0 + 2 * srow + 1);
-      x = (x - mean) * rstd * __ldg(s.p1 + s.ch0 + c) + __ldg(s.p2 + s.ch0 + c);
-      break;
-    }
-    default: break;
-  }
-  return x;
+// 8 fp32 values -> 16 bytes of bf16 hi and 16 bytes of bf16 lo (x = hi + lo to ~2^-17 relative)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  float h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+  hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
+  hi.z = pack_bf16x2(h[4], h[5]); hi.w = pack_bf16x2(h[6], h[7]);
+  lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
+  lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
 }
 
-// Epilogue for one accumulator value at (m = b*T_out + t, packed column n).  For GEGLU the caller
-// passes the value accumulator in `acc` and the gate accumulator in `acc_gate`, and n is the
-// logical output column.
+// One A element of a segment, as the TMA path sees it (zero outside the source).
+__device__ __forceinline__ float a_fetch_split(const GemmOp& op, const GSeg& s, int b, int t, int c) {
+  const SplitBuf& src = op.src[s.src];
+  const int r = t + s.tap, ch = s.c0 + c;
+  if (r < 0 || r >= src.T || ch >= src.C) return 0.f;
+  const long long off = ((long long)b * src.T + r) * src.ld + ch;
+  return __bfloat162float(src.hi[off]) + __bfloat162float(src.lo[off]);
+}
+
+// Epilogue for one accumulator value at (m = b*T_out + t, logical column n).  For GEGLU the caller
+// passes the value accumulator in `acc` and the gate accumulator in `acc_gate`.
 __device__ __forceinline__ float epi_value(const GemmOp& op, int b, long long m, int n, float acc, float acc_gate) {
   float v = acc;
   if (op.flags & EPI_GEGLU) {

@@ -57,15 +57,18 @@ int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, f
 }
 
 // ---------------------------------------------------------------------------------------------
-// SIMT debug GEMM: 64x64 tile, BK=16, 256 threads x (4x4) accumulators (x2 for GEGLU).
+// SIMT debug GEMM: 64x64 tile, BK=16, 256 threads x (4x4) accumulators (x2 for GEGLU).  Reads the
+// same split activations the TMA path reads (A = hi + lo) and the fp32 copy of the weights, so a
+// disagreement with gemm_tc isolates the TMA/UMMA/TMEM machinery.
 // ---------------------------------------------------------------------------------------------
 template <bool GEGLU>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ GemmOp op) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[GEGLU ? 2 : 1][16][64 + 4];
   const int tid = threadIdx.x;
-  const int M = op.B * op.T_out;
-  const int m0 = blockIdx.x * 64;
+  const int tiles_per_batch = (op.T_out + 63) / 64;
+  const int b = blockIdx.x / tiles_per_batch;
+  const int t0 = (blockIdx.x % tiles_per_batch) * 64;
   const int jn = blockIdx.y;                       // output column tile (64 logical columns)
   const int pcol0 = GEGLU ? jn * 128 : jn * 64;    // first packed column
   const int ty = tid / 16, tx = tid % 16;
@@ -75,74 +78,71 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; accg[i][j] = 0.f; }
 
-  // A-load assignment: row ar, channels ak..ak+3 of each 16-wide slab
-  const int ar = tid / 4, ak = (tid % 4) * 4;
-  const int am = m0 + ar;
-  const int ab = (am < M) ? am / op.T_out : 0;
-  const int at = (am < M) ? am % op.T_out : 0;
-  // B-load assignment
-  const int bk = tid / 16, bn = (tid % 16) * 4;
+  const int ar = tid / 4, ak = (tid % 4) * 4;      // A-load assignment: row ar, 4 channels of each 16-wide slab
+  const int at = t0 + ar;
+  const int bk = tid / 16, bn = (tid % 16) * 4;    // B-load assignment
 
   int kb_glob = 0;
   for (int si = 0; si < op.nseg; ++si) {
-    const ASeg& s = op.seg[si];
-    const long long srow = (am < M) ? a_src_row(op, ab, at, s.tap) : -1;
+    const GSeg& s = op.seg[si];
     const int kmax = s.nkb * 64;
     for (int k0 = 0; k0 < kmax; k0 += 16) {
-      if (k0 < ((s.nch + 15) & ~15)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) As[ak + j][ar] = a_fetch(op, s, ab, srow, k0 + ak + j);
-        const long long krow = ((long long)kb_glob * 64 + k0 + bk) * op.N;
-        const float4 bv = *reinterpret_cast<const float4*>(op.w_f32 + krow + pcol0 + bn);
-        Bs[0][bk][bn] = bv.x; Bs[0][bk][bn + 1] = bv.y; Bs[0][bk][bn + 2] = bv.z; Bs[0][bk][bn + 3] = bv.w;
-        if (GEGLU) {
-          const float4 gv = *reinterpret_cast<const float4*>(op.w_f32 + krow + pcol0 + 64 + bn);
-          Bs[1][bk][bn] = gv.x; Bs[1][bk][bn + 1] = gv.y; Bs[1][bk][bn + 2] = gv.z; Bs[1][bk][bn + 3] = gv.w;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          float a[4], bb[4], gg[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { bb[j] = Bs[0][kk][tx * 4 + j]; gg[j] = GEGLU ? Bs[GEGLU ? 1 : 0][kk][tx * 4 + j] : 0.f; }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-              if (GEGLU) accg[i][j] = fmaf(a[i], gg[j], accg[i][j]);
-            }
-        }
-        __syncthreads();
+      for (int j = 0; j < 4; ++j) As[ak + j][ar] = (at < op.T_out) ? a_fetch_split(op, s, b, at, k0 + ak + j) : 0.f;
+      const long long krow = ((long long)kb_glob * 64 + k0 + bk) * op.N;
+      const float4 bv = *reinterpret_cast<const float4*>(op.w_f32 + krow + pcol0 + bn);
+      Bs[0][bk][bn] = bv.x; Bs[0][bk][bn + 1] = bv.y; Bs[0][bk][bn + 2] = bv.z; Bs[0][bk][bn + 3] = bv.w;
+      if (GEGLU) {
+        const float4 gv = *reinterpret_cast<const float4*>(op.w_f32 + krow + pcol0 + 64 + bn);
+        Bs[GEGLU ? 1 : 0][bk][bn] = gv.x; Bs[GEGLU ? 1 : 0][bk][bn + 1] = gv.y; Bs[GEGLU ? 1 : 0][bk][bn + 2] = gv.z; Bs[GEGLU ? 1 : 0][bk][bn + 3] = gv.w;
       }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float a[4], bb[4], gg[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { bb[j] = Bs[0][kk][tx * 4 + j]; gg[j] = GEGLU ? Bs[GEGLU ? 1 : 0][kk][tx * 4 + j] : 0.f; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            if (GEGLU) accg[i][j] = fmaf(a[i], gg[j], accg[i][j]);
+          }
+      }
+      __syncthreads();
     }
     kb_glob += s.nkb;
   }
 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    const int b = (int)(m / op.T_out), t = (int)(m % op.T_out);
+    const int t = t0 + ty * 4 + i;
+    if (t >= op.T_out) continue;
+    const long long m = (long long)b * op.T_out + t;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = jn * 64 + tx * 4 + j;       // logical output column
       if (n >= op.n_valid) continue;
       const float v = epi_value(op, b, m, n, acc[i][j], accg[i][j]);
       if (op.flags & EPI_OUT_NCT) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = v;
-      else op.out[m * op.out_ld + n] = v;
+      if (op.flags & EPI_OUT_F32) op.out[m * op.out_ld + n] = v;
+      if (op.flags & EPI_OUT_SPLIT) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        op.out_hi[m * op.out_split_ld + n] = h;
+        op.out_lo[m * op.out_split_ld + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
   }
 }
 
 int launch_gemm_simt(const GemmOp& op, cudaStream_t st) {
   if (!op.w_f32) { set_error("SIMT debug GEMM requested but fp32 weights were not packed (set NS2VC_GEMM_BACKEND=simt before creating the engine)"); return -1; }
-  const int M = op.B * op.T_out;
   const bool geglu = (op.flags & EPI_GEGLU) != 0;
   const int ncols = geglu ? op.N / 2 : op.N;
-  dim3 grid(ceil_div(M, 64), ncols / 64);
+  dim3 grid(op.B * ceil_div(op.T_out, 64), ncols / 64);
   if (geglu) gemm_simt_kernel<true><<<grid, 256, 0, st>>>(op);
   else gemm_simt_kernel<false><<<grid, 256, 0, st>>>(op);
   cudaError_t e = cudaGetLastError();

@@ -8,25 +8,28 @@
 // three kind::f16 MMAs accumulate into the same TMEM tile (the lo*lo term, ~2^-16 relative, is
 // dropped).
 //
-// Warp roles (320 threads, 1 CTA/SM, 3-stage mbarrier ring of 64 KB stages):
-//   warps 0-7  A producers: read the fp32 activations (token-major rows, shifted per conv tap,
-//              strided / index-mapped for down/up-sampling, two base pointers for channel
-//              concats), apply the fused GroupNorm(+FiLM)+SiLU or LayerNorm transform, split to
-//              bf16 hi/lo and write the K-major SWIZZLE_128B shared-memory image of the UMMA A
-//              operand.  After the main loop the same warps run the epilogue:
-//              TMEM -> registers (tcgen05.ld 32x32b) -> bias / GEGLU / residual -> global.
-//   warp 8     B producer: one cp.async.bulk (UBLKCP) per hi/lo tile from the pre-swizzled packed
-//              weights; also owns the TMEM allocation.
-//   warp 9     MMA issuer: one elected lane issues tcgen05.mma and tcgen05.commit.
+// A operand: the pre-normalised "split" activations [B, T, C] (bf16 hi / lo), fetched by TMA
+// (cp.async.bulk.tensor.3d, SWIZZLE_128B) as {64 channels x 128 rows} boxes of ONE batch entry.
+// A conv tap is the same box shifted by one row; rows before 0 / past T and channels past C are
+// zero-filled by the TMA unit, which is the conv's zero padding and the ragged-edge handling at
+// once.  Channel concats are just two tensor maps.
+// B operand: weights pre-packed as the swizzled smem image, one cp.async.bulk per hi/lo tile.
+//
+// Warp roles (192 threads, 1 CTA/SM, 3-4 stage mbarrier ring):
+//   warp 0     TMA producer (one elected lane)
+//   warp 1     MMA issuer (one elected lane): tcgen05.mma x12 per k-block, tcgen05.commit
+//   warps 2-5  epilogue: TMEM -> registers (tcgen05.ld 32x32b) -> bias / GEGLU / residual ->
+//              fp32 token-major, fp32 channel-major, or bf16 hi/lo split for the next GEMM
 #include "gemm_common.cuh"
+#include <cuda.h>
 #include <cstdio>
 
 namespace ns2vc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kProdWarps = 8;
-constexpr int kThreads = (kProdWarps + 2) * 32;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kATileBytes = BM * BK * 2;                // 16 KB: one bf16 [128 x 64] A tile (hi or lo)
 
 template <int BN_> struct TileCfg {
@@ -45,9 +48,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -74,7 +74,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -82,6 +81,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// 3-D tiled TMA load: box {64 ch, 128 rows, 1 batch} at (c, t, b); out-of-range coordinates are zero-filled
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const TMap* tmap, int c, int t, int b, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(t), "r"(b)
+      : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
@@ -118,47 +124,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// ---- A-producer helpers.  One thread owns 8 consecutive channels (one 16-byte bf16 chunk) of 4 rows.
-// Must agree element-for-element with a_fetch() in gemm_common.cuh.
-struct Row8 { float v[8]; };
-
-__device__ __forceinline__ void load_raw8(const ASeg& s, long long srow, int c0, bool vec, Row8& r) {
-  const float* px = s.src + srow * s.ld + s.ch0 + c0;
-  if (vec) {
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(px));
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(px) + 1);
-    r.v[0] = x0.x; r.v[1] = x0.y; r.v[2] = x0.z; r.v[3] = x0.w; r.v[4] = x1.x; r.v[5] = x1.y; r.v[6] = x1.z; r.v[7] = x1.w;
-  } else {
+// Store 32 consecutive output columns of one row in the layout(s) the op asks for.
+__device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long long m, int nbase, const float* val) {
+  if (op.flags & EPI_OUT_NCT) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r.v[j] = (c0 + j < s.nch) ? __ldg(px + j) : 0.f;
+    for (int j = 0; j < 32; ++j) {
+      const int n = nbase + j;
+      if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = val[j];
+    }
+    return;
   }
-}
-__device__ __forceinline__ void load_vec8(const float* p, int c0, int nch, bool vec, float* o) {
-  if (vec) {
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p)), a1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    o[0] = a0.x; o[1] = a0.y; o[2] = a0.z; o[3] = a0.w; o[4] = a1.x; o[5] = a1.y; o[6] = a1.z; o[7] = a1.w;
-  } else {
+  const bool fullc = nbase + 32 <= op.n_valid;
+  if (op.flags & EPI_OUT_F32) {
+    float* po = op.out + m * op.out_ld + nbase;
+    if (fullc && ((op.out_ld & 3) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (c0 + j < nch) ? __ldg(p + j) : 0.f;
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(po + 4 * j) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) po[j] = val[j];
+    }
   }
-}
-__device__ __forceinline__ void store_split8(uint8_t* a_hi, uint8_t* a_lo, int r, int chunk, const float* v) {
-  float h[8];
+  if (op.flags & EPI_OUT_SPLIT) {
+    __nv_bfloat16* ph = op.out_hi + m * op.out_split_ld + nbase;
+    __nv_bfloat16* pl = op.out_lo + m * op.out_split_ld + nbase;
+    if (fullc && ((op.out_split_ld & 7) == 0)) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-  uint4 hi, lo;
-  hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
-  hi.z = pack_bf16x2(h[4], h[5]); hi.w = pack_bf16x2(h[6], h[7]);
-  lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
-  lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
-  const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-  *reinterpret_cast<uint4*>(a_hi + off) = hi;
-  *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(val + 8 * j, hi, lo);
+        *reinterpret_cast<uint4*>(ph + 8 * j) = hi;
+        *reinterpret_cast<uint4*>(pl + 8 * j) = lo;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nbase + j < op.n_valid) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(val[j]);
+          ph[j] = h;
+          pl[j] = __float2bfloat16_rn(val[j] - __bfloat162float(h));
+        }
+    }
+  }
 }
 
 template <int BN_>
@@ -178,20 +185,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = op.B * op.T_out;
-  const int m0 = blockIdx.x * BM;
+  const int tiles_per_batch = (op.T_out + BM - 1) / BM;
+  const int b = blockIdx.x / tiles_per_batch;
+  const int t0 = (blockIdx.x % tiles_per_batch) * BM;
   const int n0 = blockIdx.y * BN;                           // first packed column of this tile
   const int nkb = op.nkb_total;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), kProdWarps + 1);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"(Cfg::kTmemCols)
                  : "memory");
@@ -202,184 +210,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kProdWarps) {
-    // ===================== A producers =====================
-    const int chunk = tid & 7;                              // 8 channels = one 16-byte bf16 chunk
-    const int rsub = tid >> 3;                              // 0..31
-    int rb[4], rt[4];
-    bool rv[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int m = m0 + p * 32 + rsub;
-      rv[p] = m < M;
-      rb[p] = rv[p] ? m / op.T_out : 0;
-      rt[p] = rv[p] ? m % op.T_out : 0;
-    }
-    const bool same_b = (rb[0] == rb[1]) && (rb[0] == rb[2]) && (rb[0] == rb[3]);
-    int si = 0, kbl = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int stage = kb % kStages;
-      const uint32_t parity = (uint32_t)((kb / kStages) & 1);
-      const ASeg& s = op.seg[si];
-      const int c0 = kbl * 64 + chunk * 8;
-      const bool chan_ok = c0 < s.nch;
-      const bool full = c0 + 8 <= s.nch;
-      const bool vec = full && (((s.ld | s.ch0) & 3) == 0);
-      // ---- phase 1: issue every global load of this k-block before touching the data
-      long long srow[4];
-      Row8 x[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        srow[p] = (rv[p] && chan_ok) ? a_src_row(op, rb[p], rt[p], s.tap) : -1;
-        if (srow[p] >= 0) load_raw8(s, srow[p], c0, vec, x[p]);
-      }
-      float pa[8], pb[8];                                   // affine scale/shift or LN gamma/beta
-      float2 st[4];
-      const int mode = s.mode;
-      if (chan_ok) {
-        if (mode == A_AFFINE || mode == A_AFFINE_SILU) {
-          const bool pvec = full && (((s.ald | s.aoff) & 3) == 0);
-          load_vec8(s.p0 + (long long)rb[0] * s.ald + s.aoff + c0, c0, s.nch, pvec, pa);
-          load_vec8(s.p1 + (long long)rb[0] * s.ald + s.aoff + c0, c0, s.nch, pvec, pb);
-        } else if (mode == A_LN) {
-          const bool pvec = full && ((s.ch0 & 3) == 0);
-          load_vec8(s.p1 + s.ch0 + c0, c0, s.nch, pvec, pa);
-          load_vec8(s.p2 + s.ch0 + c0, c0, s.nch, pvec, pb);
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (srow[p] >= 0) st[p] = __ldg(reinterpret_cast<const float2*>(s.p0) + srow[p]);
-        }
-      }
-      mbar_wait(empty_bar(stage), parity ^ 1u);
-      uint8_t* a_hi = smem + stage * kStageBytes;
-      uint8_t* a_lo = a_hi + kATileBytes;
-      // ---- phase 2: transform, split, store
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int r = p * 32 + rsub;
-        float v[8];
-        if (srow[p] < 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = x[p].v[j];
-          if (mode == A_AFFINE || mode == A_AFFINE_SILU) {
-            float sc[8], sh[8];
-            if (same_b || rb[p] == rb[0]) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { sc[j] = pa[j]; sh[j] = pb[j]; }
-            } else {
-              const bool pvec = full && (((s.ald | s.aoff) & 3) == 0);
-              load_vec8(s.p0 + (long long)rb[p] * s.ald + s.aoff + c0, c0, s.nch, pvec, sc);
-              load_vec8(s.p1 + (long long)rb[p] * s.ald + s.aoff + c0, c0, s.nch, pvec, sh);
-            }
-            if (mode == A_AFFINE_SILU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = silu_f(fmaf(v[j], sc[j], sh[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-            }
-          } else if (mode == A_LN) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (v[j] - st[p].x) * st[p].y * pa[j] + pb[j];
-          }
-          if (!full) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (c0 + j >= s.nch) v[j] = 0.f;
-          }
-        }
-        store_split8(a_hi, a_lo, r, chunk, v);
-      }
-      fence_proxy_async();                                  // generic-proxy stores -> visible to UMMA (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++kbl == s.nkb) { kbl = 0; ++si; }
-    }
-
-    // ===================== epilogue =====================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                                 // TMEM lane quarter this warp may access
-    const int hh = warp >> 2;                               // column half
-    const int r = q * 32 + lane;
-    const long long m = (long long)m0 + r;
-    const bool mv = m < M;
-    const int b = mv ? (int)(m / op.T_out) : 0;
-    const int t = mv ? (int)(m % op.T_out) : 0;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (op.flags & EPI_GEGLU) {
-      if (BN == 128) {
-        float val[32], gate[32];
-        tmem_ld32(trow + (uint32_t)(hh * 32), val);
-        tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
-        const int nbase = blockIdx.y * 64 + hh * 32;        // logical output column
-        if (mv) {
-          float* po = op.out + m * op.out_ld + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = epi_value(op, b, m, nbase + j + 0, val[j + 0], gate[j + 0]);
-            o.y = epi_value(op, b, m, nbase + j + 1, val[j + 1], gate[j + 1]);
-            o.z = epi_value(op, b, m, nbase + j + 2, val[j + 2], gate[j + 2]);
-            o.w = epi_value(op, b, m, nbase + j + 3, val[j + 3], gate[j + 3]);
-            *reinterpret_cast<float4*>(po + j) = o;
-          }
-        }
-      }
-    } else {
-      constexpr int kChunks = BN / 64;                      // 32-column chunks per warp
-#pragma unroll 1
-      for (int cc = 0; cc < kChunks; ++cc) {
-        float acc[32];
-        const int col = hh * (BN / 2) + cc * 32;
-        tmem_ld32(trow + (uint32_t)col, acc);
-        const int nbase = n0 + col;
-        if (!mv || nbase >= op.n_valid) continue;
-        if (op.flags & EPI_OUT_NCT) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = epi_value(op, b, m, n, acc[j], 0.f);
-          }
-        } else if (nbase + 32 <= op.n_valid && ((op.out_ld & 3) == 0) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0) &&
-                   !(op.flags & EPI_ROWBIAS)) {
-          float* po = op.out + m * op.out_ld + nbase;
-          const float4* pr = (op.flags & EPI_RESIDUAL) ? reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase) : nullptr;
-          const float4* pbias = (op.flags & EPI_BIAS) ? reinterpret_cast<const float4*>(op.bias + nbase) : nullptr;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            if (pbias) { const float4 bv = __ldg(pbias + j); o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w; }
-            if (pr) { const float4 rv4 = __ldg(pr + j); o.x += rv4.x; o.y += rv4.y; o.z += rv4.z; o.w += rv4.w; }
-            *reinterpret_cast<float4*>(po + 4 * j) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            if (n < op.n_valid) op.out[m * op.out_ld + n] = epi_value(op, b, m, n, acc[j], 0.f);
-          }
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ===================== B producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
+      int si = 0, kbl = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % kStages;
         const uint32_t parity = (uint32_t)((kb / kStages) & 1);
         mbar_wait(empty_bar(stage), parity ^ 1u);
-        const uint32_t b_hi = base + stage * kStageBytes + 2 * kATileBytes;
+        const GSeg& s = op.seg[si];
+        const uint32_t a_hi = base + stage * kStageBytes;
+        const uint32_t a_lo = a_hi + kATileBytes;
+        const uint32_t b_hi = a_lo + kATileBytes;
         const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
-        mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kBTileBytes);
+        mbar_arrive_expect_tx(full_bar(stage), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+        const int c = s.c0 + kbl * 64;
+        tma_load_3d(a_hi, &op.tmap[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
+        tma_load_3d(a_lo, &op.tmap[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
         const size_t eoff = ((size_t)kb * op.N + n0) * 64;
         bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
         bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
+        if (++kbl == s.nkb) { kbl = 0; ++si; }
       }
     }
-  } else {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
@@ -389,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tc_fence_after();
         const uint32_t a_hi = base + stage * kStageBytes;
         const uint32_t a_lo = a_hi + kATileBytes;
-        const uint32_t b_hi = a_hi + 2 * kATileBytes;
+        const uint32_t b_hi = a_lo + kATileBytes;
         const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
@@ -403,13 +257,107 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       umma_commit(tmem_full_bar);                           // accumulator complete -> epilogue
     }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int t = t0 + r;
+    const bool mv = t < op.T_out;
+    const long long m = (long long)b * op.T_out + t;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (op.flags & EPI_GEGLU) {
+      if (BN == 128) {
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          float val[32], gate[32];
+          tmem_ld32(trow + (uint32_t)(hh * 32), val);
+          tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
+          const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
+          if (mv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
+            store_chunk(op, b, t, m, nbase, val);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        float acc[32];
+        tmem_ld32(trow + (uint32_t)(cc * 32), acc);
+        const int nbase = n0 + cc * 32;
+        if (!mv || nbase >= op.n_valid) continue;
+        const bool fullc = nbase + 32 <= op.n_valid;
+        if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+          if (op.flags & EPI_BIAS) {
+            const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+          }
+          if (op.flags & EPI_RESIDUAL) {
+            const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
+        }
+        store_chunk(op, b, t, m, nbase, acc);
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host: TMA descriptor encoding (driver entry point fetched through the runtime; no -lcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B) {
+  static_assert(sizeof(CUtensorMap) == sizeof(TMap), "CUtensorMap size");
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
+  if ((s.ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("split buffer not TMA-aligned (ld=%d)", s.ld); return -1; }
+  const cuuint64_t gdim[3] = {(cuuint64_t)s.C, (cuuint64_t)s.T, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)s.ld * 2, (cuuint64_t)s.T * s.ld * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)BM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), gdim, gstr,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) C=%d T=%d B=%d ld=%d", (int)r, s.C, s.T, B, s.ld); return -2; }
+  return 0;
+}
+
+int encode_tmaps(GemmOp& op) {
+  for (int i = 0; i < op.nsrc; ++i) {
+    int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B);
+    if (rc) return rc;
+    rc = encode_one(&op.tmap[2 * i + 1], op.src[i].lo, op.src[i], op.B);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 template <int BN_>
@@ -421,8 +369,7 @@ static int launch_bn(const GemmOp& op, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
-  const int M = op.B * op.T_out;
-  dim3 grid(ceil_div(M, BM), op.N / BN_);
+  dim3 grid(op.B * ceil_div(op.T_out, BM), op.N / BN_);
   gemm_tc_kernel<BN_><<<grid, kThreads, Cfg::kSmemBytes, st>>>(op);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
@@ -432,10 +379,9 @@ static int launch_bn(const GemmOp& op, cudaStream_t st) {
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
-  const int M = op.B * op.T_out;
   // N-tile: 128 wide when that already fills the 148 SMs, else 64 wide (twice the CTAs; the
   // GEGLU epilogue pairs value|gate inside a 128-column block and needs BN = 128).
-  const int ctas128 = ceil_div(M, BM) * (op.N / 128);
+  const int ctas128 = op.B * ceil_div(op.T_out, BM) * (op.N / 128);
   if ((op.flags & EPI_GEGLU) || ctas128 >= 120) return launch_bn<128>(op, st);
   return launch_bn<64>(op, st);
 }

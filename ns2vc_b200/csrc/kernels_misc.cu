@@ -1,7 +1,7 @@
 // Small HBM/L2-bound kernels of the denoiser step: layout conversion, GroupNorm/LayerNorm
 // statistics, the timestep/FiLM GEMV, AttentionPooling pieces, and the fused sampler updates.
 // All are coalesced/vectorised; none is worth tensor cores.
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <math.h>
@@ -214,6 +214,177 @@ int launch_ln_stats(const float* x, int ld, int M, int C, float eps, float* stat
 int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta, float* y,
                     int y_ld, cudaStream_t st) {
   ln_kernel<true><<<ceil_div(M, 8), 256, 0, st>>>(x, ld, M, C, eps, nullptr, gamma, beta, y, y_ld);
+  NS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activation prep: concat(src1, src2) -> [per-(b,c) affine (+SiLU)] -> bf16 hi/lo split, optionally a
+// second untransformed split (the resnet's 1x1 shortcut operand).  One thread = 8 channels of one
+// row (two 16-byte loads, 16-byte hi + lo stores); rows may be remapped (stride-2 decimation for
+// the downsample convs, nearest-upsample index table).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
+  const int C = op.C1 + op.C2;
+  const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
+  const long long total = (long long)op.B * op.T_dst * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ck = (int)(i % chunks);
+    const long long row = i / chunks;
+    const int t = (int)(row % op.T_dst);
+    const int b = (int)(row / op.T_dst);
+    const int c0 = ck * 8;
+    const int ts = op.rowmap ? __ldg(op.rowmap + t) : t * op.row_mul + op.row_add;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const bool rowok = ts >= 0 && ts < op.T_src;
+    if (rowok && c0 < C) {
+      const bool in1 = c0 < op.C1;
+      const float* p = in1 ? op.src1 + ((long long)b * op.T_src + ts) * op.ld1 + c0
+                           : op.src2 + ((long long)b * op.T_src + ts) * op.ld2 + (c0 - op.C1);
+      const int lim = in1 ? op.C1 - c0 : C - c0;           // channels left in this source
+      const int ldx = in1 ? op.ld1 : op.ld2;
+      if (lim >= 8 && ((ldx | (in1 ? c0 : c0 - op.C1)) & 3) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j;
+          if (c < C) v[j] = (c < op.C1) ? op.src1[((long long)b * op.T_src + ts) * op.ld1 + c]
+                                        : op.src2[((long long)b * op.T_src + ts) * op.ld2 + (c - op.C1)];
+        }
+      }
+    }
+    const long long orow = (long long)b * op.T_dst + t;
+    if (op.raw.hi) {
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(op.raw.hi + orow * op.raw.ld + c0) = hi;
+      *reinterpret_cast<uint4*>(op.raw.lo + orow * op.raw.ld + c0) = lo;
+    }
+    if (op.mode != PREP_RAW && rowok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        if (c < C) {
+          float y = fmaf(v[j], __ldg(op.scale + (long long)b * C + c), __ldg(op.shift + (long long)b * C + c));
+          if (op.mode == PREP_AFFINE_SILU) y = silu_f(y);
+          v[j] = y;
+        }
+      }
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(op.out.hi + orow * op.out.ld + c0) = hi;
+    *reinterpret_cast<uint4*>(op.out.lo + orow * op.out.ld + c0) = lo;
+  }
+}
+int launch_prep_split(const PrepOp& op, cudaStream_t st) {
+  if ((op.out.ld & 7) || (op.raw.hi && op.raw.ld != op.out.ld)) { set_error("prep_split: bad pitch"); return -1; }
+  const long long total = (long long)op.B * op.T_dst * (op.out.ld >> 3);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  prep_split_kernel<<<blocks, 256, 0, st>>>(op);
+  NS_LAUNCH_CHECK();
+  return 0;
+}
+
+// LayerNorm + split: one warp per row, two-pass statistics in registers (C <= 1024).
+__global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, int ld, int M, int C, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       SplitBuf out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (long long)row * ld;
+  constexpr int kMaxChunks = 4;                            // 8-channel chunks per lane: C <= 32*8*4
+  float v[kMaxChunks][8];
+  const int chunks = (C + 7) >> 3;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ck = lane + 32 * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+    if (ck < chunks) {
+      const int c0 = ck * 8;
+      if (c0 + 8 <= C && ((ld & 3) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xr + c0)), b4 = __ldg(reinterpret_cast<const float4*>(xr + c0) + 1);
+        v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w; v[k][4] = b4.x; v[k][5] = b4.y; v[k][6] = b4.z; v[k][7] = b4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c0 + j < C) v[k][j] = xr[c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ck = lane + 32 * k;
+    if (ck < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (ck * 8 + j < C) { const float d = v[k][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  const int ochunks = out.ld >> 3;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int ck = lane + 32 * k;
+    if (ck < ochunks) {
+      const int c0 = ck * 8;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        y[j] = (c < C) ? (v[k][j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+      }
+      uint4 hi, lo;
+      split8(y, hi, lo);
+      *reinterpret_cast<uint4*>(out.hi + (long long)row * out.ld + c0) = hi;
+      *reinterpret_cast<uint4*>(out.lo + (long long)row * out.ld + c0) = lo;
+    }
+  }
+}
+int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta, SplitBuf out,
+                    cudaStream_t st) {
+  if (C > 1024 || (out.ld & 7) || out.ld > 1024) { set_error("ln_split: C=%d / pitch %d unsupported", C, out.ld); return -1; }
+  ln_split_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, ld, M, C, eps, gamma, beta, out);
+  NS_LAUNCH_CHECK();
+  return 0;
+}
+
+// [B, C, T] fp32 -> split token-major [B, T, out.ld]; 32x32 smem transpose, zero-fills c >= C.
+__global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstride, int C, int T, SplitBuf out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xb = x + (long long)b * bstride;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? xb[(long long)c * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < out.ld) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const long long off = ((long long)b * T + t) * out.ld + c;
+      out.hi[off] = h;
+      out.lo[off] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st) {
+  dim3 grid(ceil_div(T, 32), ceil_div(out.ld, 32), B), block(32, 8);
+  nct_to_split_kernel<<<grid, block, 0, st>>>(x, bstride, C, T, out);
   NS_LAUNCH_CHECK();
   return 0;
 }
