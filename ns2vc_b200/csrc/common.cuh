@@ -168,7 +168,7 @@ struct AttnOp {
   int B, H, Tq, Tk, dh;
   float scale;                    // dh^-0.5
 };
-int launch_attention(const AttnOp& op, cudaStream_t st);
+int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);
 
 // ---------------------------------------------------------------------------------------------
 // Norm statistics and small kernels (kernels_misc.cu)

@@ -785,7 +785,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       case Launch::ATTN: {
         AttnOp a = l.attn;
         if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
-        rc = launch_attention(a, st);
+        rc = launch_attention(a, st, h->simt);
         break;
       }
       case Launch::GN: rc = launch_gn_affine(l.gn, st); break;

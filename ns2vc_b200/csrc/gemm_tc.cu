@@ -21,8 +21,8 @@
 //   warps 2-5  epilogue: TMEM -> registers (tcgen05.ld 32x32b) -> bias / GEGLU / residual ->
 //              fp32 token-major, fp32 channel-major, or bf16 hi/lo split for the next GEMM
 #include "gemm_common.cuh"
+#include "tc_common.cuh"
 #include <cuda.h>
-#include <cstdio>
 
 namespace ns2vc {
 
@@ -39,90 +39,8 @@ template <int BN_> struct TileCfg {
   static constexpr int kStages = (BN_ == 128) ? 3 : 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = BN_;
-  // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
-  // B=bf16 [10,13)=1, A/B K-major, N>>3 at [17,23), M>>4 at [24,29).
-  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("ns2vc gemm_tc: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// 3-D tiled TMA load: box {64 ch, 128 rows, 1 batch} at (c, t, b); out-of-range coordinates are zero-filled
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const TMap* tmap, int c, int t, int b, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(t), "r"(b)
-      : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1) | [32,46) SBO>>4 = 1024>>4
-//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // Store 32 consecutive output columns of one row in the layout(s) the op asks for.
 __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long long m, int nbase, const float* val) {
@@ -197,14 +115,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -276,8 +189,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
           const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
           if (mv) {
+            if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
+              const float4* bv = reinterpret_cast<const float4*>(op.bias + nbase);
+              const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nbase);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = __ldg(bv + j), y = __ldg(bg + j);
+                val[4 * j + 0] = (val[4 * j + 0] + x.x) * gelu_erf_f(gate[4 * j + 0] + y.x);
+                val[4 * j + 1] = (val[4 * j + 1] + x.y) * gelu_erf_f(gate[4 * j + 1] + y.y);
+                val[4 * j + 2] = (val[4 * j + 2] + x.z) * gelu_erf_f(gate[4 * j + 2] + y.z);
+                val[4 * j + 3] = (val[4 * j + 3] + x.w) * gelu_erf_f(gate[4 * j + 3] + y.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
+            }
             store_chunk(op, b, t, m, nbase, val);
           }
         }
@@ -312,9 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
-  }
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------

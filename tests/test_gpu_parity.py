@@ -82,7 +82,7 @@ def test_tiny_forward_every_op(gold, backend):
         if name in ("emb", "aug_emb"):
             continue
         assert name in taps, f"engine has no tap {name}"
-        ok, msg = close(taps[name], ref)
+        ok, msg = close(taps[name], ref, atol=2e-4)     # intermediate activations: diagnostic tolerance
         if not ok:
             bad.append(f"{name}: {msg}")
     assert not bad, "first failing ops:\n" + "\n".join(bad[:8])
