@@ -17,21 +17,31 @@ __version__ = "0.1.0"
 
 def install() -> None:
     """Make ``unet1d.unet_1d_condition``, ``sampler.dpm_solver`` and ``sampler.uni_pc`` resolve to
-    the B200 implementations (call before ``import model`` in the reference tree)."""
+    the B200 implementations (call before ``import model`` in the reference tree).  The reference's
+    own ``unet1d`` / ``sampler`` packages stay importable for their other submodules
+    (``model.py:6`` imports ``unet1d.embeddings``); only the three hot-path modules are aliased."""
+    import importlib
+    import importlib.util
+
     from . import dpm_solver, uni_pc, unet
 
-    def pkg(name):
+    def parent(name):
         m = sys.modules.get(name)
         if m is None:
-            m = types.ModuleType(name)
-            m.__path__ = []
-            sys.modules[name] = m
+            try:
+                spec = importlib.util.find_spec(name)
+            except (ImportError, ValueError):
+                spec = None
+            if spec is not None:
+                m = importlib.import_module(name)
+            else:                                   # no reference tree on sys.path: stub package
+                m = types.ModuleType(name)
+                m.__path__ = []
+                sys.modules[name] = m
         return m
 
-    u = pkg("unet1d")
-    sys.modules["unet1d.unet_1d_condition"] = unet
-    u.unet_1d_condition = unet
-    s = pkg("sampler")
-    sys.modules["sampler.dpm_solver"] = dpm_solver
-    sys.modules["sampler.uni_pc"] = uni_pc
-    s.dpm_solver, s.uni_pc = dpm_solver, uni_pc
+    for pkg, sub, mod in (("unet1d", "unet_1d_condition", unet), ("sampler", "dpm_solver", dpm_solver),
+                          ("sampler", "uni_pc", uni_pc)):
+        p = parent(pkg)
+        sys.modules[f"{pkg}.{sub}"] = mod
+        setattr(p, sub, mod)

@@ -7,6 +7,7 @@
 // K/V cache with the additive mask bias (0 / -10000, NOT -inf: reference unet_1d_condition.py:817).
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
+#include "launch.cuh"
 #include <math.h>
 
 namespace ns2vc {
@@ -177,6 +178,8 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
 
   if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 128);
+  pdl_trigger();
+  pdl_wait();
 
   // ---- Q tile -> smem (scaled, split)
   for (int i = tid; i < AQ * CK; i += kAttnTcThreads) {
@@ -382,8 +385,7 @@ static int launch_attn_tc(const AttnOp& op, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(ceil_div(op.Tq, AQ), op.H, op.B);
-  attn_tc_kernel<DHP><<<grid, kAttnTcThreads, kAttnSmem, st>>>(op);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(attn_tc_kernel<DHP>, grid, dim3(kAttnTcThreads), (size_t)kAttnSmem, st, op);
   if (e != cudaSuccess) { set_error("attention launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }

@@ -79,6 +79,7 @@ enum EpiFlags : int {
   EPI_ROWBIAS = 16,   // + rowbias[b*rowbias_ld + n]   (per-sample bias, time_embedding 'default')
   EPI_OUT_F32 = 32,   // store fp32 token-major out[m*out_ld + n]
   EPI_OUT_SPLIT = 64, // store bf16 hi/lo token-major (feeds the next GEMM's TMA)
+  EPI_STATS = 128,    // accumulate per-(b, column) sum / sum-of-squares of the fp32 output (GroupNorm of the consumer)
 };
 
 struct GemmOp {
@@ -107,6 +108,8 @@ struct GemmOp {
   __nv_bfloat16* out_lo;
   int out_split_ld;
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
+  double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
+  double* stat_sq;
 };
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).
@@ -136,6 +139,14 @@ int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, f
 // Activation prep: (concat of up to two fp32 sources) -> [GroupNorm affine (+FiLM) (+SiLU)] -> split
 // ---------------------------------------------------------------------------------------------
 enum PrepMode : int { PREP_RAW = 0, PREP_AFFINE = 1, PREP_AFFINE_SILU = 2 };
+// GroupNorm source statistics: per-(b, channel) sums accumulated by the producing GEMM epilogues.
+struct GnStats {
+  const double* sum1; const double* sq1;   // [B, C1]
+  const double* sum2; const double* sq2;   // [B, C2]
+  const float* gamma; const float* beta;   // [C1+C2]
+  const float* film; int film_ld;          // nullptr or [B, film_ld]: scale at film[b,c], shift at film[b,C+c]
+  int G; float eps;
+};
 struct PrepOp {
   const float* src1; int ld1; int C1;
   const float* src2; int ld2; int C2;     // nullptr / 0 when there is no concat
@@ -143,7 +154,8 @@ struct PrepOp {
   int row_mul, row_add;                   // src row = rowmap ? rowmap[t] : t*row_mul + row_add
   const int* rowmap;                      // nearest-upsample index table [T_dst] or nullptr
   int mode;
-  const float* scale; const float* shift; // [B, C1+C2]
+  const float* scale; const float* shift; // [B, C1+C2] precomputed affine, or nullptr: derive it from `gn`
+  GnStats gn;
   SplitBuf out;                           // transformed
   SplitBuf raw;                           // optional second output without the transform (hi == nullptr: none)
 };

@@ -63,7 +63,7 @@ struct ConvSite { std::string p; int c; PackedB w; };
 
 // One launch of the per-shape program.
 struct Launch {
-  enum Kind { GEMM, ATTN, GN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, TAP } kind;
+  enum Kind { GEMM, ATTN, GN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, MEMSET, TAP } kind;
   GemmOp gemm;
   AttnOp attn;
   GnOp gn;
@@ -73,6 +73,7 @@ struct Launch {
   // generic small args
   const float* a = nullptr; const float* b = nullptr; const float* c = nullptr; float* o = nullptr;
   int i0 = 0, i1 = 0, i2 = 0, i3 = 0; float f0 = 0;
+  void* mem = nullptr; size_t mem_bytes = 0;
   int patch = 0;             // 1: x (forward)  2: t  3: out  4: content  5: prompt  6: mask
   int tap_index = -1;
 };
@@ -464,6 +465,16 @@ struct Builder {
     if (raw) p.raw = *raw;
     out->push_back(l);
   }
+  // GroupNorm(+FiLM)(+SiLU) prep whose statistics come from the producers' epilogues
+  void emit_prep_gn(const float* s1, int C1, const double* st1, const float* s2, int C2, const double* st2, int Tn, int mode,
+                    float eps, const float* gamma, const float* beta, const float* film, int film_ld, const SplitBuf& o,
+                    const SplitBuf* raw = nullptr) {
+    emit_prep(s1, C1, s2, C2, Tn, Tn, mode, nullptr, nullptr, o, raw);
+    PrepOp& p = out->back().prep;
+    p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
+    p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
+    p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film = film; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
+  }
   void emit_ln_split(const float* x, int ld, int M, int C, const float* gamma, const float* beta, const SplitBuf& o) {
     Launch l; l.kind = Launch::LN_SPLIT; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.b = gamma; l.c = beta; l.split = o;
     out->push_back(l);
@@ -562,6 +573,18 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     NS_CHECK_CUDA(cudaMemsetAsync(gn_acc, 0, (size_t)B * G * 2 * sizeof(double), st));
     NS_CHECK_CUDA(cudaMemsetAsync(gn_cnt, 0, (size_t)B * G * sizeof(unsigned), st));
   }
+  // per-(b, channel) sum | sum-of-squares of every fp32 activation that feeds a GroupNorm, accumulated by
+  // the producing GEMM epilogues; one contiguous arena, zeroed by one memset at the top of the forward
+  size_t stat_doubles = (size_t)2 * B * c0;
+  for (auto& o : h->plan) {
+    if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
+    else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
+  }
+  double* stat_arena = ar.get<double>(stat_doubles);
+  size_t stat_used = 0;
+  auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
+  auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
+  { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
   // activation buffers
   size_t max_act = (size_t)B * T * c0, max_cat = 0, max_ff = 1, max_qkv = 1;
   for (auto& o : h->plan) {
@@ -597,7 +620,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; fwd.push_back(l);
   }
 
-  std::vector<std::pair<float*, int>> skips;   // (ptr, channels)
+  struct Skip { float* p; int c; double* st; };
+  std::vector<Skip> skips;
   int rot_i = 0;
   auto next_out = [&](bool is_skip, size_t elems) -> float* {
     if (is_skip) return ar.get<float>(elems);
@@ -605,7 +629,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   };
   auto followed_by_push = [&](size_t i) { return i + 1 < h->plan.size() && h->plan[i + 1].kind == PlanOp::PUSH; };
 
-  float* cur = nullptr; int cur_c = c0;
+  float* cur = nullptr; int cur_c = c0; double* cur_st = nullptr;
   {
     float* o = next_out(true, (size_t)B * T * c0);      // conv_in output is the first skip
     GemmOp g = bld.gemm_base(h->convin_lat, T);
@@ -614,39 +638,41 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     if (Cc > 0) { g.flags |= EPI_RESIDUAL; g.res = P; g.res_ld = c0; }
     else { g.flags |= EPI_BIAS; g.bias = h->W("conv_in.bias"); }
     g.out = o; g.out_ld = c0;
+    cur_st = new_stats(c0);
+    with_stats(g, cur_st, c0);
     bld.emit_gemm(g, h->convin_lat);
     cur = o;
     bld.emit_tap("conv_in", cur, 0, c0, T);
   }
-  const float* cat2 = nullptr;                    // pending concat source
+  const float* cat2 = nullptr; const double* cat2_st = nullptr;   // pending concat source
   size_t ri = 0, xi = 0, si = 0;
   for (size_t pi = 0; pi < h->plan.size(); ++pi) {
     const PlanOp& o = h->plan[pi];
     const int TL = Tl[o.level];
     const size_t rows = (size_t)B * TL;
     switch (o.kind) {
-      case PlanOp::PUSH: skips.push_back({cur, cur_c}); break;
-      case PlanOp::POP_CAT: cat2 = skips.back().first; skips.pop_back(); break;
+      case PlanOp::PUSH: skips.push_back({cur, cur_c, cur_st}); break;
+      case PlanOp::POP_CAT: cat2 = skips.back().p; cat2_st = skips.back().st; skips.pop_back(); break;
       case PlanOp::RESNET: {
         const ResnetSite& s = h->resnets[ri++];
         const float* s1 = cur; const float* s2 = s.c2 ? cat2 : nullptr;
-        float* sc1 = ar.get<float>((size_t)B * s.cin); float* sh1 = ar.get<float>((size_t)B * s.cin);
-        float* sc2 = ar.get<float>((size_t)B * s.cout); float* sh2 = ar.get<float>((size_t)B * s.cout);
         const SplitBuf a_in = Builder::view(SP_A, TL, s.cin), a_raw = Builder::view(SP_R, TL, s.cin), a_h = Builder::view(SP_H, TL, s.cout);
-        bld.emit_gn(s1, s.c1, s.c1, s2, s.c2, s.c2, TL, c.norm_eps, h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, sc1, sh1, gn_acc, gn_cnt);
-        bld.emit_prep(s1, s.c1, s2, s.c2, TL, TL, PREP_AFFINE_SILU, sc1, sh1, a_in, s.shortcut ? &a_raw : nullptr);
+        bld.emit_prep_gn(s1, s.c1, cur_st, s2, s.c2, s.c2 ? cat2_st : nullptr, TL, PREP_AFFINE_SILU, c.norm_eps,
+                         h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, a_in, s.shortcut ? &a_raw : nullptr);
+        double* h1_st = new_stats(s.cout);
         {
           GemmOp g = bld.gemm_base(s.conv1, TL);
           bld.conv3(g, a_in);
           g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv1.bias");
           if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
           g.out = H1; g.out_ld = s.cout;
+          with_stats(g, h1_st, s.cout);
           bld.emit_gemm(g, s.conv1);
         }
-        bld.emit_gn(H1, s.cout, s.cout, nullptr, 0, 0, TL, c.norm_eps, h->W(s.p + ".norm2.weight"), h->W(s.p + ".norm2.bias"),
-                    c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, sc2, sh2, gn_acc, gn_cnt);
-        bld.emit_prep(H1, s.cout, nullptr, 0, TL, TL, PREP_AFFINE_SILU, sc2, sh2, a_h);
+        bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
+                         h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
         float* outp = next_out(followed_by_push(pi), rows * s.cout);
+        double* out_st = new_stats(s.cout);
         {
           GemmOp g = bld.gemm_base(s.conv2, TL);
           bld.conv3(g, a_h);
@@ -654,9 +680,11 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           if (s.shortcut) { const int i = bld.add_src(g, a_raw); bld.seg(g, i, 0, s.cin, 0); }
           else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
           g.out = outp; g.out_ld = s.cout;
+          with_stats(g, out_st, s.cout);
           bld.emit_gemm(g, s.conv2);
         }
-        cur = outp; cur_c = s.cout; cat2 = nullptr;
+        cur_st = out_st;
+        cur = outp; cur_c = s.cout; cat2 = nullptr; cat2_st = nullptr;
         bld.emit_tap(s.p, cur, o.level, cur_c, TL);
         break;
       }
@@ -664,12 +692,10 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const XformerSite& x = h->xformers[xi++];
         const int C = x.c, H = c.num_heads, dh = C / H;
         const std::string b = x.p + ".transformer_blocks.0";
-        float* sc = ar.get<float>((size_t)B * C); float* sh = ar.get<float>((size_t)B * C);
         const SplitBuf sx = Builder::view(SP_X, TL, C), satt = Builder::view(SP_ATT, TL, C), sff = Builder::view(SP_FF, TL, 4 * C),
                        sh2 = Builder::view(SP_H, TL, C);
         auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
-        bld.emit_gn(cur, C, C, nullptr, 0, 0, TL, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
-        bld.emit_prep(cur, C, nullptr, 0, TL, TL, PREP_AFFINE, sc, sh, sx);
+        bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
         { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.proj_in); }
         bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
         { GemmOp g = lin(x.qkv, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; bld.emit_gemm(g, x.qkv); }
@@ -691,7 +717,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
           g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
         float* outp = next_out(followed_by_push(pi), rows * C);
-        { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C; bld.emit_gemm(g, x.proj_out); }
+        { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
+          cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.proj_out); }
         cur = outp;
         bld.emit_tap(x.p, cur, o.level, C, TL);
         break;
@@ -710,6 +737,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const int ie = bld.add_src(g, ev), io = bld.add_src(g, od);
         bld.seg(g, io, 0, s.c, -1); bld.seg(g, ie, 0, s.c, 0); bld.seg(g, io, 0, s.c, 0);
         g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        cur_st = new_stats(s.c); with_stats(g, cur_st, s.c);
         bld.emit_gemm(g, s.w);
         cur = outp;
         bld.emit_tap(s.p, cur, o.level, s.c, TL);
@@ -733,6 +761,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         GemmOp g = bld.gemm_base(s.w, TL);
         bld.conv3(g, up);
         g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
+        cur_st = new_stats(s.c); with_stats(g, cur_st, s.c);
         bld.emit_gemm(g, s.w);
         cur = outp;
         bld.emit_tap(s.p, cur, o.level, s.c, TL);
@@ -742,10 +771,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   }
   // output head: GN -> SiLU -> conv_out, stored channel-major [B, out_channels, T]
   {
-    float* sc = ar.get<float>((size_t)B * c0); float* sh = ar.get<float>((size_t)B * c0);
     const SplitBuf a_h = Builder::view(SP_H, T, c0);
-    bld.emit_gn(cur, c0, c0, nullptr, 0, 0, T, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, sc, sh, gn_acc, gn_cnt);
-    bld.emit_prep(cur, c0, nullptr, 0, T, T, PREP_AFFINE_SILU, sc, sh, a_h);
+    bld.emit_prep_gn(cur, c0, cur_st, nullptr, 0, nullptr, T, PREP_AFFINE_SILU, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, a_h);
     GemmOp g = bld.gemm_base(h->conv_out, T);
     bld.conv3(g, a_h);
     g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
@@ -811,6 +838,11 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         PrepOp p = l.prep;
         if (l.patch == 5) p.src1 = prompt;
         rc = launch_prep_split(p, st);
+        break;
+      }
+      case Launch::MEMSET: {
+        cudaError_t e = cudaMemsetAsync(l.mem, 0, l.mem_bytes, st);
+        if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = -2; }
         break;
       }
       case Launch::POOL_CLS: rc = launch_pool_class_token(l.a, l.b, h->pB, l.i0, l.i1, l.o, st); break;
@@ -1015,11 +1047,11 @@ int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {
   h->profiling = on != 0;
   return 0;
 }
-int ns2vc_profile_num_kinds(void) { return 11; }
+int ns2vc_profile_num_kinds(void) { return 12; }
 const char* ns2vc_profile_kind_name(int k) {
   static const char* names[] = {"gemm_tc", "attention", "gn_affine", "ln_split", "ln_apply", "small_linear", "nct_to_split",
-                               "pool_class_token", "pool_attend", "mask_bias", "prep_split"};
-  return (k >= 0 && k < 11) ? names[k] : "";
+                               "pool_class_token", "pool_attend", "mask_bias", "prep_split", "memset"};
+  return (k >= 0 && k < 12) ? names[k] : "";
 }
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches) {
   NS_REQUIRE(h && ms_total && launches, "null argument");

@@ -129,6 +129,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       const float v = epi_value(op, b, m, n, acc[i][j], accg[i][j]);
       if (op.flags & EPI_OUT_NCT) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = v;
       if (op.flags & EPI_OUT_F32) op.out[m * op.out_ld + n] = v;
+      if (op.flags & EPI_STATS) {
+        atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)v);
+        atomicAdd(op.stat_sq + (long long)b * op.n_valid + n, (double)v * (double)v);
+      }
       if (op.flags & EPI_OUT_SPLIT) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         op.out_hi[m * op.out_split_ld + n] = h;

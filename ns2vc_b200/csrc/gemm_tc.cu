@@ -22,6 +22,7 @@
 //              fp32 token-major, fp32 channel-major, or bf16 hi/lo split for the next GEMM
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
+#include "launch.cuh"
 #include <cuda.h>
 
 namespace ns2vc {
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  pdl_trigger();
+  pdl_wait();                                               // inputs of this GEMM come from the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,9 +217,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         float acc[32];
         tmem_ld32(trow + (uint32_t)(cc * 32), acc);
         const int nbase = n0 + cc * 32;
-        if (!mv || nbase >= op.n_valid) continue;
+        if (nbase >= op.n_valid) continue;                 // (uniform across the warp)
+        if (!mv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        }
         const bool fullc = nbase + 32 <= op.n_valid;
-        if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+        if (!mv) {
+        } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
           if (op.flags & EPI_BIAS) {
             const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
@@ -231,7 +239,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
         }
-        store_chunk(op, b, t, m, nbase, acc);
+        if (mv) store_chunk(op, b, t, m, nbase, acc);
+        if (op.flags & EPI_STATS) {
+          // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
+          // transpose through shared memory (the pipeline stages are idle now), one column per lane.
+          float* sm = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = mv ? acc[j] : 0.f;
+          __syncwarp();
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) { const float v = sm[rr * 33 + lane]; cs += v; cq += v * v; }
+          const int n = nbase + lane;
+          if (n < op.n_valid) {
+            atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)cs);
+            atomicAdd(op.stat_sq + (long long)b * op.n_valid + n, (double)cq);
+          }
+        }
       }
     }
   }
@@ -294,8 +319,7 @@ static int launch_bn(const GemmOp& op, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(op.B * ceil_div(op.T_out, BM), op.N / BN_);
-  gemm_tc_kernel<BN_><<<grid, kThreads, Cfg::kSmemBytes, st>>>(op);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(gemm_tc_kernel<BN_>, grid, dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }

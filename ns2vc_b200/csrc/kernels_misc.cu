@@ -2,6 +2,7 @@
 // statistics, the timestep/FiLM GEMV, AttentionPooling pieces, and the fused sampler updates.
 // All are coalesced/vectorised; none is worth tensor cores.
 #include "gemm_common.cuh"
+#include "launch.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <math.h>
@@ -93,6 +94,8 @@ int launch_tokens_to_nct(const float* x, int ld, int B, int C, int T, float* out
 // Reference: nn.GroupNorm (biased variance) resnet.py:536,557, transformer_1d.py:134.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gn_affine_kernel(GnOp op, int nsplit) {
+  pdl_trigger();
+  pdl_wait();
   const int bg = blockIdx.x;
   const int b = bg / op.G, g = bg % op.G;
   const int C = op.C1 + op.C2;
@@ -175,7 +178,7 @@ int launch_gn_affine(const GnOp& op, cudaStream_t st) {
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 64) nsplit = 64;
   dim3 grid(op.B * op.G, nsplit);
-  gn_affine_kernel<<<grid, 128, 0, st>>>(op, nsplit);
+  launch_k(gn_affine_kernel, grid, dim3(128), 0, st, op, nsplit);
   NS_LAUNCH_CHECK();
   return 0;
 }
@@ -225,14 +228,61 @@ int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float
 // the downsample convs, nearest-upsample index table).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
   const int C = op.C1 + op.C2;
+  const int b = blockIdx.y;
+  const bool affine = op.mode != PREP_RAW;
+  if (affine) {
+    if (op.scale) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) { aff[c] = op.scale[(long long)b * C + c]; aff[C + c] = op.shift[(long long)b * C + c]; }
+    } else {
+      // GroupNorm finalise from the per-channel sums the producer epilogues accumulated
+      // (reference nn.GroupNorm: biased variance over T x C/G elements; resnet.py:536,557, transformer_1d.py:134)
+      const GnStats& g = op.gn;
+      const int cpg = C / g.G;
+      float* gmean = aff + 2 * C;                        // [G] mean | [G] rstd
+      for (int grp = threadIdx.x >> 5; grp < g.G; grp += blockDim.x >> 5) {
+        double s = 0, q = 0;
+        for (int i = threadIdx.x & 31; i < cpg; i += 32) {
+          const int c = grp * cpg + i;
+          s += (c < op.C1) ? g.sum1[(long long)b * op.C1 + c] : g.sum2[(long long)b * op.C2 + (c - op.C1)];
+          q += (c < op.C1) ? g.sq1[(long long)b * op.C1 + c] : g.sq2[(long long)b * op.C2 + (c - op.C1)];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if ((threadIdx.x & 31) == 0) {
+          const double cnt = (double)op.T_src * cpg;
+          const double mean = s / cnt;
+          double var = q / cnt - mean * mean;
+          if (var < 0) var = 0;
+          gmean[grp] = (float)mean;
+          gmean[g.G + grp] = (float)(1.0 / sqrt(var + (double)g.eps));
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int grp = c / cpg;
+        float ga = g.gamma[c] * gmean[g.G + grp];
+        float be = g.beta[c] - gmean[grp] * ga;
+        if (g.film) {
+          const float fs = 1.f + g.film[(long long)b * g.film_ld + c];
+          const float fb = g.film[(long long)b * g.film_ld + C + c];
+          ga = ga * fs;
+          be = be * fs + fb;
+        }
+        aff[c] = ga;
+        aff[C + c] = be;
+      }
+    }
+    __syncthreads();
+  }
   const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
-  const long long total = (long long)op.B * op.T_dst * chunks;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ck = (int)(i % chunks);
-    const long long row = i / chunks;
-    const int t = (int)(row % op.T_dst);
-    const int b = (int)(row / op.T_dst);
+  const int total = op.T_dst * chunks;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ck = i % chunks;
+    const int t = i / chunks;
     const int c0 = ck * 8;
     const int ts = op.rowmap ? __ldg(op.rowmap + t) : t * op.row_mul + op.row_add;
     float v[8];
@@ -264,12 +314,12 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
       *reinterpret_cast<uint4*>(op.raw.hi + orow * op.raw.ld + c0) = hi;
       *reinterpret_cast<uint4*>(op.raw.lo + orow * op.raw.ld + c0) = lo;
     }
-    if (op.mode != PREP_RAW && rowok) {
+    if (affine && rowok) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
         if (c < C) {
-          float y = fmaf(v[j], __ldg(op.scale + (long long)b * C + c), __ldg(op.shift + (long long)b * C + c));
+          float y = fmaf(v[j], aff[c], aff[C + c]);
           if (op.mode == PREP_AFFINE_SILU) y = silu_f(y);
           v[j] = y;
         }
@@ -283,12 +333,17 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
 }
 int launch_prep_split(const PrepOp& op, cudaStream_t st) {
   if ((op.out.ld & 7) || (op.raw.hi && op.raw.ld != op.out.ld)) { set_error("prep_split: bad pitch"); return -1; }
-  const long long total = (long long)op.B * op.T_dst * (op.out.ld >> 3);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  prep_split_kernel<<<blocks, 256, 0, st>>>(op);
-  NS_LAUNCH_CHECK();
+  const int C = op.C1 + op.C2;
+  if (op.mode != PREP_RAW && !op.scale && (C % op.gn.G)) { set_error("prep_split: %d channels not divisible by %d groups", C, op.gn.G); return -1; }
+  const int total = op.T_dst * (op.out.ld >> 3);
+  int bx = (total + 255) / 256;
+  const int cap = (148 * 8 + op.B - 1) / op.B;           // ~8 blocks per SM over the whole grid
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  const size_t smem = (op.mode != PREP_RAW) ? (size_t)(2 * C + 2 * 64) * sizeof(float) : 0;
+  if (smem > 48 * 1024) { set_error("prep_split: C=%d too large", C); return -1; }
+  cudaError_t e = launch_k(prep_split_kernel, dim3(bx, op.B), dim3(256), smem, st, op);
+  if (e != cudaSuccess) { set_error("prep_split launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
@@ -296,6 +351,8 @@ int launch_prep_split(const PrepOp& op, cudaStream_t st) {
 __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, int ld, int M, int C, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        SplitBuf out) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -355,13 +412,15 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
 int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta, SplitBuf out,
                     cudaStream_t st) {
   if (C > 1024 || (out.ld & 7) || out.ld > 1024) { set_error("ln_split: C=%d / pitch %d unsupported", C, out.ld); return -1; }
-  ln_split_kernel<<<ceil_div(M, 8), 256, 0, st>>>(x, ld, M, C, eps, gamma, beta, out);
+  launch_k(ln_split_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, st, x, ld, M, C, eps, gamma, beta, out);
   NS_LAUNCH_CHECK();
   return 0;
 }
 
 // [B, C, T] fp32 -> split token-major [B, T, out.ld]; 32x32 smem transpose, zero-fills c >= C.
 __global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstride, int C, int T, SplitBuf out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -384,7 +443,7 @@ __global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstri
 }
 int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st) {
   dim3 grid(ceil_div(T, 32), ceil_div(out.ld, 32), B), block(32, 8);
-  nct_to_split_kernel<<<grid, block, 0, st>>>(x, bstride, C, T, out);
+  launch_k(nct_to_split_kernel, grid, block, 0, st, x, bstride, C, T, out);
   NS_LAUNCH_CHECK();
   return 0;
 }
@@ -396,6 +455,8 @@ int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, 
 // ---------------------------------------------------------------------------------------------
 constexpr int kLinRows = 8;
 __global__ void __launch_bounds__(256) small_linear_kernel(LinOp op) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xs[];   // [kLinRows][K]
   const int m0 = blockIdx.y * kLinRows;
   const int rows = min(kLinRows, op.M - m0);
@@ -452,7 +513,7 @@ int launch_small_linear(const LinOp& op, cudaStream_t st) {
   size_t smem = (size_t)kLinRows * op.K * sizeof(float);
   if (smem > 48 * 1024) { set_error("small_linear: K=%d too large", op.K); return -1; }
   dim3 grid(ceil_div(op.N, 8), ceil_div(op.M, kLinRows));
-  small_linear_kernel<<<grid, 256, smem, st>>>(op);
+  launch_k(small_linear_kernel, grid, dim3(256), smem, st, op);
   NS_LAUNCH_CHECK();
   return 0;
 }
@@ -543,6 +604,8 @@ __device__ __forceinline__ float x0_round_trip(float x, float o, float alpha, fl
 __global__ void __launch_bounds__(256) dpm_step_kernel(const float* __restrict__ x, const float* __restrict__ o,
                                                        const float* __restrict__ mp, DpmStepCoef c,
                                                        float* __restrict__ mc, float* __restrict__ xn, size_t n) {
+  pdl_trigger();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -562,7 +625,7 @@ int launch_dpm_step(const float* x, const float* unet_out, const float* m_prev, 
                     float* x_next, size_t n, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  dpm_step_kernel<<<blocks, 256, 0, st>>>(x, unet_out, m_prev, c, m_cur, x_next, n);
+  launch_k(dpm_step_kernel, dim3(blocks), dim3(256), 0, st, x, unet_out, m_prev, c, m_cur, x_next, n);
   NS_LAUNCH_CHECK();
   return 0;
 }
@@ -572,6 +635,8 @@ __global__ void __launch_bounds__(256) unipc_step_kernel(const float* __restrict
                                                          const float* __restrict__ m1p, UniPcStepCoef c,
                                                          float* __restrict__ mt_out, float* __restrict__ xt_out,
                                                          float* __restrict__ xpred_out, size_t n) {
+  pdl_trigger();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -611,7 +676,7 @@ int launch_unipc_step(const float* x_prev, const float* x_eval, const float* une
                       cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  unipc_step_kernel<<<blocks, 256, 0, st>>>(x_prev, x_eval, unet_out, m0, m1, c, m_t, x_t, x_pred, n);
+  launch_k(unipc_step_kernel, dim3(blocks), dim3(256), 0, st, x_prev, x_eval, unet_out, m0, m1, c, m_t, x_t, x_pred, n);
   NS_LAUNCH_CHECK();
   return 0;
 }

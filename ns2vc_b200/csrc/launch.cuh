@@ -1,0 +1,35 @@
+// Programmatic dependent launch (PDL): every kernel of the step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, fires griddepcontrol.launch_dependents at its
+// top and executes griddepcontrol.wait before its first access to global memory.  The next
+// kernel's launch latency and prologue (barrier init, TMEM alloc, descriptor fetch) then overlap the
+// tail of the current one; correctness is unchanged because `wait` returns only after the
+// prerequisite grid has completed and its writes are visible.  NS2VC_PDL=0 disables it.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdlib>
+#include <utility>
+
+namespace ns2vc {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NS2VC_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace ns2vc
