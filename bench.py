@@ -251,9 +251,10 @@ def main():
     L = _lib.lib()
     h = unet.engine(dev)
 
+    from ns2vc_b200.fused import get_session
+
     def run_device():
-        sess = DenoiserSession(unet, content_d, prompt_d, mask_d)
-        sess.prepare()
+        sess = get_session(unet, content_d, prompt_d, mask_d)
         out = sess.sample_dpmpp_2m(x_d, ns, ts)
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)

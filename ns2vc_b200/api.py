@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from .fused import DenoiserSession
+from .fused import get_session
 from .schedule import NoiseScheduleVP
 from .synth import linear_betas
 from .unet import UNet1DConditionModel
@@ -49,7 +49,7 @@ def sample_latents(unet: UNet1DConditionModel, x_T: torch.Tensor, content_TBC: t
     mask = None
     if prompt_lengths is not None:
         mask = sequence_mask(prompt_lengths.to(dev, non_blocking=nb), prompt_SBC.shape[0])
-    sess = DenoiserSession(unet, content, prompt, mask)
+    sess = get_session(unet, content, prompt, mask)
     t_T, t_0 = ns.T, 1.0 / ns.total_N
     if skip_type != "time_uniform":
         raise ValueError("sample_latents supports skip_type='time_uniform' (the reference's setting)")

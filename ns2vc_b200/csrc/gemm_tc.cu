@@ -37,7 +37,7 @@ template <int BN_> struct TileCfg {
   static constexpr int BN = BN_;
   static constexpr int kBTileBytes = BN_ * BK * 2;      // one bf16 [BN x 64] B tile (hi or lo)
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-  static constexpr int kStages = (BN_ == 128) ? 3 : 4;
+  static constexpr int kStages = (BN_ == 128) ? 3 : 2;     // BN=64: 98 KB -> two CTAs per SM overlap each other's prologue/epilogue
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = BN_;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
@@ -88,7 +88,7 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
 }
 
 template <int BN_>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
+__global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
   constexpr int kStages = Cfg::kStages;
@@ -119,8 +119,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2 * op.nsrc; ++i) prefetch_tmap(&op.tmap[i]);
+  }
   pdl_trigger();
-  pdl_wait();                                               // inputs of this GEMM come from the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -129,23 +131,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // The weights do not depend on the previous kernel: their first stages are in flight before
+      // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
+      const int npre = nkb < kStages ? nkb : kStages;
+      for (int kb = 0; kb < npre; ++kb) {
+        const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
+        mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+        const size_t eoff = ((size_t)kb * op.N + n0) * 64;
+        bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(kb));
+        bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
+      }
+      pdl_wait();
       int si = 0, kbl = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % kStages;
         const uint32_t parity = (uint32_t)((kb / kStages) & 1);
-        mbar_wait(empty_bar(stage), parity ^ 1u);
         const GSeg& s = op.seg[si];
         const uint32_t a_hi = base + stage * kStageBytes;
         const uint32_t a_lo = a_hi + kATileBytes;
         const uint32_t b_hi = a_lo + kATileBytes;
         const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
-        mbar_arrive_expect_tx(full_bar(stage), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+        if (kb >= npre) {
+          mbar_wait(empty_bar(stage), parity ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+          const size_t eoff = ((size_t)kb * op.N + n0) * 64;
+          bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
+          bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
+        }
         const int c = s.c0 + kbl * 64;
         tma_load_3d(a_hi, &op.tmap[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
         tma_load_3d(a_lo, &op.tmap[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
-        const size_t eoff = ((size_t)kb * op.N + n0) * 64;
-        bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
-        bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
         if (++kbl == s.nkb) { kbl = 0; ++si; }
       }
     }
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    pdl_wait();                                             // residual reads / output writes follow the previous kernel
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access

@@ -57,6 +57,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const TMap* tmap, int 
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_tmap(const TMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem_addr, uint32_t cols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

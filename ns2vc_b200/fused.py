@@ -22,7 +22,13 @@ from .unet import UNet1DConditionModel, trace_calls
 
 
 class DenoiserSession:
-    """One utterance batch on one GPU: UNet engine + prepared conditioning + sampler buffers."""
+    """One utterance-batch shape (B, T, S) on one GPU: UNet engine, static input buffers, prepared
+    conditioning and (optionally) the whole sampling loop captured as one CUDA graph.
+
+    The C calls are stream-ordered and allocation-free, so the N-step loop (prepare_cond + N x (UNet
+    forward + fused sampler step), ~335 kernels per step linked by programmatic dependent launch) is
+    captured once per (sampler, steps) and replayed; new inputs are copied into the static buffers.
+    ``NS2VC_GRAPH=0`` disables the capture (eager launches)."""
 
     def __init__(self, unet: UNet1DConditionModel, content_BCT: Optional[torch.Tensor], prompt_BSC: torch.Tensor,
                  prompt_mask: Optional[torch.Tensor], T: Optional[int] = None):
@@ -31,23 +37,37 @@ class DenoiserSession:
         self.unet = unet
         self.dev = prompt_BSC.device
         self.B, self.S = prompt_BSC.shape[0], prompt_BSC.shape[1]
-        Cc = unet.cfg.in_channels - unet.latent_channels
-        if Cc > 0:
-            if content_BCT is None or content_BCT.shape[1] != Cc:
-                raise ValueError(f"content must be [B, {Cc}, T]")
+        self.Cc = unet.cfg.in_channels - unet.latent_channels
+        if self.Cc > 0:
+            if content_BCT is None or content_BCT.shape[1] != self.Cc:
+                raise ValueError(f"content must be [B, {self.Cc}, T]")
             self.T = content_BCT.shape[2]
-            self.content = content_BCT.to(torch.float32).contiguous()
         else:
             if T is None:
                 raise ValueError("T is required when the model has no content channels")
             self.T = T
-            self.content = None
-        self.prompt = prompt_BSC.to(torch.float32).contiguous()
-        self.mask = prompt_mask.to(torch.bool).to(torch.uint8).contiguous() if prompt_mask is not None else None
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.content = torch.empty((self.B, self.Cc, self.T), **f32) if self.Cc > 0 else None
+        self.prompt = torch.empty((self.B, self.S, unet.cfg.cross_attention_dim), **f32)
+        self.mask = torch.empty((self.B, self.S), dtype=torch.uint8, device=self.dev) if prompt_mask is not None else None
         self.L = _lib.lib()
         self.h = unet.engine(self.dev)
         self.ws = unet.workspace(self.B, self.T, self.S, self.dev)
         self.Cl, self.Co = unet.latent_channels, unet.cfg.out_channels
+        self.x_in = torch.empty((self.B, self.Cl, self.T), **f32)
+        self._graphs = {}
+        self._wsig = unet._wsig
+        self.set_cond(content_BCT, prompt_BSC, prompt_mask)
+
+    def set_cond(self, content_BCT, prompt_BSC, prompt_mask):
+        """Copy a new utterance batch (same shapes) into the static buffers."""
+        if self.content is not None:
+            self.content.copy_(content_BCT, non_blocking=True)
+        self.prompt.copy_(prompt_BSC, non_blocking=True)
+        if (prompt_mask is None) != (self.mask is None):
+            raise ValueError("mask presence must not change within a session")
+        if self.mask is not None:
+            self.mask.copy_(prompt_mask.to(torch.bool), non_blocking=True)
         self._prepared = False
 
     def _stream(self):
@@ -57,7 +77,7 @@ class DenoiserSession:
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ns2vc_unet_prepare_cond(
                 self.h, self.content.data_ptr() if self.content is not None else None,
-                (self.content.shape[1] * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
+                (self.Cc * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
                 self.mask.data_ptr() if self.mask is not None else None, self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
         self._prepared = True
 
@@ -69,22 +89,12 @@ class DenoiserSession:
             _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
                                                  self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
 
-    # ------------------------------------------------------------------ DPM-Solver++(2M)
-    def sample_dpmpp_2m(self, x_T: torch.Tensor, ns, ts: torch.Tensor, lower_order_final: bool = True,
-                        first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """DPM-Solver++ multistep order 2 over time points ``ts`` (N+1 values), x_start model.
-        Equivalent to reference DPM_Solver.sample(method='multistep', order=2) (dpm_solver.py:1171-1213)."""
-        assert self.Cl == self.Co, "x_start parameterisation needs out_channels == latent channels"
-        table = coefs.dpmpp_2m_table(ns, ts, lower_order_final)
-        B, dev = self.B, self.dev
-        tvals = torch.tensor([[st.t_input] * B for st in table], dtype=torch.float32).to(dev, non_blocking=True)
-        x = x_T.to(torch.float32).clone(memory_format=torch.contiguous_format)   # never write the caller's tensor
+    # ------------------------------------------------------------------ loop bodies (eager or under capture)
+    def _loop_dpm(self, table, tvals, first_out=None):
+        x = self.x_in.clone()
         n = x.numel()
-        x_next = torch.empty_like(x)
-        out = torch.empty_like(x)
+        x_next, out = torch.empty_like(x), torch.empty_like(x)
         m_a, m_b = torch.empty_like(x), torch.empty_like(x)
-        if not self._prepared:
-            self.prepare()
         stream = self._stream()
         for k, st in enumerate(table):
             if k == 0 and first_out is not None:
@@ -92,41 +102,31 @@ class DenoiserSession:
             else:
                 self.forward(x, tvals[k], out)
             c = _lib.DpmCoef(st.alpha_s, st.sigma_s, st.c_x, st.c_m, st.c_d, st.inv_r0, st.order)
-            with torch.cuda.device(dev):
+            with torch.cuda.device(self.dev):
                 _lib.check(self.L.ns2vc_dpm_step(x.data_ptr(), out.data_ptr(), m_b.data_ptr(), C.byref(c), m_a.data_ptr(),
                                                  x_next.data_ptr(), n, stream))
             x, x_next = x_next, x
             m_a, m_b = m_b, m_a
         return x
 
-    # ------------------------------------------------------------------ UniPC-bh2
-    def sample_unipc(self, x_T: torch.Tensor, ns, ts: torch.Tensor, variant: str = "bh2",
-                     first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """UniPC multistep order 2, data prediction, lower_order_final (uni_pc.py:606-658)."""
-        assert self.Cl == self.Co
-        table = coefs.unipc_bh2_table(ns, ts, variant)
-        B, dev = self.B, self.dev
-        tvals = torch.tensor([[st.t_input] * B for st in table], dtype=torch.float32).to(dev, non_blocking=True)
-        n = x_T.numel()
-        x_prev = x_T.to(torch.float32).contiguous()      # x at the previous time point (corrector base); never written
-        x_eval = x_prev                                   # where the model is evaluated
+    def _loop_unipc(self, table, tvals, first_out=None):
+        x_prev = self.x_in                                 # x at the previous time point (corrector base); never written
+        x_eval = x_prev                                    # where the model is evaluated
+        n = x_prev.numel()
         out = torch.empty_like(x_prev)
         m0 = m1 = None
-        if not self._prepared:
-            self.prepare()
         stream = self._stream()
         for k, st in enumerate(table):
             if k == 0 and first_out is not None:
                 out.copy_(first_out)
             else:
                 self.forward(x_eval, tvals[k], out)
-            # fresh outputs every step (caching allocator: no sync, stream-ordered reuse)
             m_t = torch.empty_like(x_prev)
             x_t = torch.empty_like(x_prev) if st.corr_order > 0 else None
             x_pred = torch.empty_like(x_prev)
             c = _lib.UniPcCoef(st.alpha_t, st.sigma_t, st.c_x, st.c_m, st.ab, st.rk, st.rho0, st.rho1, st.corr_order,
                                st.n_c_x, st.n_c_m, st.nab, st.nrk, st.pred_order)
-            with torch.cuda.device(dev):
+            with torch.cuda.device(self.dev):
                 _lib.check(self.L.ns2vc_unipc_step(
                     x_prev.data_ptr(), x_eval.data_ptr(), out.data_ptr(), m0.data_ptr() if m0 is not None else None,
                     m1.data_ptr() if m1 is not None else None, C.byref(c), m_t.data_ptr(),
@@ -136,6 +136,74 @@ class DenoiserSession:
             x_prev = x_t if x_t is not None else x_eval
             x_eval = x_pred
         return x_eval
+
+    def _run(self, kind, x_T, ns, ts, first_out, extra):
+        assert self.Cl == self.Co, "x_start parameterisation needs out_channels == latent channels"
+        if self.unet._wsig != self._wsig:                  # weights were re-packed: captured graphs are stale
+            self._graphs.clear()
+            self.h = self.unet.engine(self.dev)
+            self._wsig = self.unet._wsig
+            self._prepared = False
+        self.x_in.copy_(x_T, non_blocking=True)
+        loop = self._loop_dpm if kind == "dpm" else self._loop_unipc
+        key = (kind, tuple(float(v) for v in ts), extra, id(ns))
+        use_graph = os.environ.get("NS2VC_GRAPH", "1") != "0"
+        ent = self._graphs.get(key)
+        if ent is None:
+            table = coefs.dpmpp_2m_table(ns, ts, extra) if kind == "dpm" else coefs.unipc_bh2_table(ns, ts, extra)
+            tvals = torch.tensor([[st.t_input] * self.B for st in table], dtype=torch.float32).to(self.dev)
+            ent = {"table": table, "tvals": tvals, "graph": None, "out": None, "warm": False}
+            self._graphs[key] = ent
+        if not use_graph:
+            if not self._prepared:
+                self.prepare()
+            return loop(ent["table"], ent["tvals"], first_out)
+        if ent["graph"] is None:
+            if not ent["warm"]:
+                # first run eagerly: builds the launch program, sets kernel attributes, warms the allocator
+                self.prepare()
+                res = loop(ent["table"], ent["tvals"], first_out)
+                ent["warm"] = True
+                return res
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.prepare()
+                ent["out"] = loop(ent["table"], ent["tvals"], None)
+            ent["graph"] = g
+        ent["graph"].replay()
+        self._prepared = True
+        return ent["out"].clone()
+
+    # ------------------------------------------------------------------ public samplers
+    def sample_dpmpp_2m(self, x_T: torch.Tensor, ns, ts: torch.Tensor, lower_order_final: bool = True,
+                        first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """DPM-Solver++ multistep order 2 over time points ``ts`` (N+1 values), x_start model.
+        Equivalent to reference DPM_Solver.sample(method='multistep', order=2) (dpm_solver.py:1171-1213)."""
+        return self._run("dpm", x_T, ns, ts, first_out, bool(lower_order_final))
+
+    def sample_unipc(self, x_T: torch.Tensor, ns, ts: torch.Tensor, variant: str = "bh2",
+                     first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """UniPC multistep order 2, data prediction, lower_order_final (uni_pc.py:606-658)."""
+        return self._run("unipc", x_T, ns, ts, first_out, variant)
+
+
+def get_session(unet: UNet1DConditionModel, content_BCT, prompt_BSC, prompt_mask, T=None) -> DenoiserSession:
+    """Session cache per (B, T, S, mask?) on the module: captured graphs and static buffers are reused
+    across utterance batches of the same shape."""
+    B, S = prompt_BSC.shape[0], prompt_BSC.shape[1]
+    Tn = content_BCT.shape[2] if content_BCT is not None else T
+    key = (B, Tn, S, prompt_mask is not None, str(prompt_BSC.device))
+    cache = unet.__dict__.setdefault("_sessions", {})
+    sess = cache.get(key)
+    if sess is None or sess.h != unet.engine(prompt_BSC.device) or sess.ws.data_ptr() != unet.workspace(B, Tn, S, prompt_BSC.device).data_ptr():
+        if len(cache) > 4:
+            cache.clear()
+        sess = DenoiserSession(unet, content_BCT, prompt_BSC, prompt_mask, T=T)
+        cache[key] = sess
+    else:
+        sess.set_cond(content_BCT, prompt_BSC, prompt_mask)
+    return sess
 
 
 def _fast_path_enabled() -> bool:
@@ -177,7 +245,7 @@ def _session_from_record(r) -> DenoiserSession:
     u = r.unet
     Cl = u.latent_channels
     content = r.sample[:, Cl:] if r.sample.shape[1] > Cl else None
-    return DenoiserSession(u, content, r.ehs, r.mask, T=r.sample.shape[2])
+    return get_session(u, content, r.ehs, r.mask, T=r.sample.shape[2])
 
 
 def try_fused_dpm(solver, x, steps, skip_type, t_T, t_0):

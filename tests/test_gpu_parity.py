@@ -202,12 +202,21 @@ def test_fused_samplers_tiny_vs_reference_fixture(gold):
     inp = tiny_inputs()
     ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
     sess = _session(m, inp)
-    out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 13))
-    ok, msg = close(out, g["dpmpp2m_12"])
-    assert ok, msg
-    out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 9))
-    ok, msg = close(out, g["unipc_bh2_8"])
-    assert ok, msg
+    outs = []
+    for i in range(3):          # 1st call eager, 2nd captures the CUDA graph, 3rd replays it
+        out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 13))
+        ok, msg = close(out, g["dpmpp2m_12"])
+        assert ok, f"call {i}: {msg}"
+        outs.append(out)
+    assert torch.equal(outs[1], outs[2]), "graph replay must reproduce the captured run"
+    # new inputs through the same captured graph
+    x2 = torch.randn_like(outs[0])
+    a = sess.sample_dpmpp_2m(x2, ns, torch.linspace(1.0, 1e-3, 13))
+    assert not torch.allclose(a, outs[2])
+    for i in range(3):
+        out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 9))
+        ok, msg = close(out, g["unipc_bh2_8"])
+        assert ok, f"unipc call {i}: {msg}"
 
 
 def test_fused_dpm_50_steps_full_model_vs_oracle(full_model):
