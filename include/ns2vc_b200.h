@@ -115,6 +115,8 @@ const char* ns2vc_build_info(void);
 /* Per-kernel-kind device timing (CUDA events around every launch on the caller's stream); used by
  * bench.py for the roofline line.  Off by default; never enable inside a timed region. */
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
+/* In-kernel %globaltimer stamps (8 per GEMM launch, CTA (0,0)) of the next forwards; NULL disables. */
+int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
 int ns2vc_profile_num_kinds(void);
 const char* ns2vc_profile_kind_name(int kind);
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches);

@@ -110,6 +110,7 @@ struct GemmOp {
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
+  unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
 };
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).

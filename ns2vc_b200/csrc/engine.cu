@@ -118,6 +118,7 @@ struct ns2vc_unet {
   std::vector<float*> tap_dst;
   int last_launches = 0;
   bool profiling = false;
+  unsigned long long* trace = nullptr; int trace_cap = 0;
   struct ProfRec { int kind; cudaEvent_t a, b; int M, N, K, nseg, ctas; };
   std::vector<ProfRec> prof;
 
@@ -791,7 +792,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 
 int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long long x_bstride, const float* t, float* out,
                 const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
-  int rc = 0, count = 0;
+  int rc = 0, count = 0, gemm_idx = 0;
   for (auto& l : prog) {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     const bool prof = h->profiling && l.kind != Launch::TAP;
@@ -801,8 +802,11 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
     }
     switch (l.kind) {
       case Launch::GEMM: {
-        if (l.patch == 3) {
-          GemmOp g = l.gemm; g.out = out;
+        if (l.patch == 3 || h->trace) {
+          GemmOp g = l.gemm;
+          if (l.patch == 3) g.out = out;
+          if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 8 * gemm_idx;
+          ++gemm_idx;
           rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
         } else {
           rc = h->simt ? launch_gemm_simt(l.gemm, st) : launch_gemm_tc(l.gemm, st);
@@ -1040,6 +1044,11 @@ int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* leve
 int ns2vc_unet_set_tap(ns2vc_unet* h, int i, float* dst) {
   NS_REQUIRE(h && i >= 0 && i < (int)h->tap_dst.size(), "tap index %d out of range", i);
   h->tap_dst[i] = dst;
+  return 0;
+}
+int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* dbuf, int n_gemms) {
+  NS_REQUIRE(h, "null handle");
+  h->trace = dbuf; h->trace_cap = n_gemms;
   return 0;
 }
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {

@@ -37,7 +37,7 @@ template <int BN_> struct TileCfg {
   static constexpr int BN = BN_;
   static constexpr int kBTileBytes = BN_ * BK * 2;      // one bf16 [BN x 64] B tile (hi or lo)
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-  static constexpr int kStages = (BN_ == 128) ? 3 : 2;     // BN=64: 98 KB -> two CTAs per SM overlap each other's prologue/epilogue
+  static constexpr int kStages = (BN_ == 128) ? 3 : 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = BN_;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
@@ -87,8 +87,11 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
   }
 }
 
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
+
 template <int BN_>
-__global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
   constexpr int kStages = Cfg::kStages;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
   const int t0 = (blockIdx.x % tiles_per_batch) * BM;
   const int n0 = blockIdx.y * BN;                           // first packed column of this tile
   const int nkb = op.nkb_total;
+  if (tid == 0) TRACE(0);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) TRACE(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -142,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
         bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
       }
       pdl_wait();
+      TRACE(2);
       int si = 0, kbl = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % kStages;
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
         const int stage = kb % kStages;
         const uint32_t parity = (uint32_t)((kb / kStages) & 1);
         mbar_wait(full_bar(stage), parity);
+        if (kb == 0) TRACE(3);
         tc_fence_after();
         const uint32_t a_hi = base + stage * kStageBytes;
         const uint32_t a_lo = a_hi + kATileBytes;
@@ -187,11 +194,13 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
         umma_commit(empty_bar(stage));                      // frees this smem stage when the MMAs retire
       }
       umma_commit(tmem_full_bar);                           // accumulator complete -> epilogue
+      TRACE(4);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     pdl_wait();                                             // residual reads / output writes follow the previous kernel
     mbar_wait(tmem_full_bar, 0);
+    if (warp == 2 && lane == 0) TRACE(5);
     tc_fence_after();
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
@@ -277,8 +286,10 @@ __global__ void __launch_bounds__(kThreads, (BN_ == 64) ? 2 : 1) gemm_tc_kernel(
     }
   }
 
+  if (warp == 2 && lane == 0) TRACE(6);
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TRACE(7);
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
