@@ -199,15 +199,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ===================== epilogue (warps 2..5) =====================
     pdl_wait();                                             // residual reads / output writes follow the previous kernel
-    mbar_wait(tmem_full_bar, 0);
-    if (warp == 2 && lane == 0) TRACE(5);
-    tc_fence_after();
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const int t = t0 + r;
     const bool mv = t < op.T_out;
     const long long m = (long long)b * op.T_out + t;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // pull this thread's residual row and the bias into L1 while the main loop runs
+    if (mv && (op.flags & EPI_RESIDUAL)) {
+      const char* pr = reinterpret_cast<const char*>(op.res + m * op.res_ld + n0);
+#pragma unroll
+      for (int i = 0; i < BN * 4 / 128; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + i * 128));
+    }
+    if ((op.flags & (EPI_BIAS | EPI_GEGLU)) && lane < BN * 4 / 128)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(op.bias + n0) + lane * 128));
+    mbar_wait(tmem_full_bar, 0);
+    if (warp == 2 && lane == 0) TRACE(5);
+    tc_fence_after();
     if (op.flags & EPI_GEGLU) {
       if (BN == 128) {
 #pragma unroll 1
@@ -237,50 +245,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
     } else {
+      float* sm_stat = reinterpret_cast<float*>(smem);      // [4 warps][32x33] transpose scratch | [4][BN][2] partials
+      float* sm_part = sm_stat + 4 * 32 * 33;
 #pragma unroll 1
       for (int cc = 0; cc < BN / 32; ++cc) {
         float acc[32];
         tmem_ld32(trow + (uint32_t)(cc * 32), acc);
         const int nbase = n0 + cc * 32;
-        if (nbase >= op.n_valid) continue;                 // (uniform across the warp)
-        if (!mv) {
+        const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
+        if (cvalid && mv) {
+          const bool fullc = nbase + 32 <= op.n_valid;
+          if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+            if (op.flags & EPI_BIAS) {
+              const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-        }
-        const bool fullc = nbase + 32 <= op.n_valid;
-        if (!mv) {
-        } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
-          if (op.flags & EPI_BIAS) {
-            const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+            }
+            if (op.flags & EPI_RESIDUAL) {
+              const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
           }
-          if (op.flags & EPI_RESIDUAL) {
-            const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
+          store_chunk(op, b, t, m, nbase, acc);
         }
-        if (mv) store_chunk(op, b, t, m, nbase, acc);
         if (op.flags & EPI_STATS) {
           // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
-          // transpose through shared memory (the pipeline stages are idle now), one column per lane.
-          float* sm = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+          // transpose through shared memory (the pipeline stages are idle now), one column per lane;
+          // the four warps' partials are combined below so each column costs one atomic per CTA.
+          float* sm = sm_stat + (warp - 2) * (32 * 33);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = mv ? acc[j] : 0.f;
+          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = (mv && cvalid) ? acc[j] : 0.f;
           __syncwarp();
           float cs = 0.f, cq = 0.f;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) { const float v = sm[rr * 33 + lane]; cs += v; cq += v * v; }
-          const int n = nbase + lane;
-          if (n < op.n_valid) {
-            atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)cs);
-            atomicAdd(op.stat_sq + (long long)b * op.n_valid + n, (double)cq);
-          }
+          sm_part[((warp - 2) * BN + cc * 32 + lane) * 2] = cs;
+          sm_part[((warp - 2) * BN + cc * 32 + lane) * 2 + 1] = cq;
+        }
+      }
+      if (op.flags & EPI_STATS) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+        const int col = tid - 64;                           // 0..127
+        if (col < BN && n0 + col < op.n_valid) {
+          double cs = 0, cq = 0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { cs += (double)sm_part[(w * BN + col) * 2]; cq += (double)sm_part[(w * BN + col) * 2 + 1]; }
+          atomicAdd(op.stat_sum + (long long)b * op.n_valid + n0 + col, cs);
+          atomicAdd(op.stat_sq + (long long)b * op.n_valid + n0 + col, cq);
         }
       }
     }

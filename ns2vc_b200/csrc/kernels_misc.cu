@@ -227,14 +227,77 @@ int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float
 // row (two 16-byte loads, 16-byte hi + lo stores); rows may be remapped (stride-2 decimation for
 // the downsample convs, nearest-upsample index table).
 // ---------------------------------------------------------------------------------------------
+struct PrepChunk { float v[8]; int t, c0; bool rowok; };
+
+__device__ __forceinline__ void prep_load(const PrepOp& op, int b, int C, int chunks, int i, PrepChunk& k) {
+  const int ck = i % chunks;
+  k.t = i / chunks;
+  k.c0 = ck * 8;
+  const int ts = op.rowmap ? __ldg(op.rowmap + k.t) : k.t * op.row_mul + op.row_add;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k.v[j] = 0.f;
+  k.rowok = ts >= 0 && ts < op.T_src;
+  if (k.rowok && k.c0 < C) {
+    const int c0 = k.c0;
+    const bool in1 = c0 < op.C1;
+    const float* p = in1 ? op.src1 + ((long long)b * op.T_src + ts) * op.ld1 + c0
+                         : op.src2 + ((long long)b * op.T_src + ts) * op.ld2 + (c0 - op.C1);
+    const int lim = in1 ? op.C1 - c0 : C - c0;             // channels left in this source
+    const int ldx = in1 ? op.ld1 : op.ld2;
+    if (lim >= 8 && ((ldx | (in1 ? c0 : c0 - op.C1)) & 3) == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = c4.x; k.v[5] = c4.y; k.v[6] = c4.z; k.v[7] = c4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        if (c < C) k.v[j] = (c < op.C1) ? op.src1[((long long)b * op.T_src + ts) * op.ld1 + c]
+                                        : op.src2[((long long)b * op.T_src + ts) * op.ld2 + (c - op.C1)];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void prep_finish(const PrepOp& op, int b, int C, const float* aff, PrepChunk& k) {
+  const long long orow = (long long)b * op.T_dst + k.t;
+  if (op.raw.hi) {
+    uint4 hi, lo;
+    split8(k.v, hi, lo);
+    *reinterpret_cast<uint4*>(op.raw.hi + orow * op.raw.ld + k.c0) = hi;
+    *reinterpret_cast<uint4*>(op.raw.lo + orow * op.raw.ld + k.c0) = lo;
+  }
+  if (op.mode != PREP_RAW && k.rowok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = k.c0 + j;
+      if (c < C) {
+        float y = fmaf(k.v[j], aff[c], aff[C + c]);
+        if (op.mode == PREP_AFFINE_SILU) y = silu_f(y);
+        k.v[j] = y;
+      }
+    }
+  }
+  uint4 hi, lo;
+  split8(k.v, hi, lo);
+  *reinterpret_cast<uint4*>(op.out.hi + orow * op.out.ld + k.c0) = hi;
+  *reinterpret_cast<uint4*>(op.out.lo + orow * op.out.ld + k.c0) = lo;
+}
+
 __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
   const int C = op.C1 + op.C2;
   const int b = blockIdx.y;
-  const bool affine = op.mode != PREP_RAW;
-  if (affine) {
+  const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
+  const int total = op.T_dst * chunks;
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // the first chunk's loads are in flight while the block derives the GroupNorm affine
+  PrepChunk k0;
+  const bool have = i < total;
+  if (have) prep_load(op, b, C, chunks, i, k0);
+  if (op.mode != PREP_RAW) {
     if (op.scale) {
       for (int c = threadIdx.x; c < C; c += blockDim.x) { aff[c] = op.scale[(long long)b * C + c]; aff[C + c] = op.shift[(long long)b * C + c]; }
     } else {
@@ -245,20 +308,20 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
       float* gmean = aff + 2 * C;                        // [G] mean | [G] rstd
       for (int grp = threadIdx.x >> 5; grp < g.G; grp += blockDim.x >> 5) {
         double s = 0, q = 0;
-        for (int i = threadIdx.x & 31; i < cpg; i += 32) {
-          const int c = grp * cpg + i;
+        for (int ii = threadIdx.x & 31; ii < cpg; ii += 32) {
+          const int c = grp * cpg + ii;
           s += (c < op.C1) ? g.sum1[(long long)b * op.C1 + c] : g.sum2[(long long)b * op.C2 + (c - op.C1)];
           q += (c < op.C1) ? g.sq1[(long long)b * op.C1 + c] : g.sq2[(long long)b * op.C2 + (c - op.C1)];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
         if ((threadIdx.x & 31) == 0) {
-          const double cnt = (double)op.T_src * cpg;
-          const double mean = s / cnt;
-          double var = q / cnt - mean * mean;
+          const double inv = 1.0 / ((double)op.T_src * cpg);
+          const double mean = s * inv;
+          double var = q * inv - mean * mean;
           if (var < 0) var = 0;
           gmean[grp] = (float)mean;
-          gmean[g.G + grp] = (float)(1.0 / sqrt(var + (double)g.eps));
+          gmean[g.G + grp] = rsqrtf((float)var + g.eps);
         }
       }
       __syncthreads();
@@ -278,57 +341,11 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
     }
     __syncthreads();
   }
-  const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
-  const int total = op.T_dst * chunks;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int ck = i % chunks;
-    const int t = i / chunks;
-    const int c0 = ck * 8;
-    const int ts = op.rowmap ? __ldg(op.rowmap + t) : t * op.row_mul + op.row_add;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    const bool rowok = ts >= 0 && ts < op.T_src;
-    if (rowok && c0 < C) {
-      const bool in1 = c0 < op.C1;
-      const float* p = in1 ? op.src1 + ((long long)b * op.T_src + ts) * op.ld1 + c0
-                           : op.src2 + ((long long)b * op.T_src + ts) * op.ld2 + (c0 - op.C1);
-      const int lim = in1 ? op.C1 - c0 : C - c0;           // channels left in this source
-      const int ldx = in1 ? op.ld1 : op.ld2;
-      if (lim >= 8 && ((ldx | (in1 ? c0 : c0 - op.C1)) & 3) == 0) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = c0 + j;
-          if (c < C) v[j] = (c < op.C1) ? op.src1[((long long)b * op.T_src + ts) * op.ld1 + c]
-                                        : op.src2[((long long)b * op.T_src + ts) * op.ld2 + (c - op.C1)];
-        }
-      }
-    }
-    const long long orow = (long long)b * op.T_dst + t;
-    if (op.raw.hi) {
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(op.raw.hi + orow * op.raw.ld + c0) = hi;
-      *reinterpret_cast<uint4*>(op.raw.lo + orow * op.raw.ld + c0) = lo;
-    }
-    if (affine && rowok) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        if (c < C) {
-          float y = fmaf(v[j], aff[c], aff[C + c]);
-          if (op.mode == PREP_AFFINE_SILU) y = silu_f(y);
-          v[j] = y;
-        }
-      }
-    }
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    *reinterpret_cast<uint4*>(op.out.hi + orow * op.out.ld + c0) = hi;
-    *reinterpret_cast<uint4*>(op.out.lo + orow * op.out.ld + c0) = lo;
+  if (have) prep_finish(op, b, C, aff, k0);
+  for (i += stride; i < total; i += stride) {
+    PrepChunk k;
+    prep_load(op, b, C, chunks, i, k);
+    prep_finish(op, b, C, aff, k);
   }
 }
 int launch_prep_split(const PrepOp& op, cudaStream_t st) {
