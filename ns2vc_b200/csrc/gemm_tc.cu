@@ -266,20 +266,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         float cs = 0.f, cq = 0.f;
         if (nv) {
           const long long mrow0 = (long long)b * op.T_out + row0;
-#pragma unroll 4
-          for (int rr = 0; rr < nrows; ++rr) {
-            float v = sm_t[rr * 33 + lane] + bias_v;
-            if (geglu) v *= gelu_erf_f(sm_t[32 * 33 + rr * 33 + lane] + bias_g);
-            const long long mm = mrow0 + rr;
-            if (op.flags & EPI_RESIDUAL) v += __ldg(op.res + mm * op.res_ld + n);
-            if (op.flags & EPI_OUT_F32) op.out[mm * op.out_ld + n] = v;
-            if (op.flags & EPI_OUT_SPLIT) {
-              const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-              op.out_hi[mm * op.out_split_ld + n] = hb;
-              op.out_lo[mm * op.out_split_ld + n] = __float2bfloat16_rn(v - __bfloat162float(hb));
+          float resv[32];
+          if (op.flags & EPI_RESIDUAL) {                    // all 32 row loads in flight at once (128 B coalesced each)
+            const float* pr = op.res + mrow0 * op.res_ld + n;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) resv[rr] = (rr < nrows) ? __ldg(pr + (long long)rr * op.res_ld) : 0.f;
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < nrows) {
+              float v = sm_t[rr * 33 + lane] + bias_v;
+              if (geglu) v *= gelu_erf_f(sm_t[32 * 33 + rr * 33 + lane] + bias_g);
+              const long long mm = mrow0 + rr;
+              if (op.flags & EPI_RESIDUAL) v += resv[rr];
+              if (op.flags & EPI_OUT_F32) op.out[mm * op.out_ld + n] = v;
+              if (op.flags & EPI_OUT_SPLIT) {
+                const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+                op.out_hi[mm * op.out_split_ld + n] = hb;
+                op.out_lo[mm * op.out_split_ld + n] = __float2bfloat16_rn(v - __bfloat162float(hb));
+              }
+              cs += v;
+              cq += v * v;
             }
-            cs += v;
-            cq += v * v;
           }
         }
         if (op.flags & EPI_STATS) {
