@@ -29,7 +29,7 @@ namespace ns2vc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;                            // two per SMSP: the epilogue is issue-latency bound
 constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kATileBytes = BM * BK * 2;                // 16 KB: one bf16 [128 x 64] A tile (hi or lo)
 
@@ -216,87 +216,80 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) TRACE(5);
     tc_fence_after();
-    // Every chunk (32 rows x 32 columns per warp) is transposed through shared memory (the pipeline
-    // stages are idle now) so that a lane owns one COLUMN: bias / residual reads and all stores are
-    // then 128-byte coalesced per row, and the GroupNorm column sums fall out of the same loop.
-    float* sm_t = reinterpret_cast<float*>(smem) + (warp - 2) * (2 * 32 * 33);   // value | gate scratch of this warp
-    float* sm_part = reinterpret_cast<float*>(smem) + 4 * (2 * 32 * 33);          // [4][BN][2] stats partials
-    const int row0 = t0 + q * 32;                           // first row of this warp
-    const int nrows = min(32, op.T_out - row0);             // valid rows (may be <= 0)
-    if (op.flags & EPI_OUT_NCT) {
-      // channel-major output (conv_out): thread = row keeps the stores coalesced along t
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        float acc[32];
-        tmem_ld32(trow + (uint32_t)(cc * 32), acc);
-        const int nbase = n0 + cc * 32;
-        if (mv && nbase < op.n_valid) {
+    if (op.flags & EPI_GEGLU) {
+      if (BN == 128) {
+        {
+          const int hh = (warp - 2) >> 2;                   // the two warps of a lane quarter take one half each
+          float val[32], gate[32];
+          tmem_ld32(trow + (uint32_t)(hh * 32), val);
+          tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
+          const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
+          if (mv) {
+            if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
+              const float4* bv = reinterpret_cast<const float4*>(op.bias + nbase);
+              const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nbase);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = epi_value(op, b, m, n, acc[j], 0.f);
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = __ldg(bv + j), y = __ldg(bg + j);
+                val[4 * j + 0] = (val[4 * j + 0] + x.x) * gelu_erf_f(gate[4 * j + 0] + y.x);
+                val[4 * j + 1] = (val[4 * j + 1] + x.y) * gelu_erf_f(gate[4 * j + 1] + y.y);
+                val[4 * j + 2] = (val[4 * j + 2] + x.z) * gelu_erf_f(gate[4 * j + 2] + y.z);
+                val[4 * j + 3] = (val[4 * j + 3] + x.w) * gelu_erf_f(gate[4 * j + 3] + y.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
+            }
+            store_chunk(op, b, t, m, nbase, val);
           }
         }
       }
     } else {
-      const bool geglu = (op.flags & EPI_GEGLU) != 0;
-      const int nchunks = geglu ? BN / 64 : BN / 32;
+      float* sm_stat = reinterpret_cast<float*>(smem);      // [8 warps][32x33] transpose scratch | [4 quarters][BN][2] partials
+      float* sm_part = sm_stat + 8 * 32 * 33;
 #pragma unroll 1
-      for (int cc = 0; cc < nchunks; ++cc) {
+      for (int cc = (warp - 2) >> 2; cc < BN / 32; cc += 2) {   // the two warps of a lane quarter alternate chunks
         float acc[32];
         tmem_ld32(trow + (uint32_t)(cc * 32), acc);
-        __syncwarp();
+        const int nbase = n0 + cc * 32;
+        const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
+        if (cvalid && mv) {
+          const bool fullc = nbase + 32 <= op.n_valid;
+          if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+            if (op.flags & EPI_BIAS) {
+              const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sm_t[lane * 33 + j] = acc[j];
-        if (geglu) {
-          tmem_ld32(trow + (uint32_t)(64 + cc * 32), acc);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sm_t[32 * 33 + lane * 33 + j] = acc[j];
-        }
-        __syncwarp();
-        // logical output column of this lane
-        const int n = (geglu ? blockIdx.y * 64 : n0) + cc * 32 + lane;
-        const bool nv = n < op.n_valid;
-        float bias_v = 0.f, bias_g = 0.f;
-        if (nv) {
-          if (geglu) { bias_v = __ldg(op.bias + n); bias_g = __ldg(op.bias + op.n_valid + n); }
-          else if (op.flags & EPI_BIAS) bias_v = __ldg(op.bias + n);
-          if (op.flags & EPI_ROWBIAS) bias_v += __ldg(op.rowbias + (long long)b * op.rowbias_ld + n);
-        }
-        float cs = 0.f, cq = 0.f;
-        if (nv) {
-          const long long mrow0 = (long long)b * op.T_out + row0;
-          float resv[32];
-          if (op.flags & EPI_RESIDUAL) {                    // all 32 row loads in flight at once (128 B coalesced each)
-            const float* pr = op.res + mrow0 * op.res_ld + n;
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) resv[rr] = (rr < nrows) ? __ldg(pr + (long long)rr * op.res_ld) : 0.f;
-          }
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < nrows) {
-              float v = sm_t[rr * 33 + lane] + bias_v;
-              if (geglu) v *= gelu_erf_f(sm_t[32 * 33 + rr * 33 + lane] + bias_g);
-              const long long mm = mrow0 + rr;
-              if (op.flags & EPI_RESIDUAL) v += resv[rr];
-              if (op.flags & EPI_OUT_F32) op.out[mm * op.out_ld + n] = v;
-              if (op.flags & EPI_OUT_SPLIT) {
-                const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-                op.out_hi[mm * op.out_split_ld + n] = hb;
-                op.out_lo[mm * op.out_split_ld + n] = __float2bfloat16_rn(v - __bfloat162float(hb));
-              }
-              cs += v;
-              cq += v * v;
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
             }
+            if (op.flags & EPI_RESIDUAL) {
+              const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
           }
+          store_chunk(op, b, t, m, nbase, acc);
         }
         if (op.flags & EPI_STATS) {
-          sm_part[((warp - 2) * BN + cc * 32 + lane) * 2] = cs;
-          sm_part[((warp - 2) * BN + cc * 32 + lane) * 2 + 1] = cq;
+          // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
+          // transpose through shared memory (the pipeline stages are idle now), one column per lane;
+          // the four warps' partials are combined below so each column costs one atomic per CTA.
+          float* sm = sm_stat + (warp - 2) * (32 * 33);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = (mv && cvalid) ? acc[j] : 0.f;
+          __syncwarp();
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) { const float v = sm[rr * 33 + lane]; cs += v; cq += v * v; }
+          sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
+          sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
         }
       }
       if (op.flags & EPI_STATS) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
         const int col = tid - 64;                           // 0..127
         if (col < BN && n0 + col < op.n_valid) {
           double cs = 0, cq = 0;
