@@ -116,6 +116,14 @@ struct ns2vc_unet {
   std::vector<int*> rowmaps;                              // device index tables owned by the program
   std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch;
   std::vector<float*> tap_dst;
+  // Inactive programs (other (B,T,S,workspace) keys, e.g. the sub-batch lanes of a multi-stream sampler):
+  // the fields above are the ACTIVE program; activate() swaps them with an entry of this list.
+  struct Stash {
+    int pB, pT, pS; void* pws; bool has_mask, cond_ready;
+    std::vector<Launch> prog_cond, prog_fwd; std::vector<int*> rowmaps;
+    std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch; std::vector<float*> tap_dst;
+  };
+  std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
   unsigned long long* trace = nullptr; int trace_cap = 0;
@@ -877,10 +885,46 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
   return 0;
 }
 
+void stash_active(ns2vc_unet* h) {
+  if (!h->pws) return;
+  ns2vc_unet::Stash s;
+  s.pB = h->pB; s.pT = h->pT; s.pS = h->pS; s.pws = h->pws; s.has_mask = h->has_mask; s.cond_ready = h->cond_ready;
+  s.prog_cond = std::move(h->prog_cond); s.prog_fwd = std::move(h->prog_fwd); s.rowmaps = std::move(h->rowmaps);
+  s.tap_names = std::move(h->tap_names); s.tap_level = std::move(h->tap_level); s.tap_ch = std::move(h->tap_ch); s.tap_dst = std::move(h->tap_dst);
+  h->prog_cond.clear(); h->prog_fwd.clear(); h->rowmaps.clear(); h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear(); h->tap_dst.clear();
+  h->pB = h->pT = h->pS = 0; h->pws = nullptr; h->cond_ready = false;
+  if (h->stash.size() >= 16) {                       // bounded: drop the oldest program
+    for (int* p : h->stash.front().rowmaps) cudaFree(p);
+    h->stash.erase(h->stash.begin());
+  }
+  h->stash.push_back(std::move(s));
+}
+
+void drop_all_programs(ns2vc_unet* h) {
+  for (int* p : h->rowmaps) cudaFree(p);
+  h->rowmaps.clear();
+  for (auto& s : h->stash) for (int* p : s.rowmaps) cudaFree(p);
+  h->stash.clear();
+  h->prog_cond.clear(); h->prog_fwd.clear();
+  h->pB = h->pT = h->pS = 0; h->pws = nullptr; h->cond_ready = false;
+}
+
+// Make the program for (B,T,S,ws) the active one; returns 1 if it already existed, 0 if built now.
 int ensure_program(ns2vc_unet* h, int B, int T, int S, void* ws, cudaStream_t st) {
   NS_REQUIRE(h->finalized, "ns2vc_unet_finalize() has not been called");
   NS_REQUIRE(ws != nullptr, "workspace is NULL");
   if (h->pB == B && h->pT == T && h->pS == S && h->pws == ws) return 0;
+  stash_active(h);
+  for (size_t i = 0; i < h->stash.size(); ++i) {
+    ns2vc_unet::Stash& s = h->stash[i];
+    if (s.pB == B && s.pT == T && s.pS == S && s.pws == ws) {
+      h->pB = s.pB; h->pT = s.pT; h->pS = s.pS; h->pws = s.pws; h->has_mask = s.has_mask; h->cond_ready = s.cond_ready;
+      h->prog_cond = std::move(s.prog_cond); h->prog_fwd = std::move(s.prog_fwd); h->rowmaps = std::move(s.rowmaps);
+      h->tap_names = std::move(s.tap_names); h->tap_level = std::move(s.tap_level); h->tap_ch = std::move(s.tap_ch); h->tap_dst = std::move(s.tap_dst);
+      h->stash.erase(h->stash.begin() + i);
+      return 0;
+    }
+  }
   return build_programs(h, B, T, S, ws, nullptr, st);
 }
 
@@ -941,7 +985,7 @@ void ns2vc_unet_destroy(ns2vc_unet* h) {
   if (!h) return;
   for (auto& w : h->weights) if (w.d) cudaFree(w.d);
   for (void* p : h->owned) cudaFree(p);
-  for (int* p : h->rowmaps) cudaFree(p);
+  drop_all_programs(h);
   delete h;
 }
 
@@ -976,7 +1020,7 @@ int ns2vc_unet_finalize(ns2vc_unet* h, ns2vc_stream stream) {
   // (re)pack: drop previous packed buffers
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear(); h->resnets.clear(); h->xformers.clear(); h->resamplers.clear();
-  h->pB = h->pT = h->pS = 0; h->pws = nullptr;
+  drop_all_programs(h);
   int rc = pack_all(h, (cudaStream_t)stream);
   if (rc) return rc;
   h->finalized = true;
@@ -1006,8 +1050,9 @@ int ns2vc_unet_prepare_cond(ns2vc_unet* h, const float* content, long long conte
 int ns2vc_unet_forward(ns2vc_unet* h, const float* x, long long x_bstride, const float* t, float* out, int B, int T, int S, void* ws,
                        ns2vc_stream stream) {
   NS_REQUIRE(h && x && t && out, "null argument");
-  NS_REQUIRE(h->pB == B && h->pT == T && h->pS == S && h->pws == ws && h->cond_ready,
-             "ns2vc_unet_prepare_cond() must be called with the same (B,T,S,workspace) before forward");
+  int rc0 = ensure_program(h, B, T, S, ws, (cudaStream_t)stream);
+  if (rc0) return rc0;
+  NS_REQUIRE(h->cond_ready, "ns2vc_unet_prepare_cond() must be called with the same (B,T,S,workspace) before forward");
   return run_program(h, h->prog_fwd, x, x_bstride, t, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 

@@ -52,9 +52,25 @@ class DenoiserSession:
         self.mask = torch.empty((self.B, self.S), dtype=torch.uint8, device=self.dev) if prompt_mask is not None else None
         self.L = _lib.lib()
         self.h = unet.engine(self.dev)
-        self.ws = unet.workspace(self.B, self.T, self.S, self.dev)
         self.Cl, self.Co = unet.latent_channels, unet.cfg.out_channels
         self.x_in = torch.empty((self.B, self.Cl, self.T), **f32)
+        # Lanes: the utterances of a batch are independent, and every kernel of the step is a short
+        # dependent-latency chain that leaves most SMs idle, so the batch is cut into sub-batches whose
+        # whole sampling loops run concurrently on separate streams (own workspace + launch program each,
+        # shared packed weights).  NS2VC_LANES=1 disables the split.
+        want = int(os.environ.get("NS2VC_LANES", "2"))
+        n_lanes = max(1, min(want, self.B))
+        while self.B % n_lanes:
+            n_lanes -= 1
+        per = self.B // n_lanes
+        self.lanes = []
+        for g in range(n_lanes):
+            n = C.c_size_t()
+            _lib.check(self.L.ns2vc_unet_workspace_bytes(self.h, per, self.T, self.S, C.byref(n)))
+            self.lanes.append(dict(sl=slice(g * per, (g + 1) * per), B=per,
+                                   ws=torch.empty(int(n.value), dtype=torch.uint8, device=self.dev),
+                                   stream=torch.cuda.Stream(device=self.dev) if n_lanes > 1 else None))
+        self.ws = self.lanes[0]["ws"]
         self._graphs = {}
         self._wsig = unet._wsig
         self.set_cond(content_BCT, prompt_BSC, prompt_mask)
@@ -73,44 +89,56 @@ class DenoiserSession:
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def prepare(self):
+    def _prepare_lane(self, lane):
+        sl = lane["sl"]
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ns2vc_unet_prepare_cond(
-                self.h, self.content.data_ptr() if self.content is not None else None,
-                (self.Cc * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
-                self.mask.data_ptr() if self.mask is not None else None, self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+                self.h, self.content[sl].data_ptr() if self.content is not None else None,
+                (self.Cc * self.T) if self.content is not None else 0, self.prompt[sl].data_ptr(),
+                self.mask[sl].data_ptr() if self.mask is not None else None, lane["B"], self.T, self.S, lane["ws"].data_ptr(), self._stream()))
+
+    def _forward_lane(self, lane, x, t, out):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
+                                                 lane["B"], self.T, self.S, lane["ws"].data_ptr(), self._stream()))
+
+    def prepare(self):
+        for lane in self.lanes:
+            self._prepare_lane(lane)
         self._prepared = True
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor):
         """x [B,Cl,T] fp32 contiguous, t [B] fp32, out [B,Co,T] fp32 — all on the session device."""
         if not self._prepared:
             self.prepare()
-        with torch.cuda.device(self.dev):
-            _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
-                                                 self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+        for lane in self.lanes:
+            sl = lane["sl"]
+            self._forward_lane(lane, x[sl], t[sl], out[sl])
 
     # ------------------------------------------------------------------ loop bodies (eager or under capture)
-    def _loop_dpm(self, table, tvals, first_out=None):
-        x = self.x_in.clone()
+    def _lane_dpm(self, lane, table, tvals, first_out, result):
+        sl = lane["sl"]
+        x = self.x_in[sl].clone()
         n = x.numel()
         x_next, out = torch.empty_like(x), torch.empty_like(x)
         m_a, m_b = torch.empty_like(x), torch.empty_like(x)
         stream = self._stream()
         for k, st in enumerate(table):
             if k == 0 and first_out is not None:
-                out.copy_(first_out)
+                out.copy_(first_out[sl])
             else:
-                self.forward(x, tvals[k], out)
+                self._forward_lane(lane, x, tvals[k][sl], out)
             c = _lib.DpmCoef(st.alpha_s, st.sigma_s, st.c_x, st.c_m, st.c_d, st.inv_r0, st.order)
             with torch.cuda.device(self.dev):
                 _lib.check(self.L.ns2vc_dpm_step(x.data_ptr(), out.data_ptr(), m_b.data_ptr(), C.byref(c), m_a.data_ptr(),
                                                  x_next.data_ptr(), n, stream))
             x, x_next = x_next, x
             m_a, m_b = m_b, m_a
-        return x
+        result[sl].copy_(x)
 
-    def _loop_unipc(self, table, tvals, first_out=None):
-        x_prev = self.x_in                                 # x at the previous time point (corrector base); never written
+    def _lane_unipc(self, lane, table, tvals, first_out, result):
+        sl = lane["sl"]
+        x_prev = self.x_in[sl]                             # x at the previous time point (corrector base); never written
         x_eval = x_prev                                    # where the model is evaluated
         n = x_prev.numel()
         out = torch.empty_like(x_prev)
@@ -118,9 +146,9 @@ class DenoiserSession:
         stream = self._stream()
         for k, st in enumerate(table):
             if k == 0 and first_out is not None:
-                out.copy_(first_out)
+                out.copy_(first_out[sl])
             else:
-                self.forward(x_eval, tvals[k], out)
+                self._forward_lane(lane, x_eval, tvals[k][sl], out)
             m_t = torch.empty_like(x_prev)
             x_t = torch.empty_like(x_prev) if st.corr_order > 0 else None
             x_pred = torch.empty_like(x_prev)
@@ -135,7 +163,27 @@ class DenoiserSession:
             m1, m0 = m0, m_t
             x_prev = x_t if x_t is not None else x_eval
             x_eval = x_pred
-        return x_eval
+        result[sl].copy_(x_eval)
+
+    def _loop(self, kind, table, tvals, first_out=None):
+        """prepare_cond + the N-step loop of every lane; lanes run concurrently on their own streams."""
+        body = self._lane_dpm if kind == "dpm" else self._lane_unipc
+        result = torch.empty_like(self.x_in)
+        cur = torch.cuda.current_stream(self.dev)
+        for lane in self.lanes:
+            if lane["stream"] is None:
+                self._prepare_lane(lane)
+                body(lane, table, tvals, first_out, result)
+            else:
+                lane["stream"].wait_stream(cur)
+                with torch.cuda.stream(lane["stream"]):
+                    self._prepare_lane(lane)
+                    body(lane, table, tvals, first_out, result)
+        for lane in self.lanes:
+            if lane["stream"] is not None:
+                cur.wait_stream(lane["stream"])
+        self._prepared = True
+        return result
 
     def _run(self, kind, x_T, ns, ts, first_out, extra):
         assert self.Cl == self.Co, "x_start parameterisation needs out_channels == latent channels"
@@ -145,7 +193,6 @@ class DenoiserSession:
             self._wsig = self.unet._wsig
             self._prepared = False
         self.x_in.copy_(x_T, non_blocking=True)
-        loop = self._loop_dpm if kind == "dpm" else self._loop_unipc
         key = (kind, tuple(float(v) for v in ts), extra, id(ns))
         use_graph = os.environ.get("NS2VC_GRAPH", "1") != "0"
         ent = self._graphs.get(key)
@@ -155,21 +202,17 @@ class DenoiserSession:
             ent = {"table": table, "tvals": tvals, "graph": None, "out": None, "warm": False}
             self._graphs[key] = ent
         if not use_graph:
-            if not self._prepared:
-                self.prepare()
-            return loop(ent["table"], ent["tvals"], first_out)
+            return self._loop(kind, ent["table"], ent["tvals"], first_out)
         if ent["graph"] is None:
             if not ent["warm"]:
-                # first run eagerly: builds the launch program, sets kernel attributes, warms the allocator
-                self.prepare()
-                res = loop(ent["table"], ent["tvals"], first_out)
+                # first run eagerly: builds the launch programs, sets kernel attributes, warms the allocator
+                res = self._loop(kind, ent["table"], ent["tvals"], first_out)
                 ent["warm"] = True
                 return res
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.prepare()
-                ent["out"] = loop(ent["table"], ent["tvals"], None)
+                ent["out"] = self._loop(kind, ent["table"], ent["tvals"], None)
             ent["graph"] = g
         ent["graph"].replay()
         self._prepared = True
@@ -196,7 +239,7 @@ def get_session(unet: UNet1DConditionModel, content_BCT, prompt_BSC, prompt_mask
     key = (B, Tn, S, prompt_mask is not None, str(prompt_BSC.device))
     cache = unet.__dict__.setdefault("_sessions", {})
     sess = cache.get(key)
-    if sess is None or sess.h != unet.engine(prompt_BSC.device) or sess.ws.data_ptr() != unet.workspace(B, Tn, S, prompt_BSC.device).data_ptr():
+    if sess is None or sess.h != unet.engine(prompt_BSC.device):
         if len(cache) > 4:
             cache.clear()
         sess = DenoiserSession(unet, content_BCT, prompt_BSC, prompt_mask, T=T)
