@@ -142,7 +142,7 @@ constexpr int kOffV = kOffK + 16384;     // V^T hi [64 d][64 keys], lo follows
 constexpr int kOffP = kOffV + 16384;     // P hi [128][64], lo follows
 constexpr int kOffBias = kOffP + 32768;  // 64 floats
 constexpr int kOffBar = kOffBias + 256;
-constexpr int kAttnSmem = kOffBar + 64 + 1024;
+constexpr int kAttnSmem = kOffBar + 64 + 1024 /*row max / row sum exchange*/ + 1024 /*alignment slack*/;
 
 __device__ __forceinline__ void load8(const float* p, bool row_ok, int d0, int dh, bool vec, float* v) {
 #pragma unroll
@@ -248,12 +248,19 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
   constexpr uint32_t idO = umma_idesc_bf16(128, DHP);
   const uint32_t sQ = base + kOffQ, sK = base + kOffK, sV = base + kOffV, sP = base + kOffP;
 
-  float o[DHP];
+  // Softmax on all 8 warps: warp w works on TMEM lane quarter (w & 3); warps 0-3 take score columns
+  // 0-31 and the first half of the head dim, warps 4-7 columns 32-63 and the second half.  The two
+  // threads of a row exchange their partial row maxima through shared memory (one 64-thread named
+  // barrier per tile) and their partial row sums once at the end.
+  constexpr int OH = DHP / 2;                              // output columns per thread
+  float o[OH];
 #pragma unroll
-  for (int d = 0; d < DHP; ++d) o[d] = 0.f;
+  for (int d = 0; d < OH; ++d) o[d] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  const int r = (warp & 3) * 32 + lane;                    // query row / TMEM lane (warps 0-3)
-  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+  const int qtr = warp & 3, hf = warp >> 2;
+  const int r = qtr * 32 + lane;                           // query row / TMEM lane
+  const uint32_t lane_base = ((uint32_t)(qtr * 32)) << 16;
+  float* xch = reinterpret_cast<float*>(smem + kOffBias + 256 + 64);   // [2][128] exchange buffer (after bias + barriers)
   const int ntiles = (op.Tk + AKT - 1) / AKT;
 
   for (int j = 0; j < ntiles; ++j) {
@@ -275,40 +282,32 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
       umma_commit(bar_s);
     }
     if (j + 1 < ntiles) load_kv((j + 1) * AKT);            // global loads overlap the MMA + softmax
-    float corr = 0.f;
-    if (warp < 4) {
-      mbar_wait(bar_s, par);
-      tc_fence_after();
-      float sv[32];
-      float mt = -INFINITY;
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        tmem_ld32(tS + lane_base + hh * 32, sv);
+    mbar_wait(bar_s, par);
+    tc_fence_after();
+    float sv[32];
+    tmem_ld32(tS + lane_base + hf * 32, sv);
+    float mt = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) mt = fmaxf(mt, sv[c] + bias_s[hh * 32 + c]);
-      }
-      const float m_new = fmaxf(m_run, mt);
-      corr = exp2f(m_run - m_new);
-      float lt = 0.f;
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        tmem_ld32(tS + lane_base + hh * 32, sv);
+    for (int c = 0; c < 32; ++c) { sv[c] += bias_s[hf * 32 + c]; mt = fmaxf(mt, sv[c]); }
+    xch[hf * 128 + r] = mt;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qtr) : "memory");          // the two warps of this lane quarter
+    const float m_new = fmaxf(m_run, fmaxf(mt, xch[(hf ^ 1) * 128 + r]));
+    const float corr = exp2f(m_run - m_new);
+    float lt = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { sv[c] = exp2f(sv[c] + bias_s[hh * 32 + c] - m_new); lt += sv[c]; }
+    for (int c = 0; c < 32; ++c) { sv[c] = exp2f(sv[c] - m_new); lt += sv[c]; }
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint4 hi, lo;
-          split8(sv + 8 * c8, hi, lo);
-          const int ck = hh * 4 + c8;
-          const int off = r * 128 + ((ck ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(smem + kOffP + off) = hi;
-          *reinterpret_cast<uint4*>(smem + kOffP + 16384 + off) = lo;
-        }
-      }
-      l_run = l_run * corr + lt;
-      m_run = m_new;
-      fence_proxy_async();
+    for (int c8 = 0; c8 < 4; ++c8) {
+      uint4 hi, lo;
+      split8(sv + 8 * c8, hi, lo);
+      const int ck = hf * 4 + c8;
+      const int off = r * 128 + ((ck ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(smem + kOffP + off) = hi;
+      *reinterpret_cast<uint4*>(smem + kOffP + 16384 + off) = lo;
     }
+    l_run = l_run * corr + lt;
+    m_run = m_new;
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 128) {
@@ -325,44 +324,47 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
     }
     mbar_wait(bar_o, par);                                 // every thread: K / V^T / P smem is free again
     tc_fence_after();
-    if (warp < 4) {
-      float ot[16];
+    {
+      float ot[8];
 #pragma unroll
-      for (int d0 = 0; d0 < DHP; d0 += 16) {
-        tmem_ld16(tO + lane_base + d0, ot);
+      for (int d0 = 0; d0 < OH; d0 += 8) {
+        tmem_ld8(tO + lane_base + hf * OH + d0, ot);
 #pragma unroll
-        for (int d = 0; d < 16; ++d) o[d0 + d] = o[d0 + d] * corr + ot[d];
+        for (int d = 0; d < 8; ++d) o[d0 + d] = o[d0 + d] * corr + ot[d];
       }
     }
   }
 
-  if (warp < 4 && q0 + r < op.Tq) {
-    const float inv = 1.0f / l_run;
+  // total row sum = the two halves' partial sums
+  xch[hf * 128 + r] = l_run;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + qtr) : "memory");
+  const float l_tot = l_run + xch[(hf ^ 1) * 128 + r];
+  if (q0 + r < op.Tq) {
+    const float inv = 1.0f / l_tot;
     const long long orow = (long long)b * op.Tq + q0 + r;
+    const int dbase = hf * OH;                              // first head-dim column of this thread
     if (op.out) {
       float* po = op.out + orow * op.out_ld + h * dh;
-      for (int d = 0; d < dh; ++d) po[d] = o[d] * inv;
+      for (int d = 0; d < OH; ++d) if (dbase + d < dh) po[dbase + d] = o[d] * inv;
     }
     if (op.out_hi) {
-      __nv_bfloat16* ph = op.out_hi + orow * op.out_split_ld + h * dh;
-      __nv_bfloat16* pl = op.out_lo + orow * op.out_split_ld + h * dh;
-      if ((dh & 7) == 0 && ((op.out_split_ld | (h * dh)) & 7) == 0) {
+      __nv_bfloat16* ph = op.out_hi + orow * op.out_split_ld + h * dh + dbase;
+      __nv_bfloat16* pl = op.out_lo + orow * op.out_split_ld + h * dh + dbase;
+      if ((dh & 15) == 0 && ((op.out_split_ld | (h * dh)) & 7) == 0) {
 #pragma unroll
-        for (int d0 = 0; d0 < DHP; d0 += 8) {
-          if (d0 < dh) {
-            float v[8];
+        for (int d0 = 0; d0 < OH; d0 += 8) {
+          float v[8];
 #pragma unroll
-            for (int d = 0; d < 8; ++d) v[d] = o[d0 + d] * inv;
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(ph + d0) = hi;
-            *reinterpret_cast<uint4*>(pl + d0) = lo;
-          }
+          for (int d = 0; d < 8; ++d) v[d] = o[d0 + d] * inv;
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(ph + d0) = hi;
+          *reinterpret_cast<uint4*>(pl + d0) = lo;
         }
       } else {
 #pragma unroll
-        for (int d = 0; d < DHP; ++d)
-          if (d < dh) {
+        for (int d = 0; d < OH; ++d)
+          if (dbase + d < dh) {
             const float v = o[d] * inv;
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             ph[d] = hi;
