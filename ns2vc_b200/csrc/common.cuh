@@ -115,12 +115,12 @@ struct GemmOp {
   // EPI_LN: the A operand is the RAW activation x; with W' = gamma (.) W packed as the B operand,
   //   LN(x) W + bias = rstd_r * (x W' - mu_r * g) + c,   g[n] = sum_k gamma_k W[k,n],  c[n] = sum_k beta_k W[k,n] + bias[n]
   // mu_r / rstd_r come from the per-row sums the producer's epilogue accumulated (EPI_ROWSTATS).
-  const float* ln_rowstats;    // [M, ln_C/32, 2] per-32-column-chunk sum | sum of squares of row m (written by the producer)
+  const double* ln_rowstats;   // [M, 2] sum | sum of squares over the ln_C channels of row m
   const float* ln_g;           // [N] (GEGLU: [2*N_out], value | gate order like bias)
   const float* ln_c;
   float ln_eps;
   int ln_C;
-  float* rowstat_out;          // EPI_ROWSTATS: [M, ceil(n_valid/32), 2]: one slot per 32-column chunk (no atomics, deterministic)
+  double* rowstat_out;         // EPI_ROWSTATS: [M, 2], pre-zeroed
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
 };
 

@@ -600,12 +600,12 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
     else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
-    if (o.kind == PlanOp::XFORMER) stat_doubles += (size_t)3 * B * Tl[o.level] * ((o.cout + 31) / 32);   // LayerNorm row-chunk sums (float2 per slot = 1 double)
+    if (o.kind == PlanOp::XFORMER) stat_doubles += (size_t)3 * 2 * B * Tl[o.level];   // LayerNorm row sums
   }
   double* stat_arena = ar.get<double>(stat_doubles);
   size_t stat_used = 0;
   auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
-  auto new_rowstats = [&](size_t rows, int C) { float* p = stat_arena ? reinterpret_cast<float*>(stat_arena + stat_used) : nullptr; stat_used += rows * ((C + 31) / 32); return p; };
+  auto new_rowstats = [&](size_t rows) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += 2 * rows; return p; };
   auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
   { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
   // activation buffers
@@ -719,10 +719,10 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
                        sh2 = Builder::view(SP_H, TL, C);
         auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
         bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
-        float* rs1 = new_rowstats(rows, C); float* rs2 = new_rowstats(rows, C); float* rs3 = new_rowstats(rows, C);
+        double* rs1 = new_rowstats(rows); double* rs2 = new_rowstats(rows); double* rs3 = new_rowstats(rows);
         const SplitBuf sraw = Builder::view(SP_A, TL, C);   // raw split of the residual stream (LayerNorm is folded into the consumers)
-        auto raw_out = [&](GemmOp& g, float* rs) { g.flags |= EPI_OUT_SPLIT | EPI_ROWSTATS; g.out_hi = sraw.hi; g.out_lo = sraw.lo; g.out_split_ld = sraw.ld; g.rowstat_out = rs; };
-        auto ln_in = [&](GemmOp& g, const float* rs, const float* gv, const float* cv) { g.flags |= EPI_LN; g.ln_rowstats = rs; g.ln_g = gv; g.ln_c = cv; g.ln_eps = 1e-5f; g.ln_C = C; };
+        auto raw_out = [&](GemmOp& g, double* rs) { g.flags |= EPI_OUT_SPLIT | EPI_ROWSTATS; g.out_hi = sraw.hi; g.out_lo = sraw.lo; g.out_split_ld = sraw.ld; g.rowstat_out = rs; };
+        auto ln_in = [&](GemmOp& g, const double* rs, const float* gv, const float* cv) { g.flags |= EPI_LN; g.ln_rowstats = rs; g.ln_g = gv; g.ln_c = cv; g.ln_eps = 1e-5f; g.ln_C = C; };
         { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; raw_out(g, rs1); bld.emit_gemm(g, x.proj_in); }
         { GemmOp g = lin(x.qkv, sraw, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; ln_in(g, rs1, x.g1, x.c1); bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));

@@ -48,14 +48,13 @@ __device__ __forceinline__ float a_fetch_split(const GemmOp& op, const GSeg& s, 
 // Epilogue for one accumulator value at (m = b*T_out + t, logical column n).  For GEGLU the caller
 // passes the value accumulator in `acc` and the gate accumulator in `acc_gate`.
 __device__ __forceinline__ void ln_row_consts(const GemmOp& op, long long m, float& mu, float& rstd) {
-  const int nslots = (op.ln_C + 31) >> 5;
-  const float2* p = reinterpret_cast<const float2*>(op.ln_rowstats) + m * nslots;
-  float s = 0.f, q = 0.f;
-  for (int i = 0; i < nslots; ++i) { const float2 v = __ldg(p + i); s += v.x; q += v.y; }
-  const float inv = 1.0f / (float)op.ln_C;
-  mu = s * inv;
-  const float var = fmaxf(q * inv - mu * mu, 0.f);
-  rstd = rsqrtf(var + op.ln_eps);
+  const double s = op.ln_rowstats[2 * m], q = op.ln_rowstats[2 * m + 1];
+  const double inv = 1.0 / (double)op.ln_C;
+  const double mean = s * inv;
+  double var = q * inv - mean * mean;
+  if (var < 0) var = 0;
+  mu = (float)mean;
+  rstd = rsqrtf((float)var + op.ln_eps);
 }
 
 __device__ __forceinline__ float epi_value(const GemmOp& op, int b, long long m, int n, float acc, float acc_gate) {

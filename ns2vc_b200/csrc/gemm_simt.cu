@@ -156,10 +156,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       const float v = epi_value(op, b, m, n, acc[i][j], accg[i][j]);
       if (op.flags & EPI_OUT_NCT) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = v;
       if (op.flags & EPI_OUT_F32) op.out[m * op.out_ld + n] = v;
-      if (op.flags & EPI_ROWSTATS) {   // debug path: slot = 32-column chunk; pre-zeroed buffer, float atomics
-        const int nslots = (op.n_valid + 31) >> 5;
-        atomicAdd(op.rowstat_out + (m * nslots + (n >> 5)) * 2, v);
-        atomicAdd(op.rowstat_out + (m * nslots + (n >> 5)) * 2 + 1, v * v);
+      if (op.flags & EPI_ROWSTATS) {
+        atomicAdd(op.rowstat_out + 2 * m, (double)v);
+        atomicAdd(op.rowstat_out + 2 * m + 1, (double)v * (double)v);
       }
       if (op.flags & EPI_STATS) {
         atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)v);

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(op.bias + n0) + lane * 128));
     float ln_mu = 0.f, ln_rstd = 1.f;
     if (mv && (op.flags & EPI_LN)) ln_row_consts(op, m, ln_mu, ln_rstd);
+    float rs_sum = 0.f, rs_sq = 0.f;                       // EPI_ROWSTATS partials of this thread's row
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) TRACE(5);
     tc_fence_after();
@@ -299,12 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
           }
           store_chunk(op, b, t, m, nbase, acc);
-          if (op.flags & EPI_ROWSTATS) {                    // this chunk's slot of the row: plain store, no atomics
-            float rs_sum = 0.f, rs_sq = 0.f;
+          if (op.flags & EPI_ROWSTATS) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) { rs_sum += acc[j]; rs_sq += acc[j] * acc[j]; }
-            const int nslots = (op.n_valid + 31) >> 5;
-            *reinterpret_cast<float2*>(op.rowstat_out + (m * nslots + (nbase >> 5)) * 2) = make_float2(rs_sum, rs_sq);
           }
         }
         if (op.flags & EPI_STATS) {
@@ -322,6 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
           sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
         }
+      }
+      if (mv && (op.flags & EPI_ROWSTATS)) {
+        atomicAdd(op.rowstat_out + 2 * m, (double)rs_sum);
+        atomicAdd(op.rowstat_out + 2 * m + 1, (double)rs_sq);
       }
       if (op.flags & EPI_STATS) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
