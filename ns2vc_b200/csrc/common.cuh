@@ -80,8 +80,6 @@ enum EpiFlags : int {
   EPI_OUT_F32 = 32,   // store fp32 token-major out[m*out_ld + n]
   EPI_OUT_SPLIT = 64, // store bf16 hi/lo token-major (feeds the next GEMM's TMA)
   EPI_STATS = 128,    // accumulate per-(b, column) sum / sum-of-squares of the fp32 output (GroupNorm of the consumer)
-  EPI_LN = 256,       // LayerNorm of the A operand folded into the epilogue (see GemmOp::ln_*)
-  EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the output (LayerNorm of the consumer)
 };
 
 struct GemmOp {
@@ -112,15 +110,6 @@ struct GemmOp {
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
-  // EPI_LN: the A operand is the RAW activation x; with W' = gamma (.) W packed as the B operand,
-  //   LN(x) W + bias = rstd_r * (x W' - mu_r * g) + c,   g[n] = sum_k gamma_k W[k,n],  c[n] = sum_k beta_k W[k,n] + bias[n]
-  // mu_r / rstd_r come from the per-row sums the producer's epilogue accumulated (EPI_ROWSTATS).
-  const double* ln_rowstats;   // [M, 2] sum | sum of squares over the ln_C channels of row m
-  const float* ln_g;           // [N] (GEGLU: [2*N_out], value | gate order like bias)
-  const float* ln_c;
-  float ln_eps;
-  int ln_C;
-  double* rowstat_out;         // EPI_ROWSTATS: [M, 2], pre-zeroed
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
 };
 
@@ -143,11 +132,7 @@ struct PackSeg {
   int kb0;            // first k-block in the packed K order
   int nkb;
   int geglu_half;     // 0: plain. >0: interleave value/gate (value rows [0,half), gate rows [half,2*half))
-  const float* kscale; // optional per-input-channel scale [cin_total] (LayerNorm gamma folded into W)
 };
-// g[n] = sum_k gamma[k] W[n,k],  c[n] = sum_k beta[k] W[n,k] + (bias ? bias[n] : 0)   for W [n_rows, K] fp32
-int launch_ln_fold(const float* W, int n_rows, int K, const float* gamma, const float* beta, const float* bias, float* g,
-                   float* c, cudaStream_t st);
 int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, float* w_f32, int Npad,
                   cudaStream_t st);
 

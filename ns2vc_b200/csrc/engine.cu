@@ -58,7 +58,6 @@ struct XformerSite {
   int c;
   PackedB proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
   int kv_off = 0;            // column offset of this block's K|V in the cross K/V cache
-  float *g1 = nullptr, *c1 = nullptr, *g2 = nullptr, *c2 = nullptr, *g3 = nullptr, *c3 = nullptr;   // LayerNorm fold vectors
 };
 struct ConvSite { std::string p; int c; PackedB w; };
 
@@ -283,11 +282,10 @@ int alloc_packed(ns2vc_unet* h, PackedB& pb, int n_logical, int n_packed, int nk
 
 // Pack `w` ([n_rows, cin_total, ktaps]) channels [cin0, cin0+ncin) of tap `tap` at k-block kb0, columns n_dst0..
 int pack_seg(ns2vc_unet* h, PackedB& pb, const std::string& wname, int n_rows, int cin_total, int ktaps, int tap, int cin0,
-             int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st, const float* kscale = nullptr) {
+             int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st) {
   const float* w = h->W(wname);
   NS_REQUIRE(w != nullptr, "pack: weight %s missing", wname.c_str());
-  PackSeg ps{};
-  ps.kscale = kscale;
+  PackSeg ps;
   ps.w = w; ps.n_rows = n_rows; ps.cin_total = cin_total; ps.ktaps = ktaps; ps.tap = tap; ps.cin0 = cin0; ps.ncin = ncin;
   ps.n_dst0 = n_dst0; ps.kb0 = kb0; ps.nkb = nkb_of(ncin); ps.geglu_half = geglu_half;
   return launch_pack_b(ps, pb.hi, pb.lo, pb.f32, pb.Npad, st);
@@ -344,27 +342,17 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
       if ((rc = pack_seg(h, x.proj_in, x.p + ".proj_in.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.qkv, 3 * C, 3 * C, nk))) return rc;
       const char* qkvn[3] = {".attn1.to_q.weight", ".attn1.to_k.weight", ".attn1.to_v.weight"};
-      // LayerNorm folded into the consumer GEMMs: W' = gamma (.) W is what gets packed; g / c vectors for the epilogue
-      const float* ga1 = h->W(b + ".norm1.weight"); const float* be1 = h->W(b + ".norm1.bias");
-      const float* ga2 = h->W(b + ".norm2.weight"); const float* be2 = h->W(b + ".norm2.bias");
-      const float* ga3 = h->W(b + ".norm3.weight"); const float* be3 = h->W(b + ".norm3.bias");
-      if (dev_alloc(h, &x.g1, (size_t)3 * C, false) || dev_alloc(h, &x.c1, (size_t)3 * C, false) || dev_alloc(h, &x.g2, (size_t)C, false) ||
-          dev_alloc(h, &x.c2, (size_t)C, false) || dev_alloc(h, &x.g3, (size_t)8 * C, false) || dev_alloc(h, &x.c3, (size_t)8 * C, false)) return -2;
-      for (int i = 0; i < 3; ++i) {
-        if ((rc = pack_seg(h, x.qkv, b + qkvn[i], C, C, 1, 0, 0, C, i * C, 0, 0, st, ga1))) return rc;
-        if ((rc = launch_ln_fold(h->W(b + qkvn[i]), C, C, ga1, be1, nullptr, x.g1 + i * C, x.c1 + i * C, st))) return rc;
-      }
+      for (int i = 0; i < 3; ++i)
+        if ((rc = pack_seg(h, x.qkv, b + qkvn[i], C, C, 1, 0, 0, C, i * C, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.out1, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.out1, b + ".attn1.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.q2, C, C, nk))) return rc;
-      if ((rc = pack_seg(h, x.q2, b + ".attn2.to_q.weight", C, C, 1, 0, 0, C, 0, 0, 0, st, ga2))) return rc;
-      if ((rc = launch_ln_fold(h->W(b + ".attn2.to_q.weight"), C, C, ga2, be2, nullptr, x.g2, x.c2, st))) return rc;
+      if ((rc = pack_seg(h, x.q2, b + ".attn2.to_q.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.out2, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.out2, b + ".attn2.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       NS_REQUIRE((4 * C) % 64 == 0, "transformer width %d: 4C must be a multiple of 64", C);
       if ((rc = alloc_packed(h, x.ff1, 4 * C, 8 * C, nk))) return rc;
-      if ((rc = pack_seg(h, x.ff1, b + ".ff.net.0.proj.weight", 8 * C, C, 1, 0, 0, C, 0, 0, 4 * C, st, ga3))) return rc;
-      if ((rc = launch_ln_fold(h->W(b + ".ff.net.0.proj.weight"), 8 * C, C, ga3, be3, h->W(b + ".ff.net.0.proj.bias"), x.g3, x.c3, st))) return rc;
+      if ((rc = pack_seg(h, x.ff1, b + ".ff.net.0.proj.weight", 8 * C, C, 1, 0, 0, C, 0, 0, 4 * C, st))) return rc;
       if ((rc = alloc_packed(h, x.ff2, C, C, nkb_of(4 * C)))) return rc;
       if ((rc = pack_seg(h, x.ff2, b + ".ff.net.2.weight", C, 4 * C, 1, 0, 0, 4 * C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.proj_out, C, C, nk))) return rc;
@@ -600,12 +588,10 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
     else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
-    if (o.kind == PlanOp::XFORMER) stat_doubles += (size_t)3 * 2 * B * Tl[o.level];   // LayerNorm row sums
   }
   double* stat_arena = ar.get<double>(stat_doubles);
   size_t stat_used = 0;
   auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
-  auto new_rowstats = [&](size_t rows) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += 2 * rows; return p; };
   auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
   { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
   // activation buffers
@@ -719,24 +705,23 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
                        sh2 = Builder::view(SP_H, TL, C);
         auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
         bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
-        double* rs1 = new_rowstats(rows); double* rs2 = new_rowstats(rows); double* rs3 = new_rowstats(rows);
-        const SplitBuf sraw = Builder::view(SP_A, TL, C);   // raw split of the residual stream (LayerNorm is folded into the consumers)
-        auto raw_out = [&](GemmOp& g, double* rs) { g.flags |= EPI_OUT_SPLIT | EPI_ROWSTATS; g.out_hi = sraw.hi; g.out_lo = sraw.lo; g.out_split_ld = sraw.ld; g.rowstat_out = rs; };
-        auto ln_in = [&](GemmOp& g, const double* rs, const float* gv, const float* cv) { g.flags |= EPI_LN; g.ln_rowstats = rs; g.ln_g = gv; g.ln_c = cv; g.ln_eps = 1e-5f; g.ln_C = C; };
-        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; raw_out(g, rs1); bld.emit_gemm(g, x.proj_in); }
-        { GemmOp g = lin(x.qkv, sraw, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; ln_in(g, rs1, x.g1, x.c1); bld.emit_gemm(g, x.qkv); }
+        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.proj_in); }
+        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
+        { GemmOp g = lin(x.qkv, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C;
           a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
           a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); fwd.push_back(l); }
-        { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; raw_out(g, rs2); bld.emit_gemm(g, x.out1); }
-        { GemmOp g = lin(x.q2, sraw, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; ln_in(g, rs2, x.g2, x.c2); bld.emit_gemm(g, x.q2); }
+        { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bld.emit_gemm(g, x.out1); }
+        bld.emit_ln_split(T1, C, (int)rows, C, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"), sx);
+        { GemmOp g = lin(x.q2, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; bld.emit_gemm(g, x.q2); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.kv_off + C; a.v_ld = h->kv_total; a.bias = maskbias;
           a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
           a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/; fwd.push_back(l); }
-        { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; raw_out(g, rs3); bld.emit_gemm(g, x.out2); }
-        { GemmOp g = lin(x.ff1, sraw, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; ln_in(g, rs3, x.g3, x.c3);
+        { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.out2); }
+        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"), sx);
+        { GemmOp g = lin(x.ff1, sx, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.0.proj.bias");
           g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld; bld.emit_gemm(g, x.ff1); }
         { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
           g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }

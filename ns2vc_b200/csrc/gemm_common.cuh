@@ -47,33 +47,11 @@ __device__ __forceinline__ float a_fetch_split(const GemmOp& op, const GSeg& s, 
 
 // Epilogue for one accumulator value at (m = b*T_out + t, logical column n).  For GEGLU the caller
 // passes the value accumulator in `acc` and the gate accumulator in `acc_gate`.
-__device__ __forceinline__ void ln_row_consts(const GemmOp& op, long long m, float& mu, float& rstd) {
-  const double s = op.ln_rowstats[2 * m], q = op.ln_rowstats[2 * m + 1];
-  const double inv = 1.0 / (double)op.ln_C;
-  const double mean = s * inv;
-  double var = q * inv - mean * mean;
-  if (var < 0) var = 0;
-  mu = (float)mean;
-  rstd = rsqrtf((float)var + op.ln_eps);
-}
-
 __device__ __forceinline__ float epi_value(const GemmOp& op, int b, long long m, int n, float acc, float acc_gate) {
   float v = acc;
-  float mu = 0.f, rstd = 1.f;
-  if (op.flags & EPI_LN) ln_row_consts(op, m, mu, rstd);
   if (op.flags & EPI_GEGLU) {
     const int half = op.n_valid;   // = 4C
-    float g = acc_gate;
-    if (op.flags & EPI_LN) {
-      v = rstd * (v - mu * __ldg(op.ln_g + n)) + __ldg(op.ln_c + n);
-      g = rstd * (g - mu * __ldg(op.ln_g + half + n)) + __ldg(op.ln_c + half + n);
-    } else {
-      v += __ldg(op.bias + n);
-      g += __ldg(op.bias + half + n);
-    }
-    v = v * gelu_erf_f(g);
-  } else if (op.flags & EPI_LN) {
-    v = rstd * (v - mu * __ldg(op.ln_g + n)) + __ldg(op.ln_c + n);
+    v = (acc + __ldg(op.bias + n)) * gelu_erf_f(acc_gate + __ldg(op.bias + half + n));
   } else if (op.flags & EPI_BIAS) {
     v += __ldg(op.bias + n);
   }

@@ -30,10 +30,7 @@ __global__ void __launch_bounds__(256) pack_b_kernel(PackSeg ps, __nv_bfloat16* 
     }
     const int c = kbl * 64 + kk;                          // channel within the segment
     float w = 0.f;
-    if (c < ps.ncin) {
-      w = ps.w[((long long)n_src * ps.cin_total + ps.cin0 + c) * ps.ktaps + ps.tap];
-      if (ps.kscale) w *= ps.kscale[ps.cin0 + c];
-    }
+    if (c < ps.ncin) w = ps.w[((long long)n_src * ps.cin_total + ps.cin0 + c) * ps.ktaps + ps.tap];
     const int n = ps.n_dst0 + nl;
     const int kb = ps.kb0 + kbl;
     const long long row = (long long)kb * Npad + n;
@@ -56,30 +53,6 @@ int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, f
   pack_b_kernel<<<blocks, 256, 0, st>>>(ps, w_hi, w_lo, w_f32, Npad);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("pack_b launch failed: %s", cudaGetErrorString(e)); return -2; }
-  return 0;
-}
-
-__global__ void ln_fold_kernel(const float* __restrict__ W, int n_rows, int K, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ g,
-                               float* __restrict__ c) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= n_rows) return;
-  float sg = 0.f, sc = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = W[(long long)n * K + k];
-    sg = fmaf(gamma[k], w, sg);
-    sc = fmaf(beta[k], w, sc);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sc += __shfl_xor_sync(0xffffffffu, sc, o); }
-  if (lane == 0) { g[n] = sg; c[n] = sc + (bias ? bias[n] : 0.f); }
-}
-int launch_ln_fold(const float* W, int n_rows, int K, const float* gamma, const float* beta, const float* bias, float* g,
-                   float* c, cudaStream_t st) {
-  ln_fold_kernel<<<ceil_div(n_rows, 8), 256, 0, st>>>(W, n_rows, K, gamma, beta, bias, g, c);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("ln_fold launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
@@ -156,10 +129,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       const float v = epi_value(op, b, m, n, acc[i][j], accg[i][j]);
       if (op.flags & EPI_OUT_NCT) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = v;
       if (op.flags & EPI_OUT_F32) op.out[m * op.out_ld + n] = v;
-      if (op.flags & EPI_ROWSTATS) {
-        atomicAdd(op.rowstat_out + 2 * m, (double)v);
-        atomicAdd(op.rowstat_out + 2 * m + 1, (double)v * (double)v);
-      }
       if (op.flags & EPI_STATS) {
         atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)v);
         atomicAdd(op.stat_sq + (long long)b * op.n_valid + n, (double)v * (double)v);

@@ -214,9 +214,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     if ((op.flags & (EPI_BIAS | EPI_GEGLU)) && lane < BN * 4 / 128)
       asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(op.bias + n0) + lane * 128));
-    float ln_mu = 0.f, ln_rstd = 1.f;
-    if (mv && (op.flags & EPI_LN)) ln_row_consts(op, m, ln_mu, ln_rstd);
-    float rs_sum = 0.f, rs_sq = 0.f;                       // EPI_ROWSTATS partials of this thread's row
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) TRACE(5);
     tc_fence_after();
@@ -229,22 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
           const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
           if (mv) {
-            if (nbase + 32 <= op.n_valid) {                 // vectorised per-column constants (value | gate halves)
-              const bool ln = (op.flags & EPI_LN) != 0;
-              const float4* bv = reinterpret_cast<const float4*>((ln ? op.ln_c : op.bias) + nbase);
-              const float4* bg = reinterpret_cast<const float4*>((ln ? op.ln_c : op.bias) + op.n_valid + nbase);
-              if (ln) {                                     // LN(x) W = rstd * (x W' - mu g) + c
-                const float4* gv = reinterpret_cast<const float4*>(op.ln_g + nbase);
-                const float4* gg = reinterpret_cast<const float4*>(op.ln_g + op.n_valid + nbase);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 x = __ldg(gv + j), y = __ldg(gg + j);
-                  val[4 * j + 0] = ln_rstd * (val[4 * j + 0] - ln_mu * x.x); gate[4 * j + 0] = ln_rstd * (gate[4 * j + 0] - ln_mu * y.x);
-                  val[4 * j + 1] = ln_rstd * (val[4 * j + 1] - ln_mu * x.y); gate[4 * j + 1] = ln_rstd * (gate[4 * j + 1] - ln_mu * y.y);
-                  val[4 * j + 2] = ln_rstd * (val[4 * j + 2] - ln_mu * x.z); gate[4 * j + 2] = ln_rstd * (gate[4 * j + 2] - ln_mu * y.z);
-                  val[4 * j + 3] = ln_rstd * (val[4 * j + 3] - ln_mu * x.w); gate[4 * j + 3] = ln_rstd * (gate[4 * j + 3] - ln_mu * y.w);
-                }
-              }
+            if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
+              const float4* bv = reinterpret_cast<const float4*>(op.bias + nbase);
+              const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nbase);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 x = __ldg(bv + j), y = __ldg(bg + j);
@@ -273,18 +257,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (cvalid && mv) {
           const bool fullc = nbase + 32 <= op.n_valid;
           if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
-            if (op.flags & EPI_LN) {
-              const float4* pg = reinterpret_cast<const float4*>(op.ln_g + nbase);
-              const float4* pc = reinterpret_cast<const float4*>(op.ln_c + nbase);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 g4 = __ldg(pg + j), c4 = __ldg(pc + j);
-                acc[4 * j] = ln_rstd * (acc[4 * j] - ln_mu * g4.x) + c4.x;
-                acc[4 * j + 1] = ln_rstd * (acc[4 * j + 1] - ln_mu * g4.y) + c4.y;
-                acc[4 * j + 2] = ln_rstd * (acc[4 * j + 2] - ln_mu * g4.z) + c4.z;
-                acc[4 * j + 3] = ln_rstd * (acc[4 * j + 3] - ln_mu * g4.w) + c4.w;
-              }
-            }
             if (op.flags & EPI_BIAS) {
               const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
@@ -300,10 +272,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
           }
           store_chunk(op, b, t, m, nbase, acc);
-          if (op.flags & EPI_ROWSTATS) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) { rs_sum += acc[j]; rs_sq += acc[j] * acc[j]; }
-          }
         }
         if (op.flags & EPI_STATS) {
           // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
@@ -320,10 +288,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
           sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
         }
-      }
-      if (mv && (op.flags & EPI_ROWSTATS)) {
-        atomicAdd(op.rowstat_out + 2 * m, (double)rs_sum);
-        atomicAdd(op.rowstat_out + 2 * m + 1, (double)rs_sq);
       }
       if (op.flags & EPI_STATS) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
