@@ -57,8 +57,8 @@ class DenoiserSession:
         # Lanes: the utterances of a batch are independent, and every kernel of the step is a short
         # dependent-latency chain that leaves most SMs idle, so the batch is cut into sub-batches whose
         # whole sampling loops run concurrently on separate streams (own workspace + launch program each,
-        # shared packed weights).  NS2VC_LANES=1 disables the split.
-        want = int(os.environ.get("NS2VC_LANES", "2"))
+        # shared packed weights).  Off by default: GEMM CTAs own a whole SM (198 KB smem), so lanes do not overlap yet.
+        want = int(os.environ.get("NS2VC_LANES", "1"))   # measured r01 (cfg2): 1 lane 1678, 2 lanes 1608, 4 lanes 1595, 8 lanes 1540 steps/s
         n_lanes = max(1, min(want, self.B))
         while self.B % n_lanes:
             n_lanes -= 1
