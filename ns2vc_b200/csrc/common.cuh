@@ -111,7 +111,11 @@ struct GemmOp {
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
+  int bn;                      // N tile (64 / 128), chosen by plan_gemm()
+  int cn;                      // cluster size along N: the cn CTAs of a cluster share the A tile by TMA multicast
 };
+// Choose the N tile and the multicast cluster size for op (fills op.bn / op.cn); must precede encode_tmaps().
+void plan_gemm(GemmOp& op);
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st);

@@ -451,6 +451,7 @@ struct Builder {
     Launch l; l.kind = Launch::GEMM; l.patch = patch;
     if (!dry) {
       if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
+      plan_gemm(g);
       if (!h->simt) { int rc = encode_tmaps(g); if (rc) err = rc; }
     }
     l.gemm = g;

@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 #include "launch.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace ns2vc {
 
@@ -91,7 +92,7 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
 
-template <int BN_>
+template <int BN_, int CN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -113,12 +114,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int t0 = (blockIdx.x % tiles_per_batch) * BM;
   const int n0 = blockIdx.y * BN;                           // first packed column of this tile
   const int nkb = op.nkb_total;
+  // Cluster of CN CTAs along N (same rows, different output columns): each CTA fetches 128/CN rows of every A
+  // box and multicasts them to the whole cluster, so the A tile crosses L2->SM once per cluster, not once per CTA.
+  const uint32_t crank = (CN > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CN) - 1u);
+  constexpr int kARows = BM / CN;
   if (tid == 0) TRACE(0);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CN);                           // every CTA of the cluster releases the stage
     }
     mbar_init(tmem_full_bar, 1);
     mbar_fence_init();
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
+  if (CN > 1) cluster_sync_all();                           // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) TRACE(1);
@@ -166,8 +173,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
         }
         const int c = s.c0 + kbl * 64;
-        tma_load_3d(a_hi, &op.tmap[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
-        tma_load_3d(a_lo, &op.tmap[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
+        if (CN == 1) {
+          tma_load_3d(a_hi, &op.tmap[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
+          tma_load_3d(a_lo, &op.tmap[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
+        } else {
+          const uint32_t roff = crank * (kARows * 128);     // this CTA's slice of the 128-row box
+          tma_load_3d_mc(a_hi + roff, &op.tmap[2 * s.src], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
+          tma_load_3d_mc(a_lo + roff, &op.tmap[2 * s.src + 1], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
+        }
         if (++kbl == s.nkb) { kbl = 0; ++si; }
       }
     }
@@ -192,7 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           umma_bf16(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
           umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
         }
-        umma_commit(empty_bar(stage));                      // frees this smem stage when the MMAs retire
+        if (CN == 1) umma_commit(empty_bar(stage));         // frees this smem stage when the MMAs retire
+        else umma_commit_mc(empty_bar(stage), kMcMask);     // ... in every CTA of the cluster (they multicast into it)
       }
       umma_commit(tmem_full_bar);                           // accumulator complete -> epilogue
       TRACE(4);
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 2 && lane == 0) TRACE(6);
   tc_fence_before();
   __syncthreads();
+  if (CN > 1) cluster_sync_all();                           // nobody exits while a peer may still multicast / signal into it
   if (tid == 0) TRACE(7);
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
@@ -327,14 +342,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B) {
+static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B, int box_rows) {
   static_assert(sizeof(CUtensorMap) == sizeof(TMap), "CUtensorMap size");
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
   if ((s.ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("split buffer not TMA-aligned (ld=%d)", s.ld); return -1; }
   const cuuint64_t gdim[3] = {(cuuint64_t)s.C, (cuuint64_t)s.T, (cuuint64_t)B};
   const cuuint64_t gstr[2] = {(cuuint64_t)s.ld * 2, (cuuint64_t)s.T * s.ld * 2};
-  const cuuint32_t box[3] = {64, (cuuint32_t)BM, 1};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), gdim, gstr,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -345,37 +360,53 @@ static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, i
 
 int encode_tmaps(GemmOp& op) {
   for (int i = 0; i < op.nsrc; ++i) {
-    int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B);
+    const int box_rows = BM / (op.cn > 0 ? op.cn : 1);
+    int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);
     if (rc) return rc;
-    rc = encode_one(&op.tmap[2 * i + 1], op.src[i].lo, op.src[i], op.B);
+    rc = encode_one(&op.tmap[2 * i + 1], op.src[i].lo, op.src[i], op.B, box_rows);
     if (rc) return rc;
   }
   return 0;
 }
 
-template <int BN_>
+template <int BN_, int CN>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
   dim3 grid(op.B * ceil_div(op.T_out, BM), op.N / BN_);
-  cudaError_t e = launch_k(gemm_tc_kernel<BN_>, grid, dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
+  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, CN>, grid, dim3(kThreads), (size_t)Cfg::kSmemBytes, st, dim3(1, CN, 1), op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+void plan_gemm(GemmOp& op) {
+  // N-tile: 128 wide when that already fills the 148 SMs, else 64 wide (twice the CTAs; the
+  // GEGLU epilogue pairs value|gate inside a 128-column block and needs BN = 128).
+  const int ctas128 = op.B * ceil_div(op.T_out, BM) * (op.N / 128);
+  op.bn = ((op.flags & EPI_GEGLU) || ctas128 >= 120) ? 128 : 64;
+  const int ntiles = op.N / op.bn;
+  static int mc = -1;
+  if (mc < 0) { const char* e = getenv("NS2VC_MULTICAST"); mc = (e && e[0] == '0') ? 0 : 1; }
+  op.cn = !mc ? 1 : (ntiles % 4 == 0) ? 4 : (ntiles % 2 == 0) ? 2 : 1;
 }
 
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
-  // N-tile: 128 wide when that already fills the 148 SMs, else 64 wide (twice the CTAs; the
-  // GEGLU epilogue pairs value|gate inside a 128-column block and needs BN = 128).
-  const int ctas128 = op.B * ceil_div(op.T_out, BM) * (op.N / 128);
-  if ((op.flags & EPI_GEGLU) || ctas128 >= 120) return launch_bn<128>(op, st);
-  return launch_bn<64>(op, st);
+  if (op.bn == 128) {
+    if (op.cn == 4) return launch_bn<128, 4>(op, st);
+    if (op.cn == 2) return launch_bn<128, 2>(op, st);
+    return launch_bn<128, 1>(op, st);
+  }
+  if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
+  if (op.cn == 4) return launch_bn<64, 4>(op, st);
+  if (op.cn == 2) return launch_bn<64, 2>(op, st);
+  return launch_bn<64, 1>(op, st);
 }
 
 }  // namespace ns2vc
