@@ -117,6 +117,9 @@ const char* ns2vc_build_info(void);
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
 /* In-kernel %globaltimer stamps (8 per GEMM launch, CTA (0,0)) of the next forwards; NULL disables. */
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
+/* [min entry, max exit] %globaltimer of every launch of the next forwards (buffer pre-set to {~0, 0} pairs). */
+int ns2vc_unet_set_span_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_launches);
+int ns2vc_unet_launch_kind(const ns2vc_unet* h, int launch_index);   /* index into ns2vc_profile_kind_name */
 int ns2vc_profile_num_kinds(void);
 const char* ns2vc_profile_kind_name(int kind);
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches);

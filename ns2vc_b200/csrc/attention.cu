@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
   const bool vk = ((op.k_ld | (h * dh)) & 3) == 0 && (dh & 7) == 0;
   const bool vv = ((op.v_ld | (h * dh)) & 3) == 0 && (dh & 7) == 0;
 
+  span_begin(op.span);
   if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_fence_init(); }
   if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), 128);
   pdl_trigger();
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kAttnTcThreads, 2) attn_tc_kernel(const AttnOp
   }
   tc_fence_before();
   __syncthreads();
+  span_end(op.span);
   if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 

@@ -111,6 +111,7 @@ struct GemmOp {
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
+  unsigned long long* span;    // diagnostics: [min entry, max exit] of the grid, or nullptr
   int bn;                      // N tile (64 / 128), chosen by plan_gemm()
   int cn;                      // cluster size along N: the cn CTAs of a cluster share the A tile by TMA multicast
 };
@@ -163,12 +164,13 @@ struct PrepOp {
   GnStats gn;
   SplitBuf out;                           // transformed
   SplitBuf raw;                           // optional second output without the transform (hi == nullptr: none)
+  unsigned long long* span;               // diagnostics
 };
 int launch_prep_split(const PrepOp& op, cudaStream_t st);
 
 // LayerNorm + split in one pass (one warp per row): out = ((x-mean)*rstd*gamma + beta) as bf16 hi/lo
 int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta,
-                    SplitBuf out, cudaStream_t st);
+                    SplitBuf out, cudaStream_t st, unsigned long long* span = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // Attention
@@ -184,6 +186,7 @@ struct AttnOp {
   int out_split_ld;
   int B, H, Tq, Tk, dh;
   float scale;                    // dh^-0.5
+  unsigned long long* span;       // diagnostics
 };
 int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);
 

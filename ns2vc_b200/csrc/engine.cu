@@ -127,6 +127,7 @@ struct ns2vc_unet {
   int last_launches = 0;
   bool profiling = false;
   unsigned long long* trace = nullptr; int trace_cap = 0;
+  unsigned long long* span = nullptr; int span_cap = 0;   // [launch][2] grid spans
   struct ProfRec { int kind; cudaEvent_t a, b; int M, N, K, nseg, ctas; };
   std::vector<ProfRec> prof;
 
@@ -811,9 +812,10 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
     }
     switch (l.kind) {
       case Launch::GEMM: {
-        if (l.patch == 3 || h->trace) {
+        if (l.patch == 3 || h->trace || h->span) {
           GemmOp g = l.gemm;
           if (l.patch == 3) g.out = out;
+          if (h->span && count < h->span_cap) g.span = h->span + 2 * count;
           if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 8 * gemm_idx;
           ++gemm_idx;
           rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
@@ -825,11 +827,12 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       case Launch::ATTN: {
         AttnOp a = l.attn;
         if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
+        if (h->span && count < h->span_cap) a.span = h->span + 2 * count;
         rc = launch_attention(a, st, h->simt);
         break;
       }
       case Launch::GN: rc = launch_gn_affine(l.gn, st); break;
-      case Launch::LN_SPLIT: rc = launch_ln_split(l.a, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.split, st); break;
+      case Launch::LN_SPLIT: rc = launch_ln_split(l.a, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.split, st, (h->span && count < h->span_cap) ? h->span + 2 * count : nullptr); break;
       case Launch::LN_APPLY: {
         const float* src = (l.patch == 5) ? prompt : l.a;
         rc = launch_ln_apply(src, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.o, l.i3, st);
@@ -850,6 +853,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       case Launch::PREP: {
         PrepOp p = l.prep;
         if (l.patch == 5) p.src1 = prompt;
+        if (h->span && count < h->span_cap) p.span = h->span + 2 * count;
         rc = launch_prep_split(p, st);
         break;
       }
@@ -1096,6 +1100,21 @@ int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* dbuf, int n_gemms) {
   NS_REQUIRE(h, "null handle");
   h->trace = dbuf; h->trace_cap = n_gemms;
   return 0;
+}
+int ns2vc_unet_set_span_trace(ns2vc_unet* h, unsigned long long* dbuf, int n_launches) {
+  NS_REQUIRE(h, "null handle");
+  h->span = dbuf; h->span_cap = n_launches;
+  return 0;
+}
+int ns2vc_unet_launch_kind(const ns2vc_unet* h, int i) {
+  if (!h || i < 0) return -1;
+  int c = 0;
+  for (auto& l : h->prog_fwd) {
+    if (l.kind == Launch::TAP) continue;
+    if (c == i) return (int)l.kind;
+    ++c;
+  }
+  return -1;
 }
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {
   NS_REQUIRE(h, "null handle");

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   constexpr uint16_t kMcMask = (uint16_t)((1u << CN) - 1u);
   constexpr int kARows = BM / CN;
   if (tid == 0) TRACE(0);
+  span_begin(op.span);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (CN > 1) cluster_sync_all();                           // nobody exits while a peer may still multicast / signal into it
   if (tid == 0) TRACE(7);
+  span_end(op.span);
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 

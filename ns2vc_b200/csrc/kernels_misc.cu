@@ -284,6 +284,7 @@ __device__ __forceinline__ void prep_finish(const PrepOp& op, int b, int C, cons
 }
 
 __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
+  span_begin(op.span);
   pdl_trigger();
   pdl_wait();
   extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
     prep_load(op, b, C, chunks, i, k);
     prep_finish(op, b, C, aff, k);
   }
+  span_end(op.span);
 }
 int launch_prep_split(const PrepOp& op, cudaStream_t st) {
   if ((op.out.ld & 7) || (op.raw.hi && op.raw.ld != op.out.ld)) { set_error("prep_split: bad pitch"); return -1; }
@@ -367,12 +369,13 @@ int launch_prep_split(const PrepOp& op, cudaStream_t st) {
 // LayerNorm + split: one warp per row, two-pass statistics in registers (C <= 1024).
 __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, int ld, int M, int C, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       SplitBuf out) {
+                                                       SplitBuf out, unsigned long long* span) {
+  span_begin(span);
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
+  if (row >= M) { span_end(span); return; }
   const float* xr = x + (long long)row * ld;
   constexpr int kMaxChunks = 4;                            // 8-channel chunks per lane: C <= 32*8*4
   float v[kMaxChunks][8];
@@ -425,11 +428,12 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
       *reinterpret_cast<uint4*>(out.lo + (long long)row * out.ld + c0) = lo;
     }
   }
+  span_end(span);
 }
 int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta, SplitBuf out,
-                    cudaStream_t st) {
+                    cudaStream_t st, unsigned long long* span) {
   if (C > 1024 || (out.ld & 7) || out.ld > 1024) { set_error("ln_split: C=%d / pitch %d unsupported", C, out.ld); return -1; }
-  launch_k(ln_split_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, st, x, ld, M, C, eps, gamma, beta, out);
+  launch_k(ln_split_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, st, x, ld, M, C, eps, gamma, beta, out, span);
   NS_LAUNCH_CHECK();
   return 0;
 }

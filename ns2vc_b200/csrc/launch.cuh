@@ -14,6 +14,11 @@ namespace ns2vc {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Diagnostics: [min entry, max exit] %globaltimer stamps of a whole grid (slot pre-set to {~0, 0}).
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void span_begin(unsigned long long* s) { if (s && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(s, gtime_ns()); }
+__device__ __forceinline__ void span_end(unsigned long long* s) { if (s && threadIdx.x == 0 && threadIdx.y == 0) atomicMax(s + 1, gtime_ns()); }
+
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("NS2VC_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
