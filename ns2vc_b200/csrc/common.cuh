@@ -193,21 +193,6 @@ int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);
 // ---------------------------------------------------------------------------------------------
 // Norm statistics and small kernels (kernels_misc.cu)
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics over a (possibly two-source, channel-concatenated) token-major tensor,
-// finalised into a per-(b, c) affine:  scale = rstd*gamma*(1+film_s), shift = (beta - mean*rstd*gamma)*(1+film_s) + film_b
-struct GnOp {
-  const float* src1; int ld1; int C1;
-  const float* src2; int ld2; int C2;    // src2 may be nullptr (C2 = 0)
-  int B, T, G;
-  float eps;
-  const float* gamma; const float* beta; // [C1+C2]
-  const float* film;  int film_ld;       // nullptr or [B, film_ld]: scale at film[b, c], shift at film[b, C + c]
-  float* scale; float* shift;            // [B, C]
-  double* acc;                           // [B*G*2] zero on entry, zero on exit
-  unsigned* counter;                     // [B*G]   zero on entry, zero on exit
-};
-int launch_gn_affine(const GnOp& op, cudaStream_t st);
-
 int launch_ln_stats(const float* x, int ld, int M, int C, float eps, float* stats /*[M,2]*/, cudaStream_t st);
 int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta,
                     float* y, int y_ld, cudaStream_t st);

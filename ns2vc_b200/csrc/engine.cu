@@ -66,7 +66,6 @@ struct Launch {
   enum Kind { GEMM, ATTN, GN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, MEMSET, TAP } kind;
   GemmOp gemm;
   AttnOp attn;
-  GnOp gn;
   LinOp lin;
   PrepOp prep;
   SplitBuf split;
@@ -458,14 +457,6 @@ struct Builder {
     l.gemm = g;
     out->push_back(l);
   }
-  void emit_gn(const float* s1, int ld1, int C1, const float* s2, int ld2, int C2, int Tl, float eps, const float* gamma,
-               const float* beta, const float* film, int film_ld, float* scale, float* shift, double* acc, unsigned* cnt) {
-    Launch l; l.kind = Launch::GN;
-    GnOp& g = l.gn; g.src1 = s1; g.ld1 = ld1; g.C1 = C1; g.src2 = s2; g.ld2 = ld2; g.C2 = C2; g.B = B; g.T = Tl;
-    g.G = h->cfg.norm_num_groups; g.eps = eps; g.gamma = gamma; g.beta = beta; g.film = film; g.film_ld = film_ld;
-    g.scale = scale; g.shift = shift; g.acc = acc; g.counter = cnt;
-    out->push_back(l);
-  }
   void emit_prep(const float* s1, int C1, const float* s2, int C2, int T_src, int T_dst, int mode, const float* scale,
                  const float* shift, const SplitBuf& o, const SplitBuf* raw = nullptr, int row_mul = 1, int row_add = 0,
                  const int* rowmap = nullptr, int patch = 0) {
@@ -502,7 +493,6 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   const ns2vc_unet_cfg& c = h->cfg;
   const bool dry = (ws == nullptr);
   const int nlev = c.n_levels;
-  const int G = c.norm_num_groups;
   const int c0 = c.block_out_channels[0];
   const int Cl = c.latent_channels, Cc = c.in_channels - Cl;
   const int xd = c.cross_attention_dim, ted = h->ted;
@@ -576,14 +566,6 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   float* temb1 = ar.get<float>((size_t)B * ted);
   float* emb = ar.get<float>((size_t)B * ted);
   float* film = ar.get<float>((size_t)B * std::max(h->film_total, 1));
-  double* gn_acc = ar.get<double>((size_t)B * G * 2);
-  unsigned* gn_cnt = ar.get<unsigned>((size_t)B * G);
-  if (!dry) {
-    // the GroupNorm kernels keep these accumulators zero between launches; they start from
-    // whatever the caller's workspace held
-    NS_CHECK_CUDA(cudaMemsetAsync(gn_acc, 0, (size_t)B * G * 2 * sizeof(double), st));
-    NS_CHECK_CUDA(cudaMemsetAsync(gn_cnt, 0, (size_t)B * G * sizeof(unsigned), st));
-  }
   // per-(b, channel) sum | sum-of-squares of every fp32 activation that feeds a GroupNorm, accumulated by
   // the producing GEMM epilogues; one contiguous arena, zeroed by one memset at the top of the forward
   size_t stat_doubles = (size_t)2 * B * c0;
@@ -831,7 +813,6 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         rc = launch_attention(a, st, h->simt);
         break;
       }
-      case Launch::GN: rc = launch_gn_affine(l.gn, st); break;
       case Launch::LN_SPLIT: rc = launch_ln_split(l.a, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.split, st, (h->span && count < h->span_cap) ? h->span + 2 * count : nullptr); break;
       case Launch::LN_APPLY: {
         const float* src = (l.patch == 5) ? prompt : l.a;

@@ -87,103 +87,6 @@ int launch_tokens_to_nct(const float* x, int ld, int B, int C, int T, float* out
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm -> per-(b,c) affine.  grid = (B*G, nsplit); each block reduces a T-slice of one
-// group (both concat sources), adds its partial (double) to acc[bg], and the LAST block of the
-// group (ticket counter) finalises mean/rstd and writes scale/shift for the group's channels,
-// then restores acc/counter to zero so the buffers are reusable without a memset.
-// Reference: nn.GroupNorm (biased variance) resnet.py:536,557, transformer_1d.py:134.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gn_affine_kernel(GnOp op, int nsplit) {
-  pdl_trigger();
-  pdl_wait();
-  const int bg = blockIdx.x;
-  const int b = bg / op.G, g = bg % op.G;
-  const int C = op.C1 + op.C2;
-  const int cpg = C / op.G;
-  const int c_lo = g * cpg;
-  // T-slice of this block; one row (cpg contiguous channels) per thread per iteration
-  const int tper = (op.T + nsplit - 1) / nsplit;
-  const int t_lo = blockIdx.y * tper;
-  const int t_hi = min(op.T, t_lo + tper);
-  float s = 0.f, ss = 0.f;
-  const bool vec = ((cpg | op.C1 | op.ld1 | (op.C2 ? op.ld2 : 0)) & 3) == 0;
-  for (int t = t_lo + threadIdx.x; t < t_hi; t += blockDim.x) {
-    const float* r1 = op.src1 + ((long long)b * op.T + t) * op.ld1;
-    const float* r2 = op.C2 ? op.src2 + ((long long)b * op.T + t) * op.ld2 : nullptr;
-    if (vec) {
-#pragma unroll 4
-      for (int c = c_lo; c < c_lo + cpg; c += 4) {
-        const float4 v = (c < op.C1) ? __ldg(reinterpret_cast<const float4*>(r1 + c))
-                                     : __ldg(reinterpret_cast<const float4*>(r2 + (c - op.C1)));
-        s += (v.x + v.y) + (v.z + v.w);
-        ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      }
-    } else {
-      for (int c = c_lo; c < c_lo + cpg; ++c) {
-        const float v = (c < op.C1) ? r1[c] : r2[c - op.C1];
-        s += v;
-        ss += v * v;
-      }
-    }
-  }
-  __shared__ double sh[2][4];
-  __shared__ bool is_last;
-  double ds = (double)warp_sum(s), dss = (double)warp_sum(ss);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sh[0][w] = ds; sh[1][w] = dss; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, q = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; q += sh[1][i]; }
-    atomicAdd(&op.acc[2 * bg], a);
-    atomicAdd(&op.acc[2 * bg + 1], q);
-    __threadfence();
-    unsigned ticket = atomicAdd(&op.counter[bg], 1u);
-    is_last = (ticket == (unsigned)nsplit - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const double cnt = (double)op.T * cpg;
-  const double a = __ldcg(&op.acc[2 * bg]), q = __ldcg(&op.acc[2 * bg + 1]);
-  const double mean_d = a / cnt;
-  double var_d = q / cnt - mean_d * mean_d;
-  if (var_d < 0) var_d = 0;
-  const float mean = (float)mean_d;
-  const float rstd = (float)(1.0 / sqrt(var_d + (double)op.eps));
-  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
-    int c = c_lo + i;
-    float ga = op.gamma[c] * rstd;
-    float be = op.beta[c] - mean * ga;
-    if (op.film) {
-      float fs = 1.f + op.film[(long long)b * op.film_ld + c];
-      float fb = op.film[(long long)b * op.film_ld + C + c];
-      ga = ga * fs;
-      be = be * fs + fb;
-    }
-    op.scale[(long long)b * C + c] = ga;
-    op.shift[(long long)b * C + c] = be;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    op.acc[2 * bg] = 0.0;
-    op.acc[2 * bg + 1] = 0.0;
-    op.counter[bg] = 0u;
-  }
-}
-int launch_gn_affine(const GnOp& op, cudaStream_t st) {
-  const int C = op.C1 + op.C2;
-  if (C % op.G) { set_error("gn: %d channels not divisible by %d groups", C, op.G); return -1; }
-  int nsplit = (op.T + 127) / 128;
-  if (nsplit < 1) nsplit = 1;
-  if (nsplit > 64) nsplit = 64;
-  dim3 grid(op.B * op.G, nsplit);
-  launch_k(gn_affine_kernel, grid, dim3(128), 0, st, op, nsplit);
-  NS_LAUNCH_CHECK();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
 // LayerNorm row statistics (one warp per row; two-pass in registers, C <= 2048).
 // ---------------------------------------------------------------------------------------------
 template <bool APPLY>
