@@ -40,7 +40,7 @@ template <int BN_> struct TileCfg {
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
   // measured r01: 4/3 stages (1 CTA/SM) beat 2 stages (2 CTAs/SM, co-resident with other lanes' kernels): 4.98 vs 5.74 ms/forward
   static constexpr int kStages = (BN_ == 128) ? 3 : 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 2048 /*descriptor copy*/ + 1024 /*alignment slack*/;
   static constexpr uint32_t kTmemCols = BN_;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
 };
@@ -92,8 +92,10 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
 
+static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descriptor copy");
+
 template <int BN_, int CN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
   constexpr int kStages = Cfg::kStages;
@@ -109,18 +111,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_per_batch = (op.T_out + BM - 1) / BM;
+  // The 1.7 KB operator descriptor lives in the kernel-parameter constant bank, which is cold at every
+  // launch: reading its fields one by one costs a chain of constant-cache misses on the critical path
+  // (producer start-up, epilogue).  Copy it to shared memory once, with all loads in flight together,
+  // before the first __syncthreads (i.e. inside the PDL window); everything below reads the copy.
+  // TMA still gets the tensor maps by their parameter-space address.
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&op_param);
+    uint4* dst = reinterpret_cast<uint4*>(smem + kStages * kStageBytes + 1024);
+    for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
+  }
+  const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + kStages * kStageBytes + 1024);
+  const TMap* tmaps = op_param.tmap;
+  const int T_out_p = op_param.T_out;                        // the few fields needed before the copy is visible
+  const int tiles_per_batch = (T_out_p + BM - 1) / BM;
   const int b = blockIdx.x / tiles_per_batch;
   const int t0 = (blockIdx.x % tiles_per_batch) * BM;
   const int n0 = blockIdx.y * BN;                           // first packed column of this tile
-  const int nkb = op.nkb_total;
+  const int nkb = op_param.nkb_total;
   // Cluster of CN CTAs along N (same rows, different output columns): each CTA fetches 128/CN rows of every A
   // box and multicasts them to the whole cluster, so the A tile crosses L2->SM once per cluster, not once per CTA.
   const uint32_t crank = (CN > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMcMask = (uint16_t)((1u << CN) - 1u);
   constexpr int kARows = BM / CN;
-  if (tid == 0) TRACE(0);
-  span_begin(op.span);
+  if (tid == 0 && op_param.trace && blockIdx.x == 0 && blockIdx.y == 0) op_param.trace[0] = gtime();
+  span_begin(op_param.span);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 2 * op.nsrc; ++i) prefetch_tmap(&op.tmap[i]);
+    for (int i = 0; i < 2 * op_param.nsrc; ++i) prefetch_tmap(&tmaps[i]);
   }
   pdl_trigger();
   tc_fence_before();
@@ -175,12 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         const int c = s.c0 + kbl * 64;
         if (CN == 1) {
-          tma_load_3d(a_hi, &op.tmap[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
-          tma_load_3d(a_lo, &op.tmap[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
+          tma_load_3d(a_hi, &tmaps[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
+          tma_load_3d(a_lo, &tmaps[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
         } else {
           const uint32_t roff = crank * (kARows * 128);     // this CTA's slice of the 128-row box
-          tma_load_3d_mc(a_hi + roff, &op.tmap[2 * s.src], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
-          tma_load_3d_mc(a_lo + roff, &op.tmap[2 * s.src + 1], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
+          tma_load_3d_mc(a_hi + roff, &tmaps[2 * s.src], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
+          tma_load_3d_mc(a_lo + roff, &tmaps[2 * s.src + 1], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
         }
         if (++kbl == s.nkb) { kbl = 0; ++si; }
       }
