@@ -247,137 +247,81 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     mbar_wait(tmem_full_bar, 0);
     if (warp == 2 && lane == 0) TRACE(5);
     tc_fence_after();
-    // Coalescing stage: a thread owns one accumulator ROW (TMEM lane), so storing straight from registers
-    // makes every warp-wide store touch 32 different 128-byte lines.  Each 32x32 chunk is therefore
-    // bounced through shared memory (the pipeline stages are idle now; pitch 36 floats = conflict-free
-    // for 128-bit accesses) and re-read as lane = (row phase, 4-column group): every LDG/STG.128 of the
-    // epilogue then covers 4 full rows x 128 B, bias / residual / GEGLU are applied in that domain, and
-    // the GroupNorm column sums need only two shuffles.
-    constexpr int kPitch = 36;
-    float* sm_t = reinterpret_cast<float*>(smem) + (warp - 2) * (2 * 32 * kPitch);   // value | gate tile of this warp
-    float* sm_part = reinterpret_cast<float*>(smem) + 8 * (2 * 32 * kPitch);           // [4 quarters][BN][2] stats partials
-    const int row0 = t0 + q * 32;                           // first row of this warp
-    const int nrows = min(32, op.T_out - row0);             // valid rows of this warp (may be <= 0)
-    const long long mrow0 = (long long)b * op.T_out + row0;
-    const int c4 = lane & 7, rph = lane >> 3;               // 4-column group, row phase
-    const bool geglu = (op.flags & EPI_GEGLU) != 0;
-    if (op.flags & EPI_OUT_NCT) {
-      // channel-major output (conv_out): thread = row keeps the stores coalesced along t
-#pragma unroll 1
-      for (int cc = (warp - 2) >> 2; cc < BN / 32; cc += 2) {
-        float acc[32];
-        tmem_ld32(trow + (uint32_t)(cc * 32), acc);
-        const int nbase = n0 + cc * 32;
-        if (mv && nbase < op.n_valid) {
+    if (op.flags & EPI_GEGLU) {
+      if (BN == 128) {
+        {
+          const int hh = (warp - 2) >> 2;                   // the two warps of a lane quarter take one half each
+          float val[32], gate[32];
+          tmem_ld32(trow + (uint32_t)(hh * 32), val);
+          tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
+          const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
+          if (mv) {
+            if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
+              const float4* bv = reinterpret_cast<const float4*>(op.bias + nbase);
+              const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nbase);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = epi_value(op, b, m, n, acc[j], 0.f);
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = __ldg(bv + j), y = __ldg(bg + j);
+                val[4 * j + 0] = (val[4 * j + 0] + x.x) * gelu_erf_f(gate[4 * j + 0] + y.x);
+                val[4 * j + 1] = (val[4 * j + 1] + x.y) * gelu_erf_f(gate[4 * j + 1] + y.y);
+                val[4 * j + 2] = (val[4 * j + 2] + x.z) * gelu_erf_f(gate[4 * j + 2] + y.z);
+                val[4 * j + 3] = (val[4 * j + 3] + x.w) * gelu_erf_f(gate[4 * j + 3] + y.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
+            }
+            store_chunk(op, b, t, m, nbase, val);
           }
         }
       }
     } else {
-      const int nchunks = geglu ? BN / 64 : BN / 32;
+      float* sm_stat = reinterpret_cast<float*>(smem);      // [8 warps][32x33] transpose scratch | [4 quarters][BN][2] partials
+      float* sm_part = sm_stat + 8 * 32 * 33;
 #pragma unroll 1
-      for (int cc = (warp - 2) >> 2; cc < nchunks; cc += 2) {   // the two warps of a lane quarter alternate chunks
+      for (int cc = (warp - 2) >> 2; cc < BN / 32; cc += 2) {   // the two warps of a lane quarter alternate chunks
         float acc[32];
-        const int nbase = (geglu ? blockIdx.y * 64 : n0) + cc * 32;   // logical output column of the chunk
-        const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
-        const bool fast = cvalid && nbase + 32 <= op.n_valid && !(op.flags & EPI_ROWBIAS) &&
-                          (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0) && (!(op.flags & EPI_OUT_F32) || (op.out_ld & 3) == 0) &&
-                          (!(op.flags & EPI_OUT_SPLIT) || (op.out_split_ld & 3) == 0);
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld32(trow + (uint32_t)(cc * 32), acc);
-        __syncwarp();
-        if (fast) {
+        const int nbase = n0 + cc * 32;
+        const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
+        if (cvalid && mv) {
+          const bool fullc = nbase + 32 <= op.n_valid;
+          if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+            if (op.flags & EPI_BIAS) {
+              const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sm_t + lane * kPitch + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          if (geglu) {
-            tmem_ld32(trow + (uint32_t)(64 + cc * 32), acc);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sm_t + 32 * kPitch + lane * kPitch + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          }
-          __syncwarp();
-          const int n = nbase + 4 * c4;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-          if (geglu) { bv = __ldg(reinterpret_cast<const float4*>(op.bias + n)); bg = __ldg(reinterpret_cast<const float4*>(op.bias + op.n_valid + n)); }
-          else if (op.flags & EPI_BIAS) bv = __ldg(reinterpret_cast<const float4*>(op.bias + n));
-          float4 rv[8];
-          if (op.flags & EPI_RESIDUAL) {                    // all residual loads in flight first
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = rph + 4 * i;
-              rv[i] = (rr < nrows) ? __ldg(reinterpret_cast<const float4*>(op.res + (mrow0 + rr) * op.res_ld + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
             }
-          }
+            if (op.flags & EPI_RESIDUAL) {
+              const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = rph + 4 * i;
-            if (rr < nrows) {
-              float4 v = *reinterpret_cast<const float4*>(sm_t + rr * kPitch + 4 * c4);
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              if (geglu) {
-                const float4 g = *reinterpret_cast<const float4*>(sm_t + 32 * kPitch + rr * kPitch + 4 * c4);
-                v.x *= gelu_erf_f(g.x + bg.x); v.y *= gelu_erf_f(g.y + bg.y); v.z *= gelu_erf_f(g.z + bg.z); v.w *= gelu_erf_f(g.w + bg.w);
-              }
-              if (op.flags & EPI_RESIDUAL) { v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w; }
-              const long long mm = mrow0 + rr;
-              if (op.flags & EPI_OUT_F32) *reinterpret_cast<float4*>(op.out + mm * op.out_ld + n) = v;
-              if (op.flags & EPI_OUT_SPLIT) {
-                const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
-                const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
-                uint2 hi, lo;
-                hi.x = pack_bf16x2(h0, h1); hi.y = pack_bf16x2(h2, h3);
-                lo.x = pack_bf16x2(v.x - h0, v.y - h1); lo.y = pack_bf16x2(v.z - h2, v.w - h3);
-                *reinterpret_cast<uint2*>(op.out_hi + mm * op.out_split_ld + n) = hi;
-                *reinterpret_cast<uint2*>(op.out_lo + mm * op.out_split_ld + n) = lo;
-              }
-              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-              cq.x += v.x * v.x; cq.y += v.y * v.y; cq.z += v.z * v.z; cq.w += v.w * v.w;
+              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
             }
-          }
-        } else if (cvalid) {
-          // ragged chunk (n_valid not a multiple of 32, unaligned pitches, per-sample bias): element-wise path
-          float gate[32];
-          if (geglu) tmem_ld32(trow + (uint32_t)(64 + cc * 32), gate);
-          if (mv) {
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], geglu ? gate[j] : 0.f);
-            store_chunk(op, b, t, m, nbase, acc);
+            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
           }
-          if (op.flags & EPI_STATS) {                       // column sums through the transpose scratch
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sm_t[lane * kPitch + j] = mv ? acc[j] : 0.f;
-            __syncwarp();
-            if (lane < 8) {
-              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-              for (int rr = 0; rr < 32; ++rr)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { const float v = sm_t[rr * kPitch + 4 * lane + k]; s4[k] += v; q4[k] += v * v; }
-              cs = make_float4(s4[0], s4[1], s4[2], s4[3]);
-              cq = make_float4(q4[0], q4[1], q4[2], q4[3]);
-            }
-          }
+          store_chunk(op, b, t, m, nbase, acc);
         }
         if (op.flags & EPI_STATS) {
-          if (fast) {                                       // combine the 4 row phases (lanes c4, c4+8, c4+16, c4+24)
+          // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
+          // transpose through shared memory (the pipeline stages are idle now), one column per lane;
+          // the four warps' partials are combined below so each column costs one atomic per CTA.
+          float* sm = sm_stat + (warp - 2) * (32 * 33);
+          __syncwarp();
 #pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-              cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
-              cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
-            }
-          }
-          if (lane < 8) {
-            float* pp = sm_part + (q * BN + cc * 32 + 4 * lane) * 2;
-            pp[0] = cs.x; pp[1] = cq.x; pp[2] = cs.y; pp[3] = cq.y; pp[4] = cs.z; pp[5] = cq.z; pp[6] = cs.w; pp[7] = cq.w;
-          }
+          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = (mv && cvalid) ? acc[j] : 0.f;
+          __syncwarp();
+          float cs = 0.f, cq = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) { const float v = sm[rr * 33 + lane]; cs += v; cq += v * v; }
+          sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
+          sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
         }
       }
       if (op.flags & EPI_STATS) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
-        const int col = tid - 64;                           // 0..255
+        const int col = tid - 64;                           // 0..127
         if (col < BN && n0 + col < op.n_valid) {
           double cs = 0, cq = 0;
 #pragma unroll
