@@ -206,6 +206,18 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+def ncu_traffic(kernel):
+    """Average DRAM bytes per launch of `kernel` from the committed ncu launch list (profiles/)."""
+    p = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    tab = json.load(open(p))
+    pref = "gemm_tc_kernel" if kernel == "gemm_tc" else "attn_tc_kernel"
+    n = sum(v["launches"] for k, v in tab.items() if k.startswith(pref))
+    tot = sum(v["launches"] * v["dram_bytes_per_launch"] for k, v in tab.items() if k.startswith(pref))
+    return tot / n if n else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,7 +302,15 @@ def main():
         return float(ms.item()), clocks
 
     ms, clocks = timed(run_device, args.steps, args.warmup, sample_clocks=True)
-    launches_fwd = L.ns2vc_unet_launch_count(h)
+    # kernel launches per run, counted from the engine's own launch programs (one memset node per
+    # forward is not a kernel and is subtracted; +1 sampler-update kernel per step)
+    cnt = DenoiserSession(unet, content_d, prompt_d, mask_d)
+    cnt.prepare()
+    launches_cond = L.ns2vc_unet_launch_count(h)
+    cnt.forward(x_d, torch.full((B,), 500.0, device=dev), torch.empty_like(x_d))
+    launches_fwd = L.ns2vc_unet_launch_count(h) - 1
+    torch.cuda.synchronize(dev)
+    del cnt
     units = world * B * nfe * args.steps
     value = units / (ms / 1e3)
     ms_e2e, _ = timed(run_e2e, args.steps, 1)
@@ -302,7 +322,8 @@ def main():
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xBF16-split tensor-core contractions, fp32 accumulate)",
            "data": "synthetic", "config": workload_cfg(world), "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": (launches_fwd + 1) * nfe * args.steps + 40 * args.steps,
+           "gpu_launches": ((launches_fwd + 1) * nfe + launches_cond) * args.steps,
+           "launches": {"per_unet_forward": launches_fwd, "sampler_update_per_step": 1, "prepare_cond_per_run": launches_cond},
            "ms_per_unet_forward": ms / args.steps / nfe}
 
     if rank == 0:
@@ -327,8 +348,9 @@ def main():
             dom = "gemm_tc"
             ach = fl_gemm / (prof[dom][0] / nprof * 1e-3) / 1e12
             alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic; the 3xBF16 split issues 3x this on the tensor pipe)"
+        traffic = ncu_traffic(dom)
         out["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                           "traffic": None, "algorithmic": alg, "peak_source": peaks["src"],
+                           "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, cold-cache capture in profiles/r01_ncu_launches.md)", "algorithmic": alg, "peak_source": peaks["src"],
                            "launch_avg_us": 1e3 * prof[dom][0] / prof[dom][1], "timing": f"CUDA events around each launch, {nprof} forwards, profiling pass outside the timed region"}
         out["kernels"] = kernels
         whole = flops_per_forward(cfg, B, T, S)[0]
