@@ -1,0 +1,382 @@
+// tcgen05 flash attention, v2 (product path): TMA-fed and warp-specialised.
+//   out = softmax(q k^T * dh^-0.5 + bias) v      (reference attention_processor.py:1025-1036)
+//
+// CTA = 128 queries of one (batch, head); key tiles of 64; 320 threads:
+//   warp 0      TMA producer: Q once, then a ring of {K_hi, K_lo, V_hi, V_lo} tiles.  q / k / v are the
+//               bf16 hi/lo "split" tensors the projection GEMMs' epilogues wrote (token-major), so a
+//               tile is a plain 3-D box {head channels, 64 keys, 1 batch} - no conversion, no transpose.
+//   warp 1      MMA issuer: S[128x64] = Q K^T (A, B K-major) and O_tile[128xdh] = P V with V as an
+//               MN-major B operand (dh contiguous, keys = MMA K dimension), each as 3 bf16 MMAs over the
+//               hi/lo splits, fp32 accumulators in TMEM (S: 64 columns, O_tile: dh columns).
+//   warps 2-9   online softmax, two threads per query row (32 score columns and dh/2 output columns
+//               each): exp2 with scale*log2(e) folded into one FFMA, P written as a SWIZZLE_128B A operand.
+// The three roles only meet through mbarriers: S(j+1) is issued as soon as the softmax warps have
+// pulled S(j) out of TMEM, and P(j) V(j) runs under softmax(j+1), so neither MMA latency nor a
+// CTA-wide barrier sits on the per-tile critical path.
+// Shared-memory rows of the Q/K/V tiles are `PB` bytes wide (32/64/128 = the TMA box width and the
+// UMMA swizzle mode), so a dh=16 head moves 32 B per key instead of a padded 128 B row.
+#include "gemm_common.cuh"
+#include "tc_common.cuh"
+#include "launch.cuh"
+#include <math.h>
+#include <cstdlib>
+
+namespace ns2vc {
+
+namespace {
+
+constexpr int kQ = 128, kKeys = 64;
+constexpr int kThreadsV2 = 320;
+
+template <int DHP, int PB> struct ACfg {
+  static constexpr int NST = (PB == 128) ? 2 : 3;
+  static constexpr int kQBytes = kQ * PB;            // Q hi (lo follows)
+  static constexpr int kTBytes = kKeys * PB;         // one K or V tile (hi or lo)
+  static constexpr int kStageBytes = 4 * kTBytes;    // K_hi | K_lo | V_hi | V_lo
+  static constexpr int kPBytes = kQ * 128;           // P hi [128 x 64] bf16 (lo follows)
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffP = 2 * kQBytes;
+  static constexpr int kOffKV = kOffP + 2 * kPBytes;
+  static constexpr int kOffBar = kOffKV + NST * kStageBytes;
+  static constexpr int kOffXch = kOffBar + 256;      // [3: parity 0 / parity 1 / row sums][2 halves][128 rows] floats
+  static constexpr int kOffBias = kOffXch + 3072;    // additive bias * log2(e) (or -inf past Tk) for up to kBiasKeys keys
+  static constexpr int kBiasKeys = 1024;
+  static constexpr int kSmem = kOffBias + 4 * kBiasKeys + 1024 /*alignment slack*/;
+  static constexpr int kMinCtas = (kSmem <= 74 * 1024) ? 3 : (kSmem <= 113 * 1024) ? 2 : 1;
+};
+
+// Shared-memory matrix descriptor for a tile whose rows are PB bytes (SWIZZLE_<PB>B), 8-row groups dense.
+template <int PB>
+__device__ __forceinline__ uint64_t desc_pb(uint32_t saddr, uint32_t lbo_bytes) {
+  constexpr uint64_t layout = (PB == 32) ? 6 : (PB == 64) ? 4 : 2;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)((8 * PB) >> 4) << 32) |
+         (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_nw(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld_nw<8>(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int DHP, int PB, bool BIAS>
+__global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_kernel(const __grid_constant__ AttnOp op) {
+  using C = ACfg<DHP, PB>;
+  constexpr int NST = C::NST;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + C::kOffBar;
+  const uint32_t q_full = bar0, s_full = bar0 + 8, s_empty = bar0 + 16, p_full = bar0 + 24, o_full = bar0 + 32;
+  auto kv_full = [&](int s) { return bar0 + 40u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar0 + 40u + 8u * (NST + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::kOffBar + 40 + 16 * NST);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQ;
+  const int dh = op.dh;
+  const int ntiles = (op.Tk + kKeys - 1) / kKeys;
+
+  span_begin(op.span);
+  if (tid == 0) {
+    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 128);
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) prefetch_tmap(&op.tm[i]);
+  }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 64;
+  const uint32_t sQ = base + C::kOffQ, sP = base + C::kOffP, sKV = base + C::kOffKV;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      pdl_wait();                                           // q / k / v are the previous kernels' outputs
+      mbar_arrive_expect_tx(q_full, 2u * C::kQBytes);
+      tma_load_3d(sQ, &op.tm[0], op.q_c0 + h * dh, q0, b, q_full);
+      tma_load_3d(sQ + C::kQBytes, &op.tm[1], op.q_c0 + h * dh, q0, b, q_full);
+      for (int j = 0; j < ntiles; ++j) {
+        const int stage = j % NST;
+        if (j >= NST) mbar_wait(kv_empty(stage), (uint32_t)(((j / NST) & 1) ^ 1));
+        const uint32_t dst = sKV + stage * C::kStageBytes;
+        mbar_arrive_expect_tx(kv_full(stage), (uint32_t)C::kStageBytes);
+        tma_load_3d(dst, &op.tm[2], op.k_c0 + h * dh, j * kKeys, b, kv_full(stage));
+        tma_load_3d(dst + C::kTBytes, &op.tm[3], op.k_c0 + h * dh, j * kKeys, b, kv_full(stage));
+        tma_load_3d(dst + 2 * C::kTBytes, &op.tm[4], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
+        tma_load_3d(dst + 3 * C::kTBytes, &op.tm[5], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idS = umma_idesc_bf16(kQ, kKeys);                     // A, B K-major
+      constexpr uint32_t idO = umma_idesc_bf16(kQ, DHP) | (1u << 16);          // B (= V) MN-major
+      auto issue_S = [&](int j) {
+        const uint32_t kst = sKV + (j % NST) * C::kStageBytes;
+#pragma unroll
+        for (int k = 0; k < DHP / 16; ++k) {
+          const uint64_t qh = desc_pb<PB>(sQ + k * 32, 16), ql = desc_pb<PB>(sQ + C::kQBytes + k * 32, 16);
+          const uint64_t kh = desc_pb<PB>(kst + k * 32, 16), kl = desc_pb<PB>(kst + C::kTBytes + k * 32, 16);
+          umma_bf16(tS, qh, kh, idS, k != 0 ? 1u : 0u);
+          umma_bf16(tS, qh, kl, idS, 1u);
+          umma_bf16(tS, ql, kh, idS, 1u);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t par = (uint32_t)(j & 1);
+        if (j + 1 < ntiles) {
+          mbar_wait(kv_full((j + 1) % NST), (uint32_t)(((j + 1) / NST) & 1));
+          mbar_wait(s_empty, par);                          // every softmax thread holds S(j) in registers
+          tc_fence_after();
+          issue_S(j + 1);
+        }
+        mbar_wait(p_full, par);                             // P(j) is in shared memory, O_tile(j-1) has been read
+        tc_fence_after();
+        const uint32_t vst = sKV + (j % NST) * C::kStageBytes + 2 * C::kTBytes;
+#pragma unroll
+        for (int k = 0; k < kKeys / 16; ++k) {
+          const uint64_t ph = umma_desc(sP + k * 32), pl = umma_desc(sP + C::kPBytes + k * 32);
+          const uint64_t vh = desc_pb<PB>(vst + k * 16 * PB, kKeys * PB), vl = desc_pb<PB>(vst + C::kTBytes + k * 16 * PB, kKeys * PB);
+          umma_bf16(tO, ph, vh, idO, k != 0 ? 1u : 0u);
+          umma_bf16(tO, ph, vl, idO, 1u);
+          umma_bf16(tO, pl, vh, idO, 1u);
+        }
+        umma_commit(o_full);
+        umma_commit(kv_empty(j % NST));                     // K(j), V(j) consumed
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    constexpr int OH = DHP / 2;                             // output columns per thread
+    const int qtr = warp & 3, hf = (warp - 2) >> 2;
+    const int r = qtr * 32 + lane;                          // query row = TMEM lane
+    const uint32_t lane_base = ((uint32_t)(qtr * 32)) << 16;
+    float* xch = reinterpret_cast<float*>(smem + C::kOffXch);
+    float* bias_s = reinterpret_cast<float*>(smem + C::kOffBias);
+    const float qscale = op.scale * 1.4426950408889634f;
+    pdl_wait();                                             // the mask bias and the output buffers belong to earlier kernels
+    if (BIAS) {                                             // additive mask bias * log2(e); -inf past Tk
+      const float* bias = op.bias + (long long)b * op.Tk;
+      for (int i = tid - 64; i < ntiles * kKeys; i += 256)
+        bias_s[i] = (i < op.Tk) ? __ldg(bias + i) * 1.4426950408889634f : -INFINITY;
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+    }
+    float o[OH];
+#pragma unroll
+    for (int d = 0; d < OH; ++d) o[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    auto add_o_tile = [&]() {                               // o += O_tile (TMEM)
+      float ot[OH];
+#pragma unroll
+      for (int d0 = 0; d0 < OH; d0 += 8) tmem_ld_nw<8>(tO + lane_base + hf * OH + d0, ot + d0);
+      tmem_wait_ld();
+#pragma unroll
+      for (int d = 0; d < OH; ++d) o[d] += ot[d];
+    };
+
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      float sv[32];
+      tmem_ld32(tS + lane_base + hf * 32, sv);
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      const int kbase = j * kKeys + hf * 32;
+      float mt = -INFINITY;
+      if (BIAS) {
+        const float4* bp = reinterpret_cast<const float4*>(bias_s + kbase);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 bb = bp[c4];
+          sv[4 * c4 + 0] = fmaf(sv[4 * c4 + 0], qscale, bb.x); sv[4 * c4 + 1] = fmaf(sv[4 * c4 + 1], qscale, bb.y);
+          sv[4 * c4 + 2] = fmaf(sv[4 * c4 + 2], qscale, bb.z); sv[4 * c4 + 3] = fmaf(sv[4 * c4 + 3], qscale, bb.w);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mt = fmaxf(mt, sv[c]);
+      } else {
+        if (j == ntiles - 1 && (op.Tk & (kKeys - 1))) {     // keys past Tk were zero-filled by TMA: mask them
+          const int nvalid = op.Tk - kbase;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if (c >= nvalid) sv[c] = -INFINITY;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mt = fmaxf(mt, sv[c]);
+        mt *= qscale;                                       // qscale > 0: max commutes with the scaling
+      }
+      xch[(par * 2 + hf) * 128 + r] = mt;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qtr) : "memory");          // the two warps of this lane quarter
+      const float m_new = fmaxf(m_run, fmaxf(mt, xch[(par * 2 + (hf ^ 1)) * 128 + r]));
+      const float corr = ex2f(m_run - m_new);
+      float lt = 0.f;
+      if (BIAS) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { sv[c] = ex2f(sv[c] - m_new); lt += sv[c]; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { sv[c] = ex2f(fmaf(sv[c], qscale, -m_new)); lt += sv[c]; }
+      }
+      l_run = l_run * corr + lt;
+      m_run = m_new;
+      if (j > 0) {                                          // O_tile(j-1): relative to the previous running max
+        mbar_wait(o_full, par ^ 1u);
+        tc_fence_after();
+        add_o_tile();
+      }
+#pragma unroll
+      for (int d = 0; d < OH; ++d) o[d] *= corr;
+      // P(j) -> shared memory (PV(j-1) has retired: the P buffer is free)
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint4 hi, lo;
+        split8(sv + 8 * c8, hi, lo);
+        const int ck = hf * 4 + c8;
+        const int off = r * 128 + ((ck ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(smem + C::kOffP + off) = hi;
+        *reinterpret_cast<uint4*>(smem + C::kOffP + C::kPBytes + off) = lo;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (uint32_t)((ntiles - 1) & 1));
+    tc_fence_after();
+    add_o_tile();
+
+    // total row sum = the two halves' partial sums
+    xch[(4 + hf) * 128 + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qtr) : "memory");
+    const float l_tot = l_run + xch[(4 + (hf ^ 1)) * 128 + r];
+    if (q0 + r < op.Tq) {
+      const float inv = 1.0f / l_tot;
+      const long long orow = (long long)b * op.Tq + q0 + r;
+      const int dbase = hf * OH;
+      if (op.out) {
+        float* po = op.out + orow * op.out_ld + h * dh;
+#pragma unroll
+        for (int d = 0; d < OH; ++d) if (dbase + d < dh) po[dbase + d] = o[d] * inv;
+      }
+      if (op.out_hi) {
+        __nv_bfloat16* ph = op.out_hi + orow * op.out_split_ld + h * dh + dbase;
+        __nv_bfloat16* pl = op.out_lo + orow * op.out_split_ld + h * dh + dbase;
+        if (((op.out_split_ld | (h * dh)) & 7) == 0) {      // dh % 16 == 0 here, so dbase % 8 == 0
+#pragma unroll
+          for (int d0 = 0; d0 < OH; d0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) v[d] = o[d0 + d] * inv;
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            *reinterpret_cast<uint4*>(ph + d0) = hi;
+            *reinterpret_cast<uint4*>(pl + d0) = lo;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < OH; ++d) {
+            const float v = o[d] * inv;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            ph[d] = hi;
+            pl[d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  span_end(op.span);
+  if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+template <int DHP, int PB, bool BIAS>
+int launch_v2b(const AttnOp& op, cudaStream_t st) {
+  using C = ACfg<DHP, PB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_v2_kernel<DHP, PB, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) { set_error("attention v2: cannot set %d B dynamic smem: %s", C::kSmem, cudaGetErrorString(e)); return -2; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(op.Tq, kQ), op.H, op.B);
+  cudaError_t e = launch_k(attn_v2_kernel<DHP, PB, BIAS>, grid, dim3(kThreadsV2), (size_t)C::kSmem, st, op);
+  if (e != cudaSuccess) { set_error("attention v2 launch failed: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+template <int DHP, int PB>
+int launch_v2(const AttnOp& op, cudaStream_t st) {
+  if (op.bias) {
+    if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
+    return launch_v2b<DHP, PB, true>(op, st);
+  }
+  return launch_v2b<DHP, PB, false>(op, st);
+}
+
+int natural_pb(int dh) { return dh == 16 ? 32 : dh == 32 ? 64 : 128; }
+
+}  // namespace
+
+bool attention_v2_supported(int dh, int Tk, bool biased) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("NS2VC_ATTN"); off = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
+  if (off || !(dh == 16 || dh == 32 || dh == 48 || dh == 64)) return false;
+  return !biased || ceil_div(Tk, kKeys) * kKeys <= 1024;   // the additive bias of a row of keys is staged in shared memory
+}
+
+int encode_attn_tmaps(AttnOp& op) {
+  static int wide = -1;                                     // NS2VC_ATTN_PB=128: padded 128-byte rows for every head dim
+  if (wide < 0) { const char* e = getenv("NS2VC_ATTN_PB"); wide = (e && atoi(e) == 128) ? 1 : 0; }
+  op.pb = wide ? 128 : natural_pb(op.dh);
+  const int bc = op.pb / 2;                                 // box width in channels
+  int rc = 0;
+  if ((rc = encode_tmap_rows(&op.tm[0], op.qs.hi, op.qs.C, op.qs.T, op.B, op.qs.ld, bc, kQ, op.pb))) return rc;
+  if ((rc = encode_tmap_rows(&op.tm[1], op.qs.lo, op.qs.C, op.qs.T, op.B, op.qs.ld, bc, kQ, op.pb))) return rc;
+  if ((rc = encode_tmap_rows(&op.tm[2], op.ks.hi, op.ks.C, op.ks.T, op.B, op.ks.ld, bc, kKeys, op.pb))) return rc;
+  if ((rc = encode_tmap_rows(&op.tm[3], op.ks.lo, op.ks.C, op.ks.T, op.B, op.ks.ld, bc, kKeys, op.pb))) return rc;
+  if ((rc = encode_tmap_rows(&op.tm[4], op.vs.hi, op.vs.C, op.vs.T, op.B, op.vs.ld, bc, kKeys, op.pb))) return rc;
+  if ((rc = encode_tmap_rows(&op.tm[5], op.vs.lo, op.vs.C, op.vs.T, op.B, op.vs.ld, bc, kKeys, op.pb))) return rc;
+  return 0;
+}
+
+int launch_attention_v2(const AttnOp& op, cudaStream_t st) {
+  if (op.Tk <= 0 || op.Tq <= 0) { set_error("attention: empty sequence"); return -1; }
+  if (op.qs.T != op.Tq || op.ks.T != op.Tk || op.vs.T != op.Tk) { set_error("attention v2: split buffer / sequence length mismatch"); return -1; }
+  const int dh = op.dh;
+  if (op.pb == 128) {
+    if (dh == 16) return launch_v2<16, 128>(op, st);
+    if (dh == 32) return launch_v2<32, 128>(op, st);
+    if (dh == 48) return launch_v2<48, 128>(op, st);
+    if (dh == 64) return launch_v2<64, 128>(op, st);
+  } else if (op.pb == 64 && dh == 32) {
+    return launch_v2<32, 64>(op, st);
+  } else if (op.pb == 32 && dh == 16) {
+    return launch_v2<16, 32>(op, st);
+  }
+  set_error("attention v2: unsupported head dim %d / box %d", dh, op.pb);
+  return -1;
+}
+
+}  // namespace ns2vc

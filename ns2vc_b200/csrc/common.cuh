@@ -187,8 +187,22 @@ struct AttnOp {
   int B, H, Tq, Tk, dh;
   float scale;                    // dh^-0.5
   unsigned long long* span;       // diagnostics
+  // v2 (TMA-fed, attention_v2.cu): q / k / v as split activations written by the projection GEMMs' epilogues.
+  // Head h of tensor x lives at columns [x_c0 + h*dh, x_c0 + (h+1)*dh) of its split buffer.
+  SplitBuf qs, ks, vs;
+  int q_c0, k_c0, v_c0;
+  int v2;                         // 1: launch the v2 kernel (needs dh % 16 == 0 and encode_attn_tmaps())
+  int pb;                         // byte width of the Q/K/V TMA boxes = shared-memory row pitch (32 / 64 / 128)
+  TMap tm[6];                     // q hi, q lo (box pb x 128 rows), k hi, k lo, v hi, v lo (box pb x 64 rows)
 };
 int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);
+int launch_attention_v2(const AttnOp& op, cudaStream_t st);
+// Can the v2 kernel run this shape?  (head dim 16/32/48/64; a biased key row must fit the staged-bias buffer)
+bool attention_v2_supported(int dh, int Tk, bool biased);
+// Host: pick the box width and encode op.tm[] (needs a CUDA context).
+int encode_attn_tmaps(AttnOp& op);
+// Generic 3-D tiled bf16 tensor map over a token-major [B, T, ld] buffer with C valid channels.
+int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes);
 
 // ---------------------------------------------------------------------------------------------
 // Norm statistics and small kernels (kernels_misc.cu)

@@ -512,6 +512,10 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   // ---- persistent conditioning buffers
   float* P = (Cc > 0) ? ar.get<float>((size_t)B * T * c0) : nullptr;      // conv_in(content) + bias
   float* kvc = ar.get<float>((size_t)B * S * std::max(h->kv_total, 1));
+  SplitBuf kvs{};                                                          // the same cache as bf16 hi/lo (attention v2 reads it by TMA)
+  kvs.T = S; kvs.C = std::max(h->kv_total, 8); kvs.ld = pad_to(kvs.C, 8);
+  kvs.hi = ar.get<__nv_bfloat16>((size_t)B * S * kvs.ld);
+  kvs.lo = ar.get<__nv_bfloat16>((size_t)B * S * kvs.ld);
   float* maskbias = ar.get<float>((size_t)B * S);
   float* aug = ar.get<float>((size_t)B * ted);
   // ---- conditioning scratch
@@ -538,7 +542,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     GemmOp g = bld.gemm_base(h->kv_all, S);
     const int i = bld.add_src(g, s_prompt);
     bld.seg(g, i, 0, xd, 0);
-    g.flags = EPI_OUT_F32; g.out = kvc; g.out_ld = h->kv_total;
+    g.flags = EPI_OUT_F32 | EPI_OUT_SPLIT; g.out = kvc; g.out_ld = h->kv_total;
+    g.out_hi = kvs.hi; g.out_lo = kvs.lo; g.out_split_ld = kvs.ld;
     bld.emit_gemm(g, h->kv_all);
   }
   if (c.add_embed_text) {
@@ -599,6 +604,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   const SplitBuf SP_X = scratch_split(max_act);      // GN / LN normalised transformer activations
   const SplitBuf SP_ATT = scratch_split(max_act);    // attention output
   const SplitBuf SP_FF = scratch_split(max_ff);      // GEGLU output
+  const SplitBuf SP_QKV = scratch_split(max_qkv);    // q | k | v of the self-attention (q of the cross-attention)
 
   // entry: x -> split tokens, time path, conv_in
   { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 1; l.i0 = Cl; l.i1 = T; l.split = s_xin; fwd.push_back(l); }
@@ -691,18 +697,32 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
         { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.proj_in); }
         bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
-        { GemmOp g = lin(x.qkv, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; bld.emit_gemm(g, x.qkv); }
+        const bool av2 = !h->simt && attention_v2_supported(dh, TL, false) && attention_v2_supported(dh, S, true);
+        const SplitBuf sqkv = Builder::view(SP_QKV, TL, 3 * C), sq2 = Builder::view(SP_QKV, TL, C);
+        { GemmOp g = lin(x.qkv, sx, C);
+          if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sqkv.hi; g.out_lo = sqkv.lo; g.out_split_ld = sqkv.ld; }
+          else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; }
+          bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C;
           a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
-          a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); fwd.push_back(l); }
+          a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh);
+          if (av2) { a.v2 = 1; a.qs = sqkv; a.ks = sqkv; a.vs = sqkv; a.q_c0 = 0; a.k_c0 = C; a.v_c0 = 2 * C;
+                     if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
+          fwd.push_back(l); }
         { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bld.emit_gemm(g, x.out1); }
         bld.emit_ln_split(T1, C, (int)rows, C, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"), sx);
-        { GemmOp g = lin(x.q2, sx, C); g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; bld.emit_gemm(g, x.q2); }
+        { GemmOp g = lin(x.q2, sx, C);
+          if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sq2.hi; g.out_lo = sq2.lo; g.out_split_ld = sq2.ld; }
+          else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; }
+          bld.emit_gemm(g, x.q2); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.kv_off + C; a.v_ld = h->kv_total; a.bias = maskbias;
           a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
-          a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/; fwd.push_back(l); }
+          a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/;
+          if (av2) { a.v2 = 1; a.qs = sq2; a.ks = kvs; a.vs = kvs; a.q_c0 = 0; a.k_c0 = x.kv_off; a.v_c0 = x.kv_off + C;
+                     if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
+          fwd.push_back(l); }
         { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.out2); }
         bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"), sx);
         { GemmOp g = lin(x.ff1, sx, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.0.proj.bias");
@@ -810,7 +830,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         AttnOp a = l.attn;
         if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
         if (h->span && count < h->span_cap) a.span = h->span + 2 * count;
-        rc = launch_attention(a, st, h->simt);
+        rc = (a.v2 && !h->simt) ? launch_attention_v2(a, st) : launch_attention(a, st, h->simt);
         break;
       }
       case Launch::LN_SPLIT: rc = launch_ln_split(l.a, l.i0, l.i1, l.i2, l.f0, l.b, l.c, l.split, st, (h->span && count < h->span_cap) ? h->span + 2 * count : nullptr); break;

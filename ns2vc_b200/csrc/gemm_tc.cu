@@ -359,20 +359,25 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B, int box_rows) {
+int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes) {
   static_assert(sizeof(CUtensorMap) == sizeof(TMap), "CUtensorMap size");
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
-  if ((s.ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("split buffer not TMA-aligned (ld=%d)", s.ld); return -1; }
-  const cuuint64_t gdim[3] = {(cuuint64_t)s.C, (cuuint64_t)s.T, (cuuint64_t)B};
-  const cuuint64_t gstr[2] = {(cuuint64_t)s.ld * 2, (cuuint64_t)s.T * s.ld * 2};
-  const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  if ((ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("split buffer not TMA-aligned (ld=%d)", ld); return -1; }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), gdim, gstr,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) C=%d T=%d B=%d ld=%d", (int)r, s.C, s.T, B, s.ld); return -2; }
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) C=%d T=%d B=%d ld=%d box=%dx%d sw=%d", (int)r, C, T, B, ld, box_c, box_rows, swizzle_bytes); return -2; }
   return 0;
+}
+
+static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B, int box_rows) {
+  return encode_tmap_rows(out, base, s.C, s.T, B, s.ld, 64, box_rows, 128);
 }
 
 int encode_tmaps(GemmOp& op) {
