@@ -117,6 +117,9 @@ const char* ns2vc_build_info(void);
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
 /* In-kernel %globaltimer stamps (8 per GEMM launch, CTA (0,0)) of the next forwards; NULL disables. */
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
+/* Diagnostics: attention launch i of the next forward writes per-key-tile SM-clock stamps of its CTA (0,0,0)
+ * to device_buf[256*i ...] ([16 tiles][16 slots], see attention_v2.cu).  NULL disables. */
+int ns2vc_unet_set_attn_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_launches);
 /* [min entry, max exit] %globaltimer of every launch of the next forwards (buffer pre-set to {~0, 0} pairs). */
 int ns2vc_unet_set_span_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_launches);
 int ns2vc_unet_launch_kind(const ns2vc_unet* h, int launch_index);   /* index into ns2vc_profile_kind_name */

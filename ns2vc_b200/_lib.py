@@ -61,6 +61,7 @@ SIGNATURES = {
     "ns2vc_unet_launch_count": (C.c_int, [_P]),
     "ns2vc_unet_set_profiling": (C.c_int, [_P, C.c_int]),
     "ns2vc_unet_set_trace": (C.c_int, [_P, _P, C.c_int]),
+    "ns2vc_unet_set_attn_trace": (C.c_int, [_P, _P, C.c_int]),
     "ns2vc_unet_set_span_trace": (C.c_int, [_P, _P, C.c_int]),
     "ns2vc_unet_launch_kind": (C.c_int, [_P, C.c_int]),
     "ns2vc_profile_num_kinds": (C.c_int, []),

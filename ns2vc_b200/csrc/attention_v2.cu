@@ -7,7 +7,8 @@
 //               tile is a plain 3-D box {head channels, 64 keys, 1 batch} - no conversion, no transpose.
 //   warp 1      MMA issuer: S[128x64] = Q K^T (A, B K-major) and O_tile[128xdh] = P V with V as an
 //               MN-major B operand (dh contiguous, keys = MMA K dimension), each as 3 bf16 MMAs over the
-//               hi/lo splits, fp32 accumulators in TMEM (S: 64 columns, O_tile: dh columns).
+//               hi/lo splits, fp32 accumulators in TMEM.  x_hi*[y_hi ; y_lo] is one instruction of twice the N
+//               (two TMEM column groups), x_lo*y_hi a second one: 2 MMAs per k-step instead of 3.
 //   warps 2-9   online softmax, two threads per query row (32 score columns and dh/2 output columns
 //               each): exp2 with scale*log2(e) folded into one FFMA, P written as a SWIZZLE_128B A operand.
 // The three roles only meet through mbarriers: S(j+1) is issued as soon as the softmax warps have
@@ -42,7 +43,15 @@ template <int DHP, int PB> struct ACfg {
   static constexpr int kOffBias = kOffXch + 3072;    // additive bias * log2(e) (or -inf past Tk) for up to kBiasKeys keys
   static constexpr int kBiasKeys = 1024;
   static constexpr int kSmem = kOffBias + 4 * kBiasKeys + 1024 /*alignment slack*/;
-  static constexpr int kMinCtas = (kSmem <= 74 * 1024) ? 3 : (kSmem <= 113 * 1024) ? 2 : 1;
+  static constexpr int NO = PB / 2;                  // channels per V tile row = width of one O column group
+  // TMEM: S = x_hi*[y_hi ; y_lo] lands in two column groups when the K tiles are issued as one N = 128 operand (SC);
+  // for 32-byte head rows (dh = 16) S stays three plain N = 64 MMAs so that 128 columns (-> 3 CTAs / SM) suffice.
+  static constexpr bool SC = (PB != 32);
+  static constexpr int kSCols = SC ? 128 : 64;
+  static constexpr int kOCols = 2 * NO;              // one O buffer: [0,NO) hi*hi + lo*hi, [NO,2NO) hi*lo
+  static constexpr int kTmemCols = (kSCols + 2 * kOCols <= 128) ? 128 : (kSCols + 2 * kOCols <= 256) ? 256 : 512;
+  static constexpr int kBySmem = (kSmem <= 74 * 1024) ? 3 : (kSmem <= 113 * 1024) ? 2 : 1;
+  static constexpr int kMinCtas = (512 / kTmemCols < kBySmem) ? 512 / kTmemCols : kBySmem;
 };
 
 // Shared-memory matrix descriptor for a tile whose rows are PB bytes (SWIZZLE_<PB>B), 8-row groups dense.
@@ -66,6 +75,8 @@ __device__ __forceinline__ void tmem_ld_nw<8>(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#define ATRACE(j, slot) do { if (tr && (j) < 16) tr[(j) * 16 + (slot)] = clk(); } while (0)
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int DHP, int PB, bool BIAS>
@@ -88,12 +99,13 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
   const int ntiles = (op.Tk + kKeys - 1) / kKeys;
 
   span_begin(op.span);
+  unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp <= 2) ? op.trace : nullptr;
   if (tid == 0) {
     mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1);
     for (int s = 0; s < NST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 128);
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
   if (warp == 0 && lane == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) prefetch_tmap(&op.tm[i]);
@@ -103,7 +115,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 64;
+  const uint32_t tS = tmem_base, tO = tmem_base + C::kSCols;   // O: two buffers of kOCols columns (tile parity)
   const uint32_t sQ = base + C::kOffQ, sP = base + C::kOffP, sKV = base + C::kOffKV;
 
   if (warp == 0) {
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
       for (int j = 0; j < ntiles; ++j) {
         const int stage = j % NST;
         if (j >= NST) mbar_wait(kv_empty(stage), (uint32_t)(((j / NST) & 1) ^ 1));
+        ATRACE(j, 12);
         const uint32_t dst = sKV + stage * C::kStageBytes;
         mbar_arrive_expect_tx(kv_full(stage), (uint32_t)C::kStageBytes);
         tma_load_3d(dst, &op.tm[2], op.k_c0 + h * dh, j * kKeys, b, kv_full(stage));
@@ -127,17 +140,27 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc_bf16(kQ, kKeys);                     // A, B K-major
-      constexpr uint32_t idO = umma_idesc_bf16(kQ, DHP) | (1u << 16);          // B (= V) MN-major
+      // Every product is hi*hi + hi*lo + lo*hi.  The hi and lo tiles of K (and of V) are adjacent in shared memory,
+      // so X_hi x [Y_hi ; Y_lo] is ONE instruction of twice the N whose result lands in two TMEM column groups;
+      // X_lo x Y_hi accumulates into the first group and the softmax warps add the groups.  (A tcgen05.mma of
+      // these shapes costs ~80 SM cycles whatever its N: instruction count is what the tensor pipe charges for.)
+      constexpr uint32_t idS2 = umma_idesc_bf16(kQ, 2 * kKeys), idS1 = umma_idesc_bf16(kQ, kKeys);                    // A, B K-major
+      constexpr uint32_t idO2 = umma_idesc_bf16(kQ, 2 * C::NO) | (1u << 16), idO1 = umma_idesc_bf16(kQ, C::NO) | (1u << 16);   // B (= V) MN-major
       auto issue_S = [&](int j) {
         const uint32_t kst = sKV + (j % NST) * C::kStageBytes;
 #pragma unroll
         for (int k = 0; k < DHP / 16; ++k) {
           const uint64_t qh = desc_pb<PB>(sQ + k * 32, 16), ql = desc_pb<PB>(sQ + C::kQBytes + k * 32, 16);
-          const uint64_t kh = desc_pb<PB>(kst + k * 32, 16), kl = desc_pb<PB>(kst + C::kTBytes + k * 32, 16);
-          umma_bf16(tS, qh, kh, idS, k != 0 ? 1u : 0u);
-          umma_bf16(tS, qh, kl, idS, 1u);
-          umma_bf16(tS, ql, kh, idS, 1u);
+          const uint64_t kh = desc_pb<PB>(kst + k * 32, 16);                   // rows [0,64) = K_hi, rows [64,128) = K_lo
+          if (C::SC) {
+            umma_bf16(tS, qh, kh, idS2, k != 0 ? 1u : 0u);
+            umma_bf16(tS, ql, kh, idS1, 1u);
+          } else {
+            const uint64_t kl = desc_pb<PB>(kst + C::kTBytes + k * 32, 16);
+            umma_bf16(tS, qh, kh, idS1, k != 0 ? 1u : 0u);
+            umma_bf16(tS, qh, kl, idS1, 1u);
+            umma_bf16(tS, ql, kh, idS1, 1u);
+          }
         }
         umma_commit(s_full);
       };
@@ -151,21 +174,24 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
           mbar_wait(kv_full((j + 1) % NST), (uint32_t)(((j + 1) / NST) & 1));
           mbar_wait(s_empty, par);                          // every softmax thread holds S(j) in registers
           tc_fence_after();
+          ATRACE(j, 8);
           issue_S(j + 1);
+          ATRACE(j, 9);
         }
         mbar_wait(p_full, par);                             // P(j) is in shared memory, O_tile(j-1) has been read
         tc_fence_after();
+        ATRACE(j, 10);
         const uint32_t vst = sKV + (j % NST) * C::kStageBytes + 2 * C::kTBytes;
 #pragma unroll
         for (int k = 0; k < kKeys / 16; ++k) {
           const uint64_t ph = umma_desc(sP + k * 32), pl = umma_desc(sP + C::kPBytes + k * 32);
-          const uint64_t vh = desc_pb<PB>(vst + k * 16 * PB, kKeys * PB), vl = desc_pb<PB>(vst + C::kTBytes + k * 16 * PB, kKeys * PB);
-          umma_bf16(tO, ph, vh, idO, k != 0 ? 1u : 0u);
-          umma_bf16(tO, ph, vl, idO, 1u);
-          umma_bf16(tO, pl, vh, idO, 1u);
+          const uint64_t vh = desc_pb<PB>(vst + k * 16 * PB, C::kTBytes);      // channel group 0 = V_hi, group 1 (+LBO) = V_lo
+          umma_bf16(tO + par * C::kOCols, ph, vh, idO2, k != 0 ? 1u : 0u);
+          umma_bf16(tO + par * C::kOCols, pl, vh, idO1, 1u);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(j % NST));                     // K(j), V(j) consumed
+        ATRACE(j, 11);
       }
     }
   } else {
@@ -189,32 +215,43 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
     for (int d = 0; d < OH; ++d) o[d] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
 
-    auto add_o_tile = [&]() {                               // o += O_tile (TMEM)
-      float ot[OH];
+    auto add_o_tile = [&](uint32_t buf, float scale) {      // o = (o + O_tile[buf] (TMEM)) * scale
+      float ot[OH], ou[OH];
+      const uint32_t to = tO + buf * C::kOCols + lane_base + hf * OH;
 #pragma unroll
-      for (int d0 = 0; d0 < OH; d0 += 8) tmem_ld_nw<8>(tO + lane_base + hf * OH + d0, ot + d0);
+      for (int d0 = 0; d0 < OH; d0 += 8) {
+        tmem_ld_nw<8>(to + d0, ot + d0);
+        tmem_ld_nw<8>(to + C::NO + d0, ou + d0);
+      }
       tmem_wait_ld();
+      const unsigned long long s2 = pk2(scale, scale);
 #pragma unroll
-      for (int d = 0; d < OH; ++d) o[d] += ot[d];
+      for (int d = 0; d < OH; d += 2)
+        upk2(fmul2(fadd2(pk2(o[d], o[d + 1]), fadd2(pk2(ot[d], ot[d + 1]), pk2(ou[d], ou[d + 1]))), s2), o[d], o[d + 1]);
     };
 
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
+      ATRACE(j, 0);
       mbar_wait(s_full, par);
       tc_fence_after();
+      ATRACE(j, 1);
       float sv[32];
-      tmem_ld32(tS + lane_base + hf * 32, sv);
+      if (C::SC) tmem_ld32_sum(tS + lane_base + hf * 32, tS + lane_base + kKeys + hf * 32, sv);
+      else tmem_ld32(tS + lane_base + hf * 32, sv);
       tc_fence_before();
       mbar_arrive(s_empty);
+      ATRACE(j, 2);
       const int kbase = j * kKeys + hf * 32;
       float mt = -INFINITY;
+      const unsigned long long qs2 = pk2(qscale, qscale);
       if (BIAS) {
         const float4* bp = reinterpret_cast<const float4*>(bias_s + kbase);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 bb = bp[c4];
-          sv[4 * c4 + 0] = fmaf(sv[4 * c4 + 0], qscale, bb.x); sv[4 * c4 + 1] = fmaf(sv[4 * c4 + 1], qscale, bb.y);
-          sv[4 * c4 + 2] = fmaf(sv[4 * c4 + 2], qscale, bb.z); sv[4 * c4 + 3] = fmaf(sv[4 * c4 + 3], qscale, bb.w);
+          upk2(ffma2(pk2(sv[4 * c4 + 0], sv[4 * c4 + 1]), qs2, pk2(bb.x, bb.y)), sv[4 * c4 + 0], sv[4 * c4 + 1]);
+          upk2(ffma2(pk2(sv[4 * c4 + 2], sv[4 * c4 + 3]), qs2, pk2(bb.z, bb.w)), sv[4 * c4 + 2], sv[4 * c4 + 3]);
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) mt = fmaxf(mt, sv[c]);
@@ -230,26 +267,30 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
       }
       xch[(par * 2 + hf) * 128 + r] = mt;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qtr) : "memory");          // the two warps of this lane quarter
+      ATRACE(j, 3);
       const float m_new = fmaxf(m_run, fmaxf(mt, xch[(par * 2 + (hf ^ 1)) * 128 + r]));
       const float corr = ex2f(m_run - m_new);
-      float lt = 0.f;
-      if (BIAS) {
+      const unsigned long long nm2 = pk2(-m_new, -m_new);
+      unsigned long long lt2 = pk2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { sv[c] = ex2f(sv[c] - m_new); lt += sv[c]; }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { sv[c] = ex2f(fmaf(sv[c], qscale, -m_new)); lt += sv[c]; }
+      for (int c = 0; c < 32; c += 2) {
+        float a, bq;
+        if (BIAS) upk2(fadd2(pk2(sv[c], sv[c + 1]), nm2), a, bq);
+        else upk2(ffma2(pk2(sv[c], sv[c + 1]), qs2, nm2), a, bq);
+        sv[c] = ex2f(a); sv[c + 1] = ex2f(bq);
+        lt2 = fadd2(lt2, pk2(sv[c], sv[c + 1]));
       }
+      float lt, lt_hi;
+      upk2(lt2, lt, lt_hi);
+      lt += lt_hi;
       l_run = l_run * corr + lt;
       m_run = m_new;
-      if (j > 0) {                                          // O_tile(j-1): relative to the previous running max
+      ATRACE(j, 4);
+      if (j > 0) {                                          // PV(j-1) has retired: the P buffer is free, O_tile(j-1) is complete
         mbar_wait(o_full, par ^ 1u);
         tc_fence_after();
-        add_o_tile();
       }
-#pragma unroll
-      for (int d = 0; d < OH; ++d) o[d] *= corr;
-      // P(j) -> shared memory (PV(j-1) has retired: the P buffer is free)
+      ATRACE(j, 5);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         uint4 hi, lo;
@@ -262,10 +303,14 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
+      ATRACE(j, 6);
+      // O_tile(j-1) (the other TMEM buffer than the one PV(j) is about to fill) is relative to the previous running max
+      if (j > 0) add_o_tile(par ^ 1u, corr);
+      ATRACE(j, 7);
     }
     mbar_wait(o_full, (uint32_t)((ntiles - 1) & 1));
     tc_fence_after();
-    add_o_tile();
+    add_o_tile((uint32_t)((ntiles - 1) & 1), 1.0f);
 
     // total row sum = the two halves' partial sums
     xch[(4 + hf) * 128 + r] = l_run;
@@ -309,7 +354,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
   tc_fence_before();
   __syncthreads();
   span_end(op.span);
-  if (warp == 2) tmem_dealloc(tmem_base, 128);
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 template <int DHP, int PB, bool BIAS>

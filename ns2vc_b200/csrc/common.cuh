@@ -187,6 +187,7 @@ struct AttnOp {
   int B, H, Tq, Tk, dh;
   float scale;                    // dh^-0.5
   unsigned long long* span;       // diagnostics
+  unsigned long long* trace;      // diagnostics (v2): per-tile clock64 stamps of CTA (0,0,0): [16 tiles][16 slots]
   // v2 (TMA-fed, attention_v2.cu): q / k / v as split activations written by the projection GEMMs' epilogues.
   // Head h of tensor x lives at columns [x_c0 + h*dh, x_c0 + (h+1)*dh) of its split buffer.
   SplitBuf qs, ks, vs;

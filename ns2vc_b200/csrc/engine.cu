@@ -126,6 +126,7 @@ struct ns2vc_unet {
   int last_launches = 0;
   bool profiling = false;
   unsigned long long* trace = nullptr; int trace_cap = 0;
+  unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
   unsigned long long* span = nullptr; int span_cap = 0;   // [launch][2] grid spans
   struct ProfRec { int kind; cudaEvent_t a, b; int M, N, K, nseg, ctas; };
   std::vector<ProfRec> prof;
@@ -804,7 +805,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 
 int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long long x_bstride, const float* t, float* out,
                 const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
-  int rc = 0, count = 0, gemm_idx = 0;
+  int rc = 0, count = 0, gemm_idx = 0, attn_idx = 0;
   for (auto& l : prog) {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     const bool prof = h->profiling && l.kind != Launch::TAP;
@@ -830,6 +831,8 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         AttnOp a = l.attn;
         if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
         if (h->span && count < h->span_cap) a.span = h->span + 2 * count;
+        if (h->attn_trace && attn_idx < h->attn_trace_cap) a.trace = h->attn_trace + 256 * attn_idx;
+        ++attn_idx;
         rc = (a.v2 && !h->simt) ? launch_attention_v2(a, st) : launch_attention(a, st, h->simt);
         break;
       }
@@ -1095,6 +1098,11 @@ int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* leve
 int ns2vc_unet_set_tap(ns2vc_unet* h, int i, float* dst) {
   NS_REQUIRE(h && i >= 0 && i < (int)h->tap_dst.size(), "tap index %d out of range", i);
   h->tap_dst[i] = dst;
+  return 0;
+}
+int ns2vc_unet_set_attn_trace(ns2vc_unet* h, unsigned long long* dbuf, int n_launches) {
+  if (!h) return -1;
+  h->attn_trace = dbuf; h->attn_trace_cap = n_launches;
   return 0;
 }
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* dbuf, int n_gemms) {

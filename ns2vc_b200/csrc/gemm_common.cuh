@@ -25,15 +25,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// 8 fp32 values -> 16 bytes of bf16 hi and 16 bytes of bf16 lo (x = hi + lo to ~2^-17 relative)
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 retire two results per issue slot)
+__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ unsigned long long fsub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// (a, b) -> packed bf16 hi = rn(a), rn(b) and lo = rn(a - hi_a), rn(b - hi_b): x = hi + lo to ~2^-17 relative.
+// 5 instructions per pair, none on the XU pipe (F2FP pack, two unpack ops, FADD2, F2FP).
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  float la, lb;
+  upk2(fsub2(pk2(a, b), pk2(ha, hb)), la, lb);
+  lo = pack_bf16x2(la, lb);
+}
+
+// 8 fp32 values -> 16 bytes of bf16 hi and 16 bytes of bf16 lo
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  float h[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-  hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
-  hi.z = pack_bf16x2(h[4], h[5]); hi.w = pack_bf16x2(h[6], h[7]);
-  lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
-  lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
+  split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
+  split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
 }
 
 // One A element of a segment, as the TMA path sees it (zero outside the source).

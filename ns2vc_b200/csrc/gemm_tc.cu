@@ -3,6 +3,12 @@
 //
 //   D[128 x BN] (fp32, TMEM) += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (3xBF16 split)
 //
+// issued as TWO MMAs per 16-wide k-step: A_hi x [B_hi ; B_lo] (one N = 2*BN instruction: the hi and lo
+// weight tiles are adjacent in shared memory, its result lands in two TMEM column groups) and
+// A_lo x B_hi (N = BN, accumulating into the first group); the epilogue adds the two groups.  A
+// tcgen05.mma of these shapes costs ~80 SM cycles whatever its N (measured, profiles/r01_attn_incta_timeline.txt),
+// so instruction count, not FLOPs, sets the main-loop time.
+//
 // fp32-level parity with the reference (rtol 1e-3 / atol 1e-4) cannot be met by single-pass
 // bf16/tf32 MMAs, so both operands are split x = hi + lo (bf16 each) and
 // three kind::f16 MMAs accumulate into the same TMEM tile (the lo*lo term, ~2^-16 relative, is
@@ -41,8 +47,9 @@ template <int BN_> struct TileCfg {
   // measured r01: 4/3 stages (1 CTA/SM) beat 2 stages (2 CTAs/SM, co-resident with other lanes' kernels): 4.98 vs 5.74 ms/forward
   static constexpr int kStages = (BN_ == 128) ? 3 : 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 2048 /*descriptor copy*/ + 1024 /*alignment slack*/;
-  static constexpr uint32_t kTmemCols = BN_;
+  static constexpr uint32_t kTmemCols = 2 * BN_;                       // [0, BN): hi*hi + lo*hi, [BN, 2BN): hi*lo
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
+  static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
 };
 
 // Store 32 consecutive output columns of one row in the layout(s) the op asks for.
@@ -212,13 +219,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const uint32_t a_hi = base + stage * kStageBytes;
         const uint32_t a_lo = a_hi + kATileBytes;
         const uint32_t b_hi = a_lo + kATileBytes;
-        const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
-          const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
-          umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
+          const uint64_t dbh = umma_desc(b_hi + k * 32);     // rows [0, BN) = B_hi tile, rows [BN, 2BN) = B_lo tile (adjacent)
+          umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc2, (kb | k) != 0 ? 1u : 0u);
           umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
         }
         if (CN == 1) umma_commit(empty_bar(stage));         // frees this smem stage when the MMAs retire
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         {
           const int hh = (warp - 2) >> 2;                   // the two warps of a lane quarter take one half each
           float val[32], gate[32];
-          tmem_ld32(trow + (uint32_t)(hh * 32), val);
-          tmem_ld32(trow + (uint32_t)(64 + hh * 32), gate);
+          tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
+          tmem_ld32_sum(trow + (uint32_t)(64 + hh * 32), trow + (uint32_t)(BN + 64 + hh * 32), gate);
           const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
           if (mv) {
             if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll 1
       for (int cc = (warp - 2) >> 2; cc < BN / 32; cc += 2) {   // the two warps of a lane quarter alternate chunks
         float acc[32];
-        tmem_ld32(trow + (uint32_t)(cc * 32), acc);
+        tmem_ld32_sum(trow + (uint32_t)(cc * 32), trow + (uint32_t)(BN + cc * 32), acc);
         const int nbase = n0 + cc * 32;
         const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
         if (cvalid && mv) {
