@@ -115,7 +115,9 @@ const char* ns2vc_build_info(void);
 /* Per-kernel-kind device timing (CUDA events around every launch on the caller's stream); used by
  * bench.py for the roofline line.  Off by default; never enable inside a timed region. */
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
-/* In-kernel %globaltimer stamps (8 per GEMM launch, CTA (0,0)) of the next forwards; NULL disables. */
+/* In-kernel stamps of CTA (0,0) of every GEMM launch of the next forwards, 16 slots per launch: [0,8) %globaltimer
+ * (entry, prologue, PDL wait, first stage full, MMAs issued, accumulator ready, epilogue done, exit), [8,16) SM-clock
+ * stamps of the epilogue sub-steps.  NULL disables. */
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
 /* Diagnostics: attention launch i of the next forward writes per-key-tile SM-clock stamps of its CTA (0,0,0)
  * to device_buf[256*i ...] ([16 tiles][16 slots], see attention_v2.cu).  NULL disables. */

@@ -112,6 +112,8 @@ struct GemmOp {
   double* stat_sq;
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
   unsigned long long* span;    // diagnostics: [min entry, max exit] of the grid, or nullptr
+  TMap tmap_out[3];            // TMA store maps: fp32 out (box 32 cols x 32 rows, SWIZZLE_128B), out_hi, out_lo (SWIZZLE_64B)
+  int tma_out;                 // bit 0: fp32 output goes through tmap_out[0]; bit 1: split output through tmap_out[1..2]
   int bn;                      // N tile (64 / 128), chosen by plan_gemm()
   int cn;                      // cluster size along N: the cn CTAs of a cluster share the A tile by TMA multicast
 };
@@ -204,6 +206,8 @@ bool attention_v2_supported(int dh, int Tk, bool biased);
 int encode_attn_tmaps(AttnOp& op);
 // Generic 3-D tiled bf16 tensor map over a token-major [B, T, ld] buffer with C valid channels.
 int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes);
+// Same for fp32 data (elem_bytes = 4) / bf16 (elem_bytes = 2)
+int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes);
 
 // ---------------------------------------------------------------------------------------------
 // Norm statistics and small kernels (kernels_misc.cu)

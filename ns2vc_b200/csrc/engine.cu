@@ -819,7 +819,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
           GemmOp g = l.gemm;
           if (l.patch == 3) g.out = out;
           if (h->span && count < h->span_cap) g.span = h->span + 2 * count;
-          if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 8 * gemm_idx;
+          if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 16 * gemm_idx;
           ++gemm_idx;
           rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
         } else {

@@ -53,8 +53,8 @@ template <int BN_> struct TileCfg {
 };
 
 // Store 32 consecutive output columns of one row in the layout(s) the op asks for.
-__device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long long m, int nbase, const float* val) {
-  if (op.flags & EPI_OUT_NCT) {
+__device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, int t, long long m, int nbase, const float* val) {
+  if (flags & EPI_OUT_NCT) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = nbase + j;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
     return;
   }
   const bool fullc = nbase + 32 <= op.n_valid;
-  if (op.flags & EPI_OUT_F32) {
+  if (flags & EPI_OUT_F32) {
     float* po = op.out + m * op.out_ld + nbase;
     if (fullc && ((op.out_ld & 3) == 0)) {
 #pragma unroll
@@ -73,7 +73,7 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
       for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) po[j] = val[j];
     }
   }
-  if (op.flags & EPI_OUT_SPLIT) {
+  if (flags & EPI_OUT_SPLIT) {
     __nv_bfloat16* ph = op.out_hi + m * op.out_split_ld + nbase;
     __nv_bfloat16* pl = op.out_lo + m * op.out_split_ld + nbase;
     if (fullc && ((op.out_split_ld & 7) == 0)) {
@@ -96,8 +96,52 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int b, int t, long
   }
 }
 
+// Per-warp staging area of the epilogue (the pipeline stages are idle by then): 8 KB per warp =
+//   [0, 4096)    fp32 chunk  [32 rows][32 cols]  as a SWIZZLE_128B box image
+//   [4096, 6144) bf16 hi     [32 rows][32 cols]  as a SWIZZLE_64B box image,  [6144, 8192) bf16 lo
+constexpr int kStagePerWarp = 8192;
+constexpr int kStageOff = 4096;                        // after the GroupNorm partial sums
+__device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) {      // 16-byte group c4 (0..7) of row
+  return reinterpret_cast<float*>(st + row * 128 + ((c4 ^ (row & 7)) << 4));
+}
+// Store one 32-column chunk of this warp's 32 rows.  val: this thread's row (already zero for rows past T_out).
+__device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool stage_f32, int b, int t,
+                                           int t_warp0, long long m, bool mv, int nbase, const float* val) {
+  if (stage_f32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage_f32_ptr(st, lane, j)) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
+  }
+  if (op.tma_out & 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 hi, lo;
+      split8(val + 8 * j, hi, lo);
+      const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(st + 4096 + off) = hi;
+      *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
+    }
+  }
+  if (op.tma_out) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t sa = smem_u32(st);
+      if (op.tma_out & 1) tma_store_3d(&tmo[0], sa, nbase, t_warp0, b);
+      if (op.tma_out & 2) { tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b); tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b); }
+      bulk_commit();
+    }
+  }
+  // whatever does not go through TMA (channel-major output, unaligned leading dimensions)
+  const int direct = ((op.flags & EPI_OUT_NCT) ? EPI_OUT_NCT : 0) | (((op.flags & EPI_OUT_F32) && !(op.tma_out & 1)) ? EPI_OUT_F32 : 0) |
+                     (((op.flags & EPI_OUT_SPLIT) && !(op.tma_out & 2)) ? EPI_OUT_SPLIT : 0);
+  if (direct && mv) store_chunk(op, direct, b, t, m, nbase, val);
+}
+
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
+// epilogue sub-steps of warp 2 / lane 0 of CTA (0,0), SM clock: slots 8..15 of the 16-slot trace record
+__device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#define ETRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) op.trace[8 + (i)] = gclk(); } while (0)
 
 static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descriptor copy");
 
@@ -241,57 +285,91 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool mv = t < op.T_out;
     const long long m = (long long)b * op.T_out + t;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    // pull this thread's residual row and the bias into L1 while the main loop runs
-    if (mv && (op.flags & EPI_RESIDUAL)) {
-      const char* pr = reinterpret_cast<const char*>(op.res + m * op.res_ld + n0);
-#pragma unroll
-      for (int i = 0; i < BN * 4 / 128; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + i * 128));
-    }
-    if ((op.flags & (EPI_BIAS | EPI_GEGLU)) && lane < BN * 4 / 128)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(op.bias + n0) + lane * 128));
-    mbar_wait(tmem_full_bar, 0);
-    if (warp == 2 && lane == 0) TRACE(5);
-    tc_fence_after();
+    // While the main loop runs these warps have nothing to do: fetch this thread's bias and residual values for
+    // its first 32-column chunk into registers now, so no global-load latency is left on the epilogue's critical path.
+    const int cc0 = (warp - 2) >> 2;
+    float pre[32];                                          // bias + residual of chunk cc0 (plain path); GEGLU: value bias
+    float preg[32];                                         // GEGLU: gate bias
+    bool pre_ok = false;
     if (op.flags & EPI_GEGLU) {
-      if (BN == 128) {
-        {
-          const int hh = (warp - 2) >> 2;                   // the two warps of a lane quarter take one half each
-          float val[32], gate[32];
-          tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
-          tmem_ld32_sum(trow + (uint32_t)(64 + hh * 32), trow + (uint32_t)(BN + 64 + hh * 32), gate);
-          const int nbase = blockIdx.y * 64 + hh * 32;      // logical output column
-          if (mv) {
-            if (nbase + 32 <= op.n_valid) {                 // vectorised bias loads (value | gate halves)
-              const float4* bv = reinterpret_cast<const float4*>(op.bias + nbase);
-              const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nbase);
+      const int nb = blockIdx.y * 64 + cc0 * 32;
+      if (BN == 128 && nb + 32 <= op.n_valid) {
+        pre_ok = true;
+        const float4* bv = reinterpret_cast<const float4*>(op.bias + nb);
+        const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x = __ldg(bv + j), y = __ldg(bg + j);
-                val[4 * j + 0] = (val[4 * j + 0] + x.x) * gelu_erf_f(gate[4 * j + 0] + y.x);
-                val[4 * j + 1] = (val[4 * j + 1] + x.y) * gelu_erf_f(gate[4 * j + 1] + y.y);
-                val[4 * j + 2] = (val[4 * j + 2] + x.z) * gelu_erf_f(gate[4 * j + 2] + y.z);
-                val[4 * j + 3] = (val[4 * j + 3] + x.w) * gelu_erf_f(gate[4 * j + 3] + y.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = epi_value(op, b, m, nbase + j, val[j], gate[j]);
-            }
-            store_chunk(op, b, t, m, nbase, val);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = __ldg(bv + j), y = __ldg(bg + j);
+          pre[4 * j] = x.x; pre[4 * j + 1] = x.y; pre[4 * j + 2] = x.z; pre[4 * j + 3] = x.w;
+          preg[4 * j] = y.x; preg[4 * j + 1] = y.y; preg[4 * j + 2] = y.z; preg[4 * j + 3] = y.w;
         }
       }
     } else {
-      float* sm_stat = reinterpret_cast<float*>(smem);      // [8 warps][32x33] transpose scratch | [4 quarters][BN][2] partials
-      float* sm_part = sm_stat + 8 * 32 * 33;
+      const int nb = n0 + cc0 * 32;
+      if (mv && nb + 32 <= op.n_valid && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+        pre_ok = true;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pre[j] = 0.f;
+        if (op.flags & EPI_BIAS) {
+          const float4* pb = reinterpret_cast<const float4*>(op.bias + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w; }
+        }
+        if (op.flags & EPI_RESIDUAL) {
+          const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w; }
+        }
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    if (warp == 2 && lane == 0) TRACE(5);
+    ETRACE(0);
+    tc_fence_after();
+    uint8_t* st = smem + kStageOff + (warp - 2) * kStagePerWarp;   // this warp's staging area
+    const int t_warp0 = t0 + q * 32;                        // first row of this warp's 32-row slab
+    const TMap* tmo = op_param.tmap_out;
+    if (op.flags & EPI_GEGLU) {
+      if (BN == 128) {
+        const int hh = cc0;                                 // the two warps of a lane quarter take one half each
+        float val[32], gate[32];
+        tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
+        tmem_ld32_sum(trow + (uint32_t)(64 + hh * 32), trow + (uint32_t)(BN + 64 + hh * 32), gate);
+        const int nbase = blockIdx.y * 64 + hh * 32;        // logical output column
+        if (nbase < op.n_valid) {                           // (uniform across the warp)
+          if (!mv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = 0.f;
+          } else if (pre_ok) {                              // biases were fetched before the accumulator wait
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = (val[j] + pre[j]) * gelu_erf_f(gate[j] + preg[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
+          }
+          emit_chunk(op, tmo, st, lane, false, b, t, t_warp0, m, mv, nbase, val);
+        }
+      }
+    } else {
+      float* sm_part = reinterpret_cast<float*>(smem);      // [4 quarters][BN][2] GroupNorm partial sums
+      const bool stage_f32 = (op.tma_out & 1) || (op.flags & EPI_STATS);
+      bool staged_once = false;
 #pragma unroll 1
-      for (int cc = (warp - 2) >> 2; cc < BN / 32; cc += 2) {   // the two warps of a lane quarter alternate chunks
+      for (int cc = cc0; cc < BN / 32; cc += 2) {           // the two warps of a lane quarter alternate chunks
         float acc[32];
         tmem_ld32_sum(trow + (uint32_t)(cc * 32), trow + (uint32_t)(BN + cc * 32), acc);
+        ETRACE(1);
         const int nbase = n0 + cc * 32;
         const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
-        if (cvalid && mv) {
+        if (cvalid) {
           const bool fullc = nbase + 32 <= op.n_valid;
-          if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+          if (!mv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          } else if (cc == cc0 && pre_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += pre[j];
+          } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
             if (op.flags & EPI_BIAS) {
               const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
@@ -304,28 +382,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) acc[j] = epi_value(op, b, m, nbase + j, acc[j], 0.f);
+            for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
           }
-          store_chunk(op, b, t, m, nbase, acc);
-        }
-        if (op.flags & EPI_STATS) {
-          // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm:
-          // transpose through shared memory (the pipeline stages are idle now), one column per lane;
-          // the four warps' partials are combined below so each column costs one atomic per CTA.
-          float* sm = sm_stat + (warp - 2) * (32 * 33);
-          __syncwarp();
+          ETRACE(2);
+          if (staged_once && op.tma_out) {                  // the TMA unit must have read the previous chunk out of the staging area
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc);
+          staged_once = true;
+          ETRACE(3);
+          if (op.flags & EPI_STATS) {
+            // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm: read the staged
+            // chunk column-wise (one column per lane; a row's 32 columns are one permuted 128-byte line: conflict-free);
+            // the four lane quarters' partials are combined below so each column costs one atomic per CTA.
+            __syncwarp();
+            float cs = 0.f, cq = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = (mv && cvalid) ? acc[j] : 0.f;
-          __syncwarp();
-          float cs = 0.f, cq = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) { const float v = sm[rr * 33 + lane]; cs += v; cq += v * v; }
-          sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
-          sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
+            for (int rr = 0; rr < 32; ++rr) { const float v = stage_f32_ptr(st, rr, lane >> 2)[lane & 3]; cs += v; cq += v * v; }
+            sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
+            sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
+            ETRACE(4);
+          }
+        } else if (op.flags & EPI_STATS) {
+          sm_part[(q * BN + cc * 32 + lane) * 2] = 0.f;
+          sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = 0.f;
         }
       }
       if (op.flags & EPI_STATS) {
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
+        ETRACE(5);
         const int col = tid - 64;                           // 0..127
         if (col < BN && n0 + col < op.n_valid) {
           double cs = 0, cq = 0;
@@ -336,11 +422,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
     }
+    if (op.tma_out && lane == 0) bulk_wait_all();           // the bulk stores of this warp have landed
   }
-
   if (warp == 2 && lane == 0) TRACE(6);
+  ETRACE(6);
   tc_fence_before();
   __syncthreads();
+  ETRACE(7);
   if (CN > 1) cluster_sync_all();                           // nobody exits while a peer may still multicast / signal into it
   if (tid == 0) TRACE(7);
   span_end(op.span);
@@ -364,21 +452,25 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes) {
+int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes) {
   static_assert(sizeof(CUtensorMap) == sizeof(TMap), "CUtensorMap size");
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
-  if ((ld & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("split buffer not TMA-aligned (ld=%d)", ld); return -1; }
+  if (((long long)ld * elem_bytes) % 16 || (reinterpret_cast<uintptr_t>(base) & 15)) { set_error("buffer not TMA-aligned (ld=%d)", ld); return -1; }
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  const cuuint64_t gstr[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)T * ld * elem_bytes};
   const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), gdim, gstr,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) C=%d T=%d B=%d ld=%d box=%dx%d sw=%d", (int)r, C, T, B, ld, box_c, box_rows, swizzle_bytes); return -2; }
   return 0;
+}
+int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes) {
+  return encode_tmap_any(out, base, 2, C, T, B, ld, box_c, box_rows, swizzle_bytes);
 }
 
 static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B, int box_rows) {
@@ -386,6 +478,26 @@ static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, i
 }
 
 int encode_tmaps(GemmOp& op) {
+  // Outputs: the epilogue stages each warp's 32 x 32 chunk in shared memory and hands it to the TMA unit
+  // (thread = row straight out of TMEM would cost 32 LSU wavefronts per 128-bit store instruction).
+  static int tma_st = -1;
+  if (tma_st < 0) { const char* e = getenv("NS2VC_TMA_STORE"); tma_st = (e && e[0] == '0') ? 0 : 1; }
+  op.tma_out = 0;
+  if (tma_st && !(op.flags & EPI_OUT_NCT)) {
+    if ((op.flags & EPI_OUT_F32) && op.out && (op.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(op.out) & 15) == 0) {
+      int rc = encode_tmap_any(&op.tmap_out[0], op.out, 4, op.n_valid, op.T_out, op.B, op.out_ld, 32, 32, 128);
+      if (rc) return rc;
+      op.tma_out |= 1;
+    }
+    if ((op.flags & EPI_OUT_SPLIT) && (op.out_split_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(op.out_hi) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(op.out_lo) & 15) == 0) {
+      int rc = encode_tmap_any(&op.tmap_out[1], op.out_hi, 2, op.n_valid, op.T_out, op.B, op.out_split_ld, 32, 32, 64);
+      if (rc) return rc;
+      rc = encode_tmap_any(&op.tmap_out[2], op.out_lo, 2, op.n_valid, op.T_out, op.B, op.out_split_ld, 32, 32, 64);
+      if (rc) return rc;
+      op.tma_out |= 2;
+    }
+  }
   for (int i = 0; i < op.nsrc; ++i) {
     const int box_rows = BM / (op.cn > 0 ? op.cn : 1);
     int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);

@@ -57,6 +57,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const TMap* tmap, int 
       : "memory");
 }
 
+// 3-D tiled TMA store of a shared-memory box to (c, t, b); parts of the box outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const TMap* tmap, uint32_t src, int c, int t, int b) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c), "r"(t), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // multicast variant: the box lands at the same smem offset of every CTA in `mask`, and signals each one's barrier
 __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const TMap* tmap, int c, int t, int b, uint32_t bar, uint16_t mask) {
   asm volatile(

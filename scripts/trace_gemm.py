@@ -20,12 +20,14 @@ for _ in range(3): sess.forward(x, t, o)
 torch.cuda.synchronize()
 L = _lib.lib(); h = unet.engine(torch.device("cuda", 0))
 n = 200
-buf = torch.zeros(n * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(n * 16, dtype=torch.int64, device="cuda")
 _lib.check(L.ns2vc_unet_set_trace(h, buf.data_ptr(), n))
 sess.forward(x, t, o); torch.cuda.synchronize()
 _lib.check(L.ns2vc_unet_set_trace(h, None, 0))
-tr = buf.view(n, 8).cpu()
-tr = tr[tr[:, 0] > 0]
+full = buf.view(n, 16).cpu()
+tr = full[:, :8]
+keep = tr[:, 0] > 0
+tr = tr[keep]; ep = full[keep][:, 8:]
 t00 = int(tr[0, 0])
 names = ["entry", "prologue_done", "pdl_wait_done", "first_full", "mma_issued", "acc_ready", "epi_done", "exit"]
 print("idx start_us " + " ".join(f"d_{n}" for n in names[1:]) + " gap_from_prev_exit")
@@ -41,3 +43,15 @@ for i in range(tr.shape[0]):
     gaps += gap
 print("mean per launch (us since entry):", {k: round(v / tr.shape[0], 2) for k, v in tot.items()}, "mean gap to next gemm entry", round(gaps / tr.shape[0], 2))
 print("forward span us", (int(tr[-1, 7]) - t00) / 1e3, "n gemm", tr.shape[0])
+
+enames = ["acc_ready", "tmem->reg", "bias+res", "stores", "stats_smem", "bar", "atomics/done", "cta_sync"]
+print("epilogue sub-steps, SM cycles since acc_ready (warp 2 lane 0 of CTA (0,0)):")
+print("idx " + " ".join(f"{n:>12s}" for n in enames[1:]))
+acc = [0.0] * 8; cnt = [0] * 8
+for i in range(ep.shape[0]):
+    e = [int(v) for v in ep[i]]
+    d = [(e[j] - e[0]) if e[j] else 0 for j in range(8)]
+    if i < 40: print(f"{i:3d} " + " ".join(f"{v:12d}" for v in d[1:]))
+    for j in range(8):
+        if e[j]: acc[j] += d[j]; cnt[j] += 1
+print("mean " + " ".join(f"{(acc[j] / cnt[j] if cnt[j] else 0):12.0f}" for j in range(1, 8)))
