@@ -29,15 +29,15 @@ namespace {
 constexpr int kQ = 128, kKeys = 64;
 constexpr int kThreadsV2 = 320;
 
-template <int DHP, int PB> struct ACfg {
+template <int DHP, int PB, bool PF16> struct ACfg {
   static constexpr int NST = (PB == 128) ? 2 : 3;
   static constexpr int kQBytes = kQ * PB;            // Q hi (lo follows)
   static constexpr int kTBytes = kKeys * PB;         // one K or V tile (hi or lo)
   static constexpr int kStageBytes = 4 * kTBytes;    // K_hi | K_lo | V_hi | V_lo
-  static constexpr int kPBytes = kQ * 128;           // P hi [128 x 64] bf16 (lo follows)
+  static constexpr int kPBytes = kQ * 128;           // P [128 x 64] 16-bit: fp16 (PF16), or bf16 hi with lo following
   static constexpr int kOffQ = 0;
   static constexpr int kOffP = 2 * kQBytes;
-  static constexpr int kOffKV = kOffP + 2 * kPBytes;
+  static constexpr int kOffKV = kOffP + (PF16 ? 1 : 2) * kPBytes;
   static constexpr int kOffBar = kOffKV + NST * kStageBytes;
   static constexpr int kOffXch = kOffBar + 256;      // [3: parity 0 / parity 1 / row sums][2 halves][128 rows] floats
   static constexpr int kOffBias = kOffXch + 3072;    // additive bias * log2(e) (or -inf past Tk) for up to kBiasKeys keys
@@ -79,9 +79,9 @@ __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 
 #define ATRACE(j, slot) do { if (tr && (j) < 16) tr[(j) * 16 + (slot)] = clk(); } while (0)
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int DHP, int PB, bool BIAS>
-__global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_kernel(const __grid_constant__ AttnOp op) {
-  using C = ACfg<DHP, PB>;
+template <int DHP, int PB, bool BIAS, bool PF16>
+__global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) attn_v2_kernel(const __grid_constant__ AttnOp op) {
+  using C = ACfg<DHP, PB, PF16>;
   constexpr int NST = C::NST;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -184,10 +184,15 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
         const uint32_t vst = sKV + (j % NST) * C::kStageBytes + 2 * C::kTBytes;
 #pragma unroll
         for (int k = 0; k < kKeys / 16; ++k) {
-          const uint64_t ph = umma_desc(sP + k * 32), pl = umma_desc(sP + C::kPBytes + k * 32);
+          const uint64_t ph = umma_desc(sP + k * 32);
           const uint64_t vh = desc_pb<PB>(vst + k * 16 * PB, C::kTBytes);      // channel group 0 = V_hi, group 1 (+LBO) = V_lo
-          umma_bf16(tO + par * C::kOCols, ph, vh, idO2, k != 0 ? 1u : 0u);
-          umma_bf16(tO + par * C::kOCols, pl, vh, idO1, 1u);
+          if (PF16) {
+            umma_bf16(tO + par * C::kOCols, ph, vh, idO2 & ~((7u << 7) | (7u << 10)), k != 0 ? 1u : 0u);   // A = fp16 P, B = fp16 [V_hi | V_lo] (format fields 0)
+          } else {
+            const uint64_t pl = umma_desc(sP + C::kPBytes + k * 32);
+            umma_bf16(tO + par * C::kOCols, ph, vh, idO2, k != 0 ? 1u : 0u);
+            umma_bf16(tO + par * C::kOCols, pl, vh, idO1, 1u);
+          }
         }
         umma_commit(o_full);
         umma_commit(kv_empty(j % NST));                     // K(j), V(j) consumed
@@ -272,12 +277,18 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
       const float corr = ex2f(m_run - m_new);
       const unsigned long long nm2 = pk2(-m_new, -m_new);
       unsigned long long lt2 = pk2(0.f, 0.f);
+      uint32_t ph2[PF16 ? 16 : 1];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         float a, bq;
         if (BIAS) upk2(fadd2(pk2(sv[c], sv[c + 1]), nm2), a, bq);
         else upk2(ffma2(pk2(sv[c], sv[c + 1]), qs2, nm2), a, bq);
         sv[c] = ex2f(a); sv[c + 1] = ex2f(bq);
+        if (PF16) {                                         // the weights ARE the fp16-rounded values: numerator and row sum agree
+          const uint32_t h2 = pack_f16x2(sv[c], sv[c + 1]);
+          ph2[c >> 1] = h2;
+          sv[c] = f16lo_to_f32(h2); sv[c + 1] = f16hi_to_f32(h2);
+        }
         lt2 = fadd2(lt2, pk2(sv[c], sv[c + 1]));
       }
       float lt, lt_hi;
@@ -293,12 +304,16 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
       ATRACE(j, 5);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
-        uint4 hi, lo;
-        split8(sv + 8 * c8, hi, lo);
         const int ck = hf * 4 + c8;
         const int off = r * 128 + ((ck ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(smem + C::kOffP + off) = hi;
-        *reinterpret_cast<uint4*>(smem + C::kOffP + C::kPBytes + off) = lo;
+        if (PF16) {
+          *reinterpret_cast<uint4*>(smem + C::kOffP + off) = make_uint4(ph2[4 * c8], ph2[4 * c8 + 1], ph2[4 * c8 + 2], ph2[4 * c8 + 3]);
+        } else {
+          uint4 hi, lo;
+          split8(sv + 8 * c8, hi, lo);
+          *reinterpret_cast<uint4*>(smem + C::kOffP + off) = hi;
+          *reinterpret_cast<uint4*>(smem + C::kOffP + C::kPBytes + off) = lo;
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -357,32 +372,41 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB>::kMinCtas) attn_v2_k
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-template <int DHP, int PB, bool BIAS>
+template <int DHP, int PB, bool BIAS, bool PF16>
 int launch_v2b(const AttnOp& op, cudaStream_t st) {
-  using C = ACfg<DHP, PB>;
+  using C = ACfg<DHP, PB, PF16>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_v2_kernel<DHP, PB, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_v2_kernel<DHP, PB, BIAS, PF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) { set_error("attention v2: cannot set %d B dynamic smem: %s", C::kSmem, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(op.Tq, kQ), op.H, op.B);
-  cudaError_t e = launch_k(attn_v2_kernel<DHP, PB, BIAS>, grid, dim3(kThreadsV2), (size_t)C::kSmem, st, op);
+  cudaError_t e = launch_k(attn_v2_kernel<DHP, PB, BIAS, PF16>, grid, dim3(kThreadsV2), (size_t)C::kSmem, st, op);
   if (e != cudaSuccess) { set_error("attention v2 launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
+// Softmax weights: fp16 (one P*[V_hi|V_lo] MMA per k-step; the weights are DEFINED as the rounded values, so the result
+// is an exact weighted mean with weights perturbed by <= 2^-12 relative) or bf16 hi/lo split (NS2VC_ATTN_P=split).
+bool p_fp16() { return attention_v2_p_fp16(); }
 template <int DHP, int PB>
 int launch_v2(const AttnOp& op, cudaStream_t st) {
   if (op.bias) {
-    if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
-    return launch_v2b<DHP, PB, true>(op, st);
+    if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB, true>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
+    return p_fp16() ? launch_v2b<DHP, PB, true, true>(op, st) : launch_v2b<DHP, PB, true, false>(op, st);
   }
-  return launch_v2b<DHP, PB, false>(op, st);
+  return p_fp16() ? launch_v2b<DHP, PB, false, true>(op, st) : launch_v2b<DHP, PB, false, false>(op, st);
 }
 
 int natural_pb(int dh) { return dh == 16 ? 32 : dh == 32 ? 64 : 128; }
 
 }  // namespace
+
+bool attention_v2_p_fp16() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NS2VC_ATTN_P"); v = (e && e[0] == 's') ? 0 : 1; }
+  return v == 1;
+}
 
 bool attention_v2_supported(int dh, int Tk, bool biased) {
   static int off = -1;

@@ -108,6 +108,7 @@ struct GemmOp {
   __nv_bfloat16* out_lo;
   int out_split_ld;
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
+  int f16_col0;                // split output columns >= f16_col0 (a multiple of 32) are written as FP16 hi/lo instead of bf16
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
@@ -202,6 +203,8 @@ int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);
 int launch_attention_v2(const AttnOp& op, cudaStream_t st);
 // Can the v2 kernel run this shape?  (head dim 16/32/48/64; a biased key row must fit the staged-bias buffer)
 bool attention_v2_supported(int dh, int Tk, bool biased);
+// v2 softmax weights as fp16 (then V must be an fp16 hi/lo split) or as a bf16 hi/lo split (NS2VC_ATTN_P=split)
+bool attention_v2_p_fp16();
 // Host: pick the box width and encode op.tm[] (needs a CUDA context).
 int encode_attn_tmaps(AttnOp& op);
 // Generic 3-D tiled bf16 tensor map over a token-major [B, T, ld] buffer with C valid channels.

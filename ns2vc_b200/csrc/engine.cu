@@ -57,7 +57,8 @@ struct XformerSite {
   std::string p;
   int c;
   PackedB proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
-  int kv_off = 0;            // column offset of this block's K|V in the cross K/V cache
+  int kv_off = 0;            // column offset of this block's K in the cross K/V cache (all K first ...)
+  int v_off = 0;             // ... then all V: column offset of this block's V
 };
 struct ConvSite { std::string p; int c; PackedB w; };
 
@@ -104,7 +105,7 @@ struct ns2vc_unet {
   std::vector<XformerSite> xformers;
   std::vector<ConvSite> resamplers;
   PackedB convin_lat, convin_content, conv_out, kv_all;
-  int kv_total = 0, film_total = 0;
+  int kv_total = 0, k_total = 0, film_total = 0;
   float* film_W = nullptr; float* film_b = nullptr;       // concatenated time_emb_proj
   float* pool_kv_W = nullptr; float* pool_kv_b = nullptr; // concatenated k_proj | v_proj
   std::vector<void*> owned;                               // everything to cudaFree
@@ -359,7 +360,7 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
       if ((rc = alloc_packed(h, x.proj_out, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.proj_out, x.p + ".proj_out.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       x.kv_off = kv_off;
-      kv_off += 2 * C;
+      kv_off += C;
       h->xformers.push_back(x);
     } else if (o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) {
       ConvSite s; s.p = o.prefix; s.c = o.cout;
@@ -371,7 +372,9 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
     }
   }
   h->film_total = film_off;
-  h->kv_total = kv_off;
+  h->k_total = kv_off;                                   // cache columns: [K of every block | V of every block]
+  for (auto& x : h->xformers) x.v_off = h->k_total + x.kv_off;
+  h->kv_total = 2 * kv_off;
   // conv_out
   {
     const int nk = nkb_of(c0);
@@ -386,7 +389,7 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
     for (auto& x : h->xformers) {
       const std::string b = x.p + ".transformer_blocks.0";
       if ((rc = pack_seg(h, h->kv_all, b + ".attn2.to_k.weight", x.c, xd, 1, 0, 0, xd, x.kv_off, 0, 0, st))) return rc;
-      if ((rc = pack_seg(h, h->kv_all, b + ".attn2.to_v.weight", x.c, xd, 1, 0, 0, xd, x.kv_off + x.c, 0, 0, st))) return rc;
+      if ((rc = pack_seg(h, h->kv_all, b + ".attn2.to_v.weight", x.c, xd, 1, 0, 0, xd, x.v_off, 0, 0, st))) return rc;
     }
   }
   // concatenated FiLM projection [film_total, ted]
@@ -436,6 +439,7 @@ struct Builder {
     GemmOp g; memset(&g, 0, sizeof(g));
     g.B = B; g.T_out = T_out;
     g.w_hi = w.hi; g.w_lo = w.lo; g.w_f32 = w.f32; g.N = w.Npad; g.n_valid = w.n_logical;
+    g.f16_col0 = 0x7fffffff;
     return g;
   }
   int add_src(GemmOp& g, const SplitBuf& s) { g.src[g.nsrc] = s; return g.nsrc++; }
@@ -545,6 +549,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     bld.seg(g, i, 0, xd, 0);
     g.flags = EPI_OUT_F32 | EPI_OUT_SPLIT; g.out = kvc; g.out_ld = h->kv_total;
     g.out_hi = kvs.hi; g.out_lo = kvs.lo; g.out_split_ld = kvs.ld;
+    if (attention_v2_p_fp16()) g.f16_col0 = h->k_total;     // V columns as fp16 hi/lo (attention v2: fp16 softmax weights x fp16 V)
     bld.emit_gemm(g, h->kv_all);
   }
   if (c.add_embed_text) {
@@ -701,7 +706,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const bool av2 = !h->simt && attention_v2_supported(dh, TL, false) && attention_v2_supported(dh, S, true);
         const SplitBuf sqkv = Builder::view(SP_QKV, TL, 3 * C), sq2 = Builder::view(SP_QKV, TL, C);
         { GemmOp g = lin(x.qkv, sx, C);
-          if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sqkv.hi; g.out_lo = sqkv.lo; g.out_split_ld = sqkv.ld; }
+          if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sqkv.hi; g.out_lo = sqkv.lo; g.out_split_ld = sqkv.ld;
+                     if (attention_v2_p_fp16()) g.f16_col0 = 2 * C; }
           else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; }
           bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
@@ -718,10 +724,10 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; }
           bld.emit_gemm(g, x.q2); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
-          a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.kv_off + C; a.v_ld = h->kv_total; a.bias = maskbias;
+          a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.v_off; a.v_ld = h->kv_total; a.bias = maskbias;
           a.out_hi = satt.hi; a.out_lo = satt.lo; a.out_split_ld = satt.ld;
           a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/;
-          if (av2) { a.v2 = 1; a.qs = sq2; a.ks = kvs; a.vs = kvs; a.q_c0 = 0; a.k_c0 = x.kv_off; a.v_c0 = x.kv_off + C;
+          if (av2) { a.v2 = 1; a.qs = sq2; a.ks = kvs; a.vs = kvs; a.q_c0 = 0; a.k_c0 = x.kv_off; a.v_c0 = x.v_off;
                      if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
           fwd.push_back(l); }
         { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.out2); }

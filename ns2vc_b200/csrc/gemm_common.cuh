@@ -47,6 +47,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = pack_bf16x2(la, lb);
 }
 
+// fp16 flavour of split2 / split8 (operands of the attention's fp16 P x V product)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) { uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+__device__ __forceinline__ float f16lo_to_f32(uint32_t h2) { float f; asm("{.reg .f16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(f) : "r"(h2)); return f; }
+__device__ __forceinline__ float f16hi_to_f32(uint32_t h2) { float f; asm("{.reg .f16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, h;}" : "=f"(f) : "r"(h2)); return f; }
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2(a, b);
+  float la, lb;
+  upk2(fsub2(pk2(a, b), pk2(f16lo_to_f32(hi), f16hi_to_f32(hi))), la, lb);
+  lo = pack_f16x2(la, lb);
+}
+__device__ __forceinline__ void split8_f16(const float* v, uint4& hi, uint4& lo) {
+  split2_f16(v[0], v[1], hi.x, lo.x); split2_f16(v[2], v[3], hi.y, lo.y);
+  split2_f16(v[4], v[5], hi.z, lo.z); split2_f16(v[6], v[7], hi.w, lo.w);
+}
+
 // 8 fp32 values -> 16 bytes of bf16 hi and 16 bytes of bf16 lo
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);

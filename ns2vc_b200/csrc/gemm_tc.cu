@@ -30,6 +30,7 @@
 #include "tc_common.cuh"
 #include "launch.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 namespace ns2vc {
@@ -77,10 +78,11 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, 
     __nv_bfloat16* ph = op.out_hi + m * op.out_split_ld + nbase;
     __nv_bfloat16* pl = op.out_lo + m * op.out_split_ld + nbase;
     if (fullc && ((op.out_split_ld & 7) == 0)) {
+      const bool f16 = nbase >= op.f16_col0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 hi, lo;
-        split8(val + 8 * j, hi, lo);
+        if (f16) split8_f16(val + 8 * j, hi, lo); else split8(val + 8 * j, hi, lo);
         *reinterpret_cast<uint4*>(ph + 8 * j) = hi;
         *reinterpret_cast<uint4*>(pl + 8 * j) = lo;
       }
@@ -88,9 +90,15 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, 
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (nbase + j < op.n_valid) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(val[j]);
-          ph[j] = h;
-          pl[j] = __float2bfloat16_rn(val[j] - __bfloat162float(h));
+          if (nbase >= op.f16_col0) {
+            const __half h = __float2half_rn(val[j]);
+            reinterpret_cast<__half*>(ph)[j] = h;
+            reinterpret_cast<__half*>(pl)[j] = __float2half_rn(val[j] - __half2float(h));
+          } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(val[j]);
+            ph[j] = h;
+            pl[j] = __float2bfloat16_rn(val[j] - __bfloat162float(h));
+          }
         }
     }
   }
@@ -112,10 +120,11 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage_f32_ptr(st, lane, j)) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
   }
   if (op.tma_out & 2) {
+    const bool f16 = nbase >= op.f16_col0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 hi, lo;
-      split8(val + 8 * j, hi, lo);
+      if (f16) split8_f16(val + 8 * j, hi, lo); else split8(val + 8 * j, hi, lo);
       const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
       *reinterpret_cast<uint4*>(st + 4096 + off) = hi;
       *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
