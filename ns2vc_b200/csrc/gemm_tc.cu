@@ -21,11 +21,12 @@
 // once.  Channel concats are just two tensor maps.
 // B operand: weights pre-packed as the swizzled smem image, one cp.async.bulk per hi/lo tile.
 //
-// Warp roles (192 threads, 1 CTA/SM, 3-4 stage mbarrier ring):
-//   warp 0     TMA producer (one elected lane)
-//   warp 1     MMA issuer (one elected lane): tcgen05.mma x12 per k-block, tcgen05.commit
-//   warps 2-5  epilogue: TMEM -> registers (tcgen05.ld 32x32b) -> bias / GEGLU / residual ->
-//              fp32 token-major, fp32 channel-major, or bf16 hi/lo split for the next GEMM
+// Persistent CTAs (one per SM at most, 320 threads), each looping over its share of the output tiles:
+//   warp 0     TMA producer (one elected lane): 2-4 stage mbarrier ring running across tiles
+//   warp 1     MMA issuer (one elected lane): tcgen05.mma x8 per k-block into TMEM accumulator buffer (tile & 1)
+//   warps 2-9  epilogue of tile i while the main loop of tile i+1 runs: TMEM -> registers (tcgen05.ld 32x32b)
+//              -> bias / GEGLU / residual -> staged 32x32 chunks -> TMA bulk stores (fp32 token-major, 16-bit hi/lo
+//              split for the next GEMM / attention), or direct channel-major stores for the output head
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
 #include "launch.cuh"
@@ -41,17 +42,31 @@ constexpr int kEpiWarps = 8;                            // two per SMSP: the epi
 constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kATileBytes = BM * BK * 2;                // 16 KB: one bf16 [128 x 64] A tile (hi or lo)
 
+constexpr int kMaxStages = 4;
+// Per-warp staging area of the epilogue: 8 KB per warp =
+//   [0, 4096)    fp32 chunk  [32 rows][32 cols]  as a SWIZZLE_128B box image
+//   [4096, 6144) 16-bit hi   [32 rows][32 cols]  as a SWIZZLE_64B box image,  [6144, 8192) 16-bit lo
+constexpr int kStagePerWarp = 8192;
+constexpr int kStageOff = 8192;                         // the staging area starts with two GroupNorm partial-sum buffers (tile parity), <= 4 KB each
+constexpr int kStagingBytes = kStageOff + kEpiWarps * kStagePerWarp;   // 68 KB
+
 template <int BN_> struct TileCfg {
   static constexpr int BN = BN_;
   static constexpr int kBTileBytes = BN_ * BK * 2;      // one bf16 [BN x 64] B tile (hi or lo)
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
   // measured r01: 4/3 stages (1 CTA/SM) beat 2 stages (2 CTAs/SM, co-resident with other lanes' kernels): 4.98 vs 5.74 ms/forward
-  static constexpr int kStages = (BN_ == 128) ? 3 : 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 2048 /*descriptor copy*/ + 1024 /*alignment slack*/;
-  static constexpr uint32_t kTmemCols = 2 * BN_;                       // [0, BN): hi*hi + lo*hi, [BN, 2BN): hi*lo
+  static constexpr int kStagesSingle = (BN_ == 128) ? 3 : 4;   // a CTA with one tile: the epilogue stages its output in the idle stage buffers
+  static constexpr int kStagesMulti = (BN_ == 128) ? 2 : 3;    // a CTA with several tiles: dedicated staging area after the stages
+  static constexpr int kOffStagingMulti = kStagesMulti * kStageBytes;
+  static constexpr int kPipeBytes = (kStagesSingle * kStageBytes > kOffStagingMulti + kStagingBytes) ? kStagesSingle * kStageBytes : kOffStagingMulti + kStagingBytes;
+  static constexpr int kOffBar = kPipeBytes;
+  static constexpr int kOffDesc = kOffBar + 1024;
+  static constexpr int kSmemBytes = kOffDesc + 2048 /*descriptor copy*/ + 1024 /*alignment slack*/;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
 };
+static_assert(TileCfg<64>::kSmemBytes <= 227 * 1024 && TileCfg<128>::kSmemBytes <= 227 * 1024, "shared memory budget");
+
 
 // Store 32 consecutive output columns of one row in the layout(s) the op asks for.
 __device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, int t, long long m, int nbase, const float* val) {
@@ -104,11 +119,6 @@ __device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, 
   }
 }
 
-// Per-warp staging area of the epilogue (the pipeline stages are idle by then): 8 KB per warp =
-//   [0, 4096)    fp32 chunk  [32 rows][32 cols]  as a SWIZZLE_128B box image
-//   [4096, 6144) bf16 hi     [32 rows][32 cols]  as a SWIZZLE_64B box image,  [6144, 8192) bf16 lo
-constexpr int kStagePerWarp = 8192;
-constexpr int kStageOff = 4096;                        // after the GroupNorm partial sums
 __device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) {      // 16-byte group c4 (0..7) of row
   return reinterpret_cast<float*>(st + row * 128 + ((c4 ^ (row & 7)) << 4));
 }
@@ -154,21 +164,22 @@ __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64
 
 static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descriptor copy");
 
-template <int BN_, int CN>
+template <int BN_>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
-  constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytes = Cfg::kStageBytes;
+  constexpr int kAccCols = 2 * BN;                          // one accumulator buffer: [0,BN) hi*hi + lo*hi, [BN,2BN) hi*lo
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bar_base = base + kStages * kStageBytes;
+  const uint32_t bar_base = base + Cfg::kOffBar;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 1));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kOffBar + 8 * (2 * kMaxStages + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // The 1.7 KB operator descriptor lives in the kernel-parameter constant bank, which is cold at every
@@ -178,270 +189,291 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // TMA still gets the tensor maps by their parameter-space address.
   {
     const uint4* src = reinterpret_cast<const uint4*>(&op_param);
-    uint4* dst = reinterpret_cast<uint4*>(smem + kStages * kStageBytes + 1024);
+    uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc);
     for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
   }
-  const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + kStages * kStageBytes + 1024);
+  const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + Cfg::kOffDesc);
   const TMap* tmaps = op_param.tmap;
-  const int T_out_p = op_param.T_out;                        // the few fields needed before the copy is visible
-  const int tiles_per_batch = (T_out_p + BM - 1) / BM;
-  const int b = blockIdx.x / tiles_per_batch;
-  const int t0 = (blockIdx.x % tiles_per_batch) * BM;
-  const int n0 = blockIdx.y * BN;                           // first packed column of this tile
+  // Persistent tile loop: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile).
+  // A CTA with a single tile keeps all kMaxStages pipeline stages and stages its epilogue output in the (then idle)
+  // stage buffers; a CTA with several tiles gives the last stage(s) up for a dedicated staging area, so that the
+  // epilogue of tile i (TMEM accumulator buffer i & 1) runs under the main loop of tile i + 1.
+  const int tiles_per_batch = (op_param.T_out + BM - 1) / BM;
+  const int n_tiles = op_param.N / BN;
+  const int total_tiles = op_param.B * tiles_per_batch * n_tiles;
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool multi = my_tiles > 1;
+  const int nst = multi ? Cfg::kStagesMulti : Cfg::kStagesSingle;   // pipeline depth actually used
+  uint8_t* stage_area = smem + (multi ? Cfg::kOffStagingMulti : 0);
   const int nkb = op_param.nkb_total;
-  // Cluster of CN CTAs along N (same rows, different output columns): each CTA fetches 128/CN rows of every A
-  // box and multicasts them to the whole cluster, so the A tile crosses L2->SM once per cluster, not once per CTA.
-  const uint32_t crank = (CN > 1) ? cluster_ctarank() : 0u;
-  constexpr uint16_t kMcMask = (uint16_t)((1u << CN) - 1u);
-  constexpr int kARows = BM / CN;
-  if (tid == 0 && op_param.trace && blockIdx.x == 0 && blockIdx.y == 0) op_param.trace[0] = gtime();
+  const bool tr0 = blockIdx.x == 0;
+  if (tid == 0 && op_param.trace && tr0) op_param.trace[0] = gtime();
   span_begin(op_param.span);
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CN);                           // every CTA of the cluster releases the stage
-    }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), kEpiWarps); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), Cfg::kTmemCols);
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * op_param.nsrc; ++i) prefetch_tmap(&tmaps[i]);
   }
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
-  if (CN > 1) cluster_sync_all();                           // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) TRACE(1);
+  if (tid == 0 && tr0) TRACE(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // The weights do not depend on the previous kernel: their first stages are in flight before
+      // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
       // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
-      const int npre = nkb < kStages ? nkb : kStages;
-      for (int kb = 0; kb < npre; ++kb) {
-        const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
-        mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
-        const size_t eoff = ((size_t)kb * op.N + n0) * 64;
-        bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(kb));
-        bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
+      const int npre = nkb < nst ? nkb : nst;
+      {
+        const int n0 = ((int)blockIdx.x % n_tiles) * BN;
+        for (int kb = 0; kb < npre; ++kb) {
+          const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
+          mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+          const size_t eoff = ((size_t)kb * op.N + n0) * 64;
+          bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(kb));
+          bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
+        }
       }
       pdl_wait();
-      TRACE(2);
-      int si = 0, kbl = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int stage = kb % kStages;
-        const uint32_t parity = (uint32_t)((kb / kStages) & 1);
-        const GSeg& s = op.seg[si];
-        const uint32_t a_hi = base + stage * kStageBytes;
-        const uint32_t a_lo = a_hi + kATileBytes;
-        const uint32_t b_hi = a_lo + kATileBytes;
-        const uint32_t b_lo = b_hi + Cfg::kBTileBytes;
-        if (kb >= npre) {
-          mbar_wait(empty_bar(stage), parity ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
-          const size_t eoff = ((size_t)kb * op.N + n0) * 64;
-          bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
-          bulk_g2s(b_lo, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
-        }
-        const int c = s.c0 + kbl * 64;
-        if (CN == 1) {
+      if (tr0) TRACE(2);
+      int g = 0;                                            // k-block counter across this CTA's tiles
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+        const int b = mt / tiles_per_batch, t0 = (mt % tiles_per_batch) * BM;
+        int si = 0, kbl = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int stage = g % nst;
+          const GSeg& s = op.seg[si];
+          const uint32_t a_hi = base + stage * kStageBytes;
+          const uint32_t a_lo = a_hi + kATileBytes;
+          const uint32_t b_hi = a_lo + kATileBytes;
+          if (g >= npre) {
+            if (g >= nst) mbar_wait(empty_bar(stage), (uint32_t)(((g / nst) & 1) ^ 1));
+            mbar_arrive_expect_tx(full_bar(stage), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+            const size_t eoff = ((size_t)kb * op.N + n0) * 64;
+            bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(stage));
+            bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(stage));
+          }
+          const int c = s.c0 + kbl * 64;
           tma_load_3d(a_hi, &tmaps[2 * s.src], c, t0 + s.tap, b, full_bar(stage));
           tma_load_3d(a_lo, &tmaps[2 * s.src + 1], c, t0 + s.tap, b, full_bar(stage));
-        } else {
-          const uint32_t roff = crank * (kARows * 128);     // this CTA's slice of the 128-row box
-          tma_load_3d_mc(a_hi + roff, &tmaps[2 * s.src], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
-          tma_load_3d_mc(a_lo + roff, &tmaps[2 * s.src + 1], c, t0 + s.tap + (int)crank * kARows, b, full_bar(stage), kMcMask);
+          if (++kbl == s.nkb) { kbl = 0; ++si; }
         }
-        if (++kbl == s.nkb) { kbl = 0; ++si; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int stage = kb % kStages;
-        const uint32_t parity = (uint32_t)((kb / kStages) & 1);
-        mbar_wait(full_bar(stage), parity);
-        if (kb == 0) TRACE(3);
-        tc_fence_after();
-        const uint32_t a_hi = base + stage * kStageBytes;
-        const uint32_t a_lo = a_hi + kATileBytes;
-        const uint32_t b_hi = a_lo + kATileBytes;
+      int g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t acc = tmem_base + (uint32_t)((it & 1) * kAccCols);
+        if (it >= 2) { mbar_wait(acc_empty(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1)); tc_fence_after(); }   // epilogue of tile it-2 has drained this buffer
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int stage = g % nst;
+          mbar_wait(full_bar(stage), (uint32_t)((g / nst) & 1));
+          if (g == 0 && tr0) TRACE(3);
+          tc_fence_after();
+          const uint32_t a_hi = base + stage * kStageBytes;
+          const uint32_t a_lo = a_hi + kATileBytes;
+          const uint32_t b_hi = a_lo + kATileBytes;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
-          const uint64_t dbh = umma_desc(b_hi + k * 32);     // rows [0, BN) = B_hi tile, rows [BN, 2BN) = B_lo tile (adjacent)
-          umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc2, (kb | k) != 0 ? 1u : 0u);
-          umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
+            const uint64_t dbh = umma_desc(b_hi + k * 32);   // rows [0, BN) = B_hi tile, rows [BN, 2BN) = B_lo tile (adjacent)
+            umma_bf16(acc, dah, dbh, Cfg::kIdesc2, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(acc, dal, dbh, Cfg::kIdesc, 1u);
+          }
+          umma_commit(empty_bar(stage));                     // frees this smem stage when the MMAs retire
         }
-        if (CN == 1) umma_commit(empty_bar(stage));         // frees this smem stage when the MMAs retire
-        else umma_commit_mc(empty_bar(stage), kMcMask);     // ... in every CTA of the cluster (they multicast into it)
+        umma_commit(acc_full(it & 1));                       // accumulator complete -> epilogue
+        if (it == 0 && tr0) TRACE(4);
       }
-      umma_commit(tmem_full_bar);                           // accumulator complete -> epilogue
-      TRACE(4);
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     pdl_wait();                                             // residual reads / output writes follow the previous kernel
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
-    const int t = t0 + r;
-    const bool mv = t < op.T_out;
-    const long long m = (long long)b * op.T_out + t;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    // While the main loop runs these warps have nothing to do: fetch this thread's bias and residual values for
-    // its first 32-column chunk into registers now, so no global-load latency is left on the epilogue's critical path.
     const int cc0 = (warp - 2) >> 2;
-    float pre[32];                                          // bias + residual of chunk cc0 (plain path); GEGLU: value bias
-    float preg[32];                                         // GEGLU: gate bias
-    bool pre_ok = false;
-    if (op.flags & EPI_GEGLU) {
-      const int nb = blockIdx.y * 64 + cc0 * 32;
-      if (BN == 128 && nb + 32 <= op.n_valid) {
-        pre_ok = true;
-        const float4* bv = reinterpret_cast<const float4*>(op.bias + nb);
-        const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nb);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = __ldg(bv + j), y = __ldg(bg + j);
-          pre[4 * j] = x.x; pre[4 * j + 1] = x.y; pre[4 * j + 2] = x.z; pre[4 * j + 3] = x.w;
-          preg[4 * j] = y.x; preg[4 * j + 1] = y.y; preg[4 * j + 2] = y.z; preg[4 * j + 3] = y.w;
-        }
-      }
-    } else {
-      const int nb = n0 + cc0 * 32;
-      if (mv && nb + 32 <= op.n_valid && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
-        pre_ok = true;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) pre[j] = 0.f;
-        if (op.flags & EPI_BIAS) {
-          const float4* pb = reinterpret_cast<const float4*>(op.bias + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w; }
-        }
-        if (op.flags & EPI_RESIDUAL) {
-          const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w; }
-        }
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    if (warp == 2 && lane == 0) TRACE(5);
-    ETRACE(0);
-    tc_fence_after();
-    uint8_t* st = smem + kStageOff + (warp - 2) * kStagePerWarp;   // this warp's staging area
-    const int t_warp0 = t0 + q * 32;                        // first row of this warp's 32-row slab
+    uint8_t* st = stage_area + kStageOff + (warp - 2) * kStagePerWarp;   // this warp's staging area
     const TMap* tmo = op_param.tmap_out;
-    if (op.flags & EPI_GEGLU) {
-      if (BN == 128) {
-        const int hh = cc0;                                 // the two warps of a lane quarter take one half each
-        float val[32], gate[32];
-        tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
-        tmem_ld32_sum(trow + (uint32_t)(64 + hh * 32), trow + (uint32_t)(BN + 64 + hh * 32), gate);
-        const int nbase = blockIdx.y * 64 + hh * 32;        // logical output column
-        if (nbase < op.n_valid) {                           // (uniform across the warp)
-          if (!mv) {
+    bool staged_once = false;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int mt = tile / n_tiles, nt = tile % n_tiles, n0 = nt * BN;
+      const int b = mt / tiles_per_batch, t0 = (mt % tiles_per_batch) * BM;
+      const int t = t0 + r;
+      const bool mv = t < op.T_out;
+      const long long m = (long long)b * op.T_out + t;
+      const uint32_t trow = tmem_base + (uint32_t)((it & 1) * kAccCols) + ((uint32_t)(q * 32) << 16);
+      const int t_warp0 = t0 + q * 32;                      // first row of this warp's 32-row slab
+      // While the main loop runs these warps have nothing to do: fetch this thread's bias and residual values for
+      // its first 32-column chunk into registers now, so no global-load latency is left on the epilogue's critical path.
+      float pre[32];                                        // bias + residual of chunk cc0 (plain path); GEGLU: value bias
+      float preg[32];                                       // GEGLU: gate bias
+      bool pre_ok = false;
+      if (op.flags & EPI_GEGLU) {
+        const int nb = nt * 64 + cc0 * 32;
+        if (BN == 128 && nb + 32 <= op.n_valid) {
+          pre_ok = true;
+          const float4* bv = reinterpret_cast<const float4*>(op.bias + nb);
+          const float4* bg = reinterpret_cast<const float4*>(op.bias + op.n_valid + nb);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = 0.f;
-          } else if (pre_ok) {                              // biases were fetched before the accumulator wait
-#pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = (val[j] + pre[j]) * gelu_erf_f(gate[j] + preg[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = __ldg(bv + j), y = __ldg(bg + j);
+            pre[4 * j] = x.x; pre[4 * j + 1] = x.y; pre[4 * j + 2] = x.z; pre[4 * j + 3] = x.w;
+            preg[4 * j] = y.x; preg[4 * j + 1] = y.y; preg[4 * j + 2] = y.z; preg[4 * j + 3] = y.w;
           }
-          emit_chunk(op, tmo, st, lane, false, b, t, t_warp0, m, mv, nbase, val);
+        }
+      } else {
+        const int nb = n0 + cc0 * 32;
+        if (mv && nb + 32 <= op.n_valid && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+          pre_ok = true;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pre[j] = 0.f;
+          if (op.flags & EPI_BIAS) {
+            const float4* pb = reinterpret_cast<const float4*>(op.bias + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w; }
+          }
+          if (op.flags & EPI_RESIDUAL) {
+            const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w; }
+          }
         }
       }
-    } else {
-      float* sm_part = reinterpret_cast<float*>(smem);      // [4 quarters][BN][2] GroupNorm partial sums
-      const bool stage_f32 = (op.tma_out & 1) || (op.flags & EPI_STATS);
-      bool staged_once = false;
+      mbar_wait(acc_full(it & 1), (uint32_t)((it >> 1) & 1));
+      if (it == 0 && tr0 && warp == 2 && lane == 0) TRACE(5);
+      if (it == 0 && tr0) ETRACE(0);
+      tc_fence_after();
+      auto release_acc = [&]() {                            // this warp has read everything it needs from the accumulator buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(it & 1));
+      };
+      auto wait_staging = [&]() {                           // the TMA unit must have read the previous chunk out of the staging area
+        if (staged_once && op.tma_out) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+      };
+      if (op.flags & EPI_GEGLU) {
+        if (BN == 128) {
+          const int hh = cc0;                               // the two warps of a lane quarter take one half each
+          float val[32], gate[32];
+          tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
+          tmem_ld32_sum(trow + (uint32_t)(64 + hh * 32), trow + (uint32_t)(BN + 64 + hh * 32), gate);
+          release_acc();
+          const int nbase = nt * 64 + hh * 32;              // logical output column
+          if (nbase < op.n_valid) {                         // (uniform across the warp)
+            if (!mv) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = 0.f;
+            } else if (pre_ok) {                            // biases were fetched before the accumulator wait
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = (val[j] + pre[j]) * gelu_erf_f(gate[j] + preg[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
+            }
+            wait_staging();
+            emit_chunk(op, tmo, st, lane, false, b, t, t_warp0, m, mv, nbase, val);
+            staged_once = true;
+          }
+        } else {
+          release_acc();
+        }
+      } else {
+        float* sm_part = reinterpret_cast<float*>(stage_area) + (it & 1) * (4 * BN * 2);   // [4 quarters][BN][2] GroupNorm partial sums (per tile parity)
+        const bool stage_f32 = (op.tma_out & 1) || (op.flags & EPI_STATS);
 #pragma unroll 1
-      for (int cc = cc0; cc < BN / 32; cc += 2) {           // the two warps of a lane quarter alternate chunks
-        float acc[32];
-        tmem_ld32_sum(trow + (uint32_t)(cc * 32), trow + (uint32_t)(BN + cc * 32), acc);
-        ETRACE(1);
-        const int nbase = n0 + cc * 32;
-        const bool cvalid = nbase < op.n_valid;             // (uniform across the warp)
-        if (cvalid) {
-          const bool fullc = nbase + 32 <= op.n_valid;
-          if (!mv) {
+        for (int cc = cc0; cc < BN / 32; cc += 2) {         // the two warps of a lane quarter alternate chunks
+          float acc[32];
+          tmem_ld32_sum(trow + (uint32_t)(cc * 32), trow + (uint32_t)(BN + cc * 32), acc);
+          if (cc + 2 >= BN / 32) release_acc();
+          if (it == 0 && tr0) ETRACE(1);
+          const int nbase = n0 + cc * 32;
+          const bool cvalid = nbase < op.n_valid;           // (uniform across the warp)
+          if (cvalid) {
+            const bool fullc = nbase + 32 <= op.n_valid;
+            if (!mv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-          } else if (cc == cc0 && pre_ok) {
+              for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            } else if (cc == cc0 && pre_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += pre[j];
-          } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
-            if (op.flags & EPI_BIAS) {
-              const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
+              for (int j = 0; j < 32; ++j) acc[j] += pre[j];
+            } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+              if (op.flags & EPI_BIAS) {
+                const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+                for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pb + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+              }
+              if (op.flags & EPI_RESIDUAL) {
+                const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
             }
-            if (op.flags & EPI_RESIDUAL) {
-              const float4* pr = reinterpret_cast<const float4*>(op.res + m * op.res_ld + nbase);
+            if (it == 0 && tr0) ETRACE(2);
+            wait_staging();
+            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc);
+            staged_once = true;
+            if (it == 0 && tr0) ETRACE(3);
+            if (op.flags & EPI_STATS) {
+              // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm: read the staged
+              // chunk column-wise (one column per lane; a row's 32 columns are one permuted 128-byte line: conflict-free);
+              // the four lane quarters' partials are combined below so each column costs one atomic per CTA.
+              __syncwarp();
+              float cs = 0.f, cq = 0.f;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
+              for (int rr = 0; rr < 32; ++rr) { const float v = stage_f32_ptr(st, rr, lane >> 2)[lane & 3]; cs += v; cq += v * v; }
+              sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
+              sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
+              if (it == 0 && tr0) ETRACE(4);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
+          } else if (op.flags & EPI_STATS) {
+            sm_part[(q * BN + cc * 32 + lane) * 2] = 0.f;
+            sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = 0.f;
           }
-          ETRACE(2);
-          if (staged_once && op.tma_out) {                  // the TMA unit must have read the previous chunk out of the staging area
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-          }
-          emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc);
-          staged_once = true;
-          ETRACE(3);
-          if (op.flags & EPI_STATS) {
-            // per-(b, column) sum / sum-of-squares over this tile's rows for the consumer's GroupNorm: read the staged
-            // chunk column-wise (one column per lane; a row's 32 columns are one permuted 128-byte line: conflict-free);
-            // the four lane quarters' partials are combined below so each column costs one atomic per CTA.
-            __syncwarp();
-            float cs = 0.f, cq = 0.f;
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) { const float v = stage_f32_ptr(st, rr, lane >> 2)[lane & 3]; cs += v; cq += v * v; }
-            sm_part[(q * BN + cc * 32 + lane) * 2] = cs;
-            sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = cq;
-            ETRACE(4);
-          }
-        } else if (op.flags & EPI_STATS) {
-          sm_part[(q * BN + cc * 32 + lane) * 2] = 0.f;
-          sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = 0.f;
         }
-      }
-      if (op.flags & EPI_STATS) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps
-        ETRACE(5);
-        const int col = tid - 64;                           // 0..127
-        if (col < BN && n0 + col < op.n_valid) {
-          double cs = 0, cq = 0;
+        if (op.flags & EPI_STATS) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 epilogue warps
+          if (it == 0 && tr0) ETRACE(5);
+          const int col = tid - 64;                         // 0..127
+          if (col < BN && n0 + col < op.n_valid) {
+            double cs = 0, cq = 0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { cs += (double)sm_part[(w * BN + col) * 2]; cq += (double)sm_part[(w * BN + col) * 2 + 1]; }
-          atomicAdd(op.stat_sum + (long long)b * op.n_valid + n0 + col, cs);
-          atomicAdd(op.stat_sq + (long long)b * op.n_valid + n0 + col, cq);
+            for (int w = 0; w < 4; ++w) { cs += (double)sm_part[(w * BN + col) * 2]; cq += (double)sm_part[(w * BN + col) * 2 + 1]; }
+            atomicAdd(op.stat_sum + (long long)b * op.n_valid + n0 + col, cs);
+            atomicAdd(op.stat_sq + (long long)b * op.n_valid + n0 + col, cq);
+          }
         }
       }
     }
     if (op.tma_out && lane == 0) bulk_wait_all();           // the bulk stores of this warp have landed
   }
-  if (warp == 2 && lane == 0) TRACE(6);
-  ETRACE(6);
+
+  if (warp == 2 && lane == 0 && tr0) TRACE(6);
+  if (tr0) ETRACE(6);
   tc_fence_before();
   __syncthreads();
-  ETRACE(7);
-  if (CN > 1) cluster_sync_all();                           // nobody exits while a peer may still multicast / signal into it
-  if (tid == 0) TRACE(7);
+  if (tr0) ETRACE(7);
+  if (tid == 0 && tr0) TRACE(7);
   span_end(op.span);
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -508,7 +540,7 @@ int encode_tmaps(GemmOp& op) {
     }
   }
   for (int i = 0; i < op.nsrc; ++i) {
-    const int box_rows = BM / (op.cn > 0 ? op.cn : 1);
+    const int box_rows = BM;
     int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);
     if (rc) return rc;
     rc = encode_one(&op.tmap[2 * i + 1], op.src[i].lo, op.src[i], op.B, box_rows);
@@ -517,46 +549,47 @@ int encode_tmaps(GemmOp& op) {
   return 0;
 }
 
-template <int BN_, int CN>
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN_>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
-  dim3 grid(op.B * ceil_div(op.T_out, BM), op.N / BN_);
-  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, CN>, grid, dim3(kThreads), (size_t)Cfg::kSmemBytes, st, dim3(1, CN, 1), op);
+  // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
+  const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  cudaError_t e = launch_k(gemm_tc_kernel<BN_>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
 void plan_gemm(GemmOp& op) {
-  // N-tile: 128 wide when that already fills the 148 SMs, else 64 wide (twice the CTAs; the
-  // GEGLU epilogue pairs value|gate inside a 128-column block and needs BN = 128).
-  const int ctas128 = op.B * ceil_div(op.T_out, BM) * (op.N / 128);
-  op.bn = ((op.flags & EPI_GEGLU) || ctas128 >= 120) ? 128 : 64;
-  const int ntiles = op.N / op.bn;
-  static int mc = -1;
-  // measured r01 (cfg2): multicast 4.65 ms vs 4.54 ms per forward without -> the 3xBF16 main loop is bound by
-  // shared-memory bandwidth (MMA operand reads + TMA fills), not by L2->SM traffic; kept as an opt-in.
-  if (mc < 0) { const char* e = getenv("NS2VC_MULTICAST"); mc = (e && e[0] == '1') ? 1 : 0; }
-  op.cn = !mc ? 1 : (ntiles % 4 == 0) ? 4 : (ntiles % 2 == 0) ? 2 : 1;
+  // N tile: 64 wide (more, smaller tiles balance better over the persistent CTAs); the GEGLU epilogue pairs
+  // value|gate inside a 128-column block and needs BN = 128.
+  // (TMA multicast clusters along N were measured slower in r01 — 4.65 vs 4.54 ms per forward — and were removed.)
+  op.bn = (op.flags & EPI_GEGLU) ? 128 : 64;
+  op.cn = 1;
 }
 
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
-  if (op.bn == 128) {
-    if (op.cn == 4) return launch_bn<128, 4>(op, st);
-    if (op.cn == 2) return launch_bn<128, 2>(op, st);
-    return launch_bn<128, 1>(op, st);
-  }
+  if (op.bn == 128) return launch_bn<128>(op, st);
   if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
-  if (op.cn == 4) return launch_bn<64, 4>(op, st);
-  if (op.cn == 2) return launch_bn<64, 2>(op, st);
-  return launch_bn<64, 1>(op, st);
+  return launch_bn<64>(op, st);
 }
 
 }  // namespace ns2vc
