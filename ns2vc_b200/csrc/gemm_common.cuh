@@ -47,6 +47,31 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = pack_bf16x2(la, lb);
 }
 
+// erf-GELU of two values at once on the packed fp32x2 pipes (same A&S 7.1.26 polynomial as gelu_erf_f)
+__device__ __forceinline__ unsigned long long gelu_erf2(unsigned long long v2) {
+  float a, b;
+  upk2(v2, a, b);
+  const unsigned long long x2 = pk2(fabsf(a) * 0.70710678118654752440f, fabsf(b) * 0.70710678118654752440f);
+  float da, db;
+  upk2(ffma2(pk2(0.3275911f, 0.3275911f), x2, pk2(1.0f, 1.0f)), da, db);
+  float ta, tb;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(da));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(db));
+  const unsigned long long t2 = pk2(ta, tb);
+  unsigned long long p2 = ffma2(t2, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
+  p2 = ffma2(t2, p2, pk2(1.421413741f, 1.421413741f));
+  p2 = ffma2(t2, p2, pk2(-0.284496736f, -0.284496736f));
+  p2 = ffma2(t2, p2, pk2(0.254829592f, 0.254829592f));
+  float ea, eb;
+  upk2(fmul2(fmul2(x2, x2), pk2(-1.4426950408889634f, -1.4426950408889634f)), ea, eb);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(ea));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(eb));
+  float ra, rb;
+  upk2(fsub2(pk2(1.0f, 1.0f), fmul2(fmul2(p2, t2), pk2(ea, eb))), ra, rb);     // erf(|x|)
+  const unsigned long long one_plus = fadd2(pk2(1.0f, 1.0f), pk2(copysignf(ra, a), copysignf(rb, b)));
+  return fmul2(fmul2(v2, pk2(0.5f, 0.5f)), one_plus);
+}
+
 // fp16 flavour of split2 / split8 (operands of the attention's fp16 P x V product)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) { uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
 __device__ __forceinline__ float f16lo_to_f32(uint32_t h2) { float f; asm("{.reg .f16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(f) : "r"(h2)); return f; }

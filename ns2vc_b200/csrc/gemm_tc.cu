@@ -381,7 +381,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               for (int j = 0; j < 32; ++j) val[j] = 0.f;
             } else if (pre_ok) {                            // biases were fetched before the accumulator wait
 #pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = (val[j] + pre[j]) * gelu_erf_f(gate[j] + preg[j]);
+              for (int j = 0; j < 32; j += 2)
+                upk2(fmul2(fadd2(pk2(val[j], val[j + 1]), pk2(pre[j], pre[j + 1])), gelu_erf2(fadd2(pk2(gate[j], gate[j + 1]), pk2(preg[j], preg[j + 1])))),
+                     val[j], val[j + 1]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
