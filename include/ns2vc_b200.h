@@ -120,7 +120,8 @@ int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
  * stamps of the epilogue sub-steps.  NULL disables. */
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
 /* Diagnostics: attention launch i of the next forward writes per-key-tile SM-clock stamps of its CTA (0,0,0)
- * to device_buf[256*i ...] ([16 tiles][16 slots], see attention_v2.cu).  NULL disables. */
+ * to device_buf[2048*i ...] ([16 tiles][16 slots], then [start ns, end ns, SM id] of up to 597 CTAs; see attention_v2.cu).
+ * NULL disables. */
 int ns2vc_unet_set_attn_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_launches);
 /* [min entry, max exit] %globaltimer of every launch of the next forwards (buffer pre-set to {~0, 0} pairs). */
 int ns2vc_unet_set_span_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_launches);

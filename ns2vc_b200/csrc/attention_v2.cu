@@ -27,9 +27,9 @@ namespace ns2vc {
 namespace {
 
 constexpr int kQ = 128, kKeys = 64;
-constexpr int kThreadsV2 = 320;
+constexpr int kThreadsV2 = 288;                          // warp 0: TMA producer (lane 0) + MMA issuer (lane 1); warps 1-8: softmax
 
-template <int DHP, int PB, bool PF16> struct ACfg {
+template <int DHP, int PB, bool PF16, bool BIAS> struct ACfg {
   static constexpr int NST = (PB == 128) ? 2 : 3;
   static constexpr int kQBytes = kQ * PB;            // Q hi (lo follows)
   static constexpr int kTBytes = kKeys * PB;         // one K or V tile (hi or lo)
@@ -42,7 +42,7 @@ template <int DHP, int PB, bool PF16> struct ACfg {
   static constexpr int kOffXch = kOffBar + 256;      // [3: parity 0 / parity 1 / row sums][2 halves][128 rows] floats
   static constexpr int kOffBias = kOffXch + 3072;    // additive bias * log2(e) (or -inf past Tk) for up to kBiasKeys keys
   static constexpr int kBiasKeys = 1024;
-  static constexpr int kSmem = kOffBias + 4 * kBiasKeys + 1024 /*alignment slack*/;
+  static constexpr int kSmem = kOffBias + (BIAS ? 4 * kBiasKeys : 0) + 1024 /*alignment slack*/;
   static constexpr int NO = PB / 2;                  // channels per V tile row = width of one O column group
   // TMEM: S = x_hi*[y_hi ; y_lo] lands in two column groups when the K tiles are issued as one N = 128 operand (SC);
   // for 32-byte head rows (dh = 16) S stays three plain N = 64 MMAs so that 128 columns (-> 3 CTAs / SM) suffice.
@@ -50,7 +50,7 @@ template <int DHP, int PB, bool PF16> struct ACfg {
   static constexpr int kSCols = SC ? 128 : 64;
   static constexpr int kOCols = 2 * NO;              // one O buffer: [0,NO) hi*hi + lo*hi, [NO,2NO) hi*lo
   static constexpr int kTmemCols = (kSCols + 2 * kOCols <= 128) ? 128 : (kSCols + 2 * kOCols <= 256) ? 256 : 512;
-  static constexpr int kBySmem = (kSmem <= 74 * 1024) ? 3 : (kSmem <= 113 * 1024) ? 2 : 1;
+  static constexpr int kBySmem = (kSmem <= 56 * 1024) ? 4 : (kSmem <= 74 * 1024) ? 3 : (kSmem <= 113 * 1024) ? 2 : 1;
   static constexpr int kMinCtas = (512 / kTmemCols < kBySmem) ? 512 / kTmemCols : kBySmem;
 };
 
@@ -80,8 +80,8 @@ __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int DHP, int PB, bool BIAS, bool PF16>
-__global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) attn_v2_kernel(const __grid_constant__ AttnOp op) {
-  using C = ACfg<DHP, PB, PF16>;
+__global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCtas) attn_v2_kernel(const __grid_constant__ AttnOp op) {
+  using C = ACfg<DHP, PB, PF16, BIAS>;
   constexpr int NST = C::NST;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -99,13 +99,20 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
   const int ntiles = (op.Tk + kKeys - 1) / kKeys;
 
   span_begin(op.span);
-  unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp <= 2) ? op.trace : nullptr;
+  // diagnostics: [start, end, SM id] of every CTA at trace[256 + 3 * linear CTA id] (globaltimer ns)
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (op.trace && tid == 0 && cta_lin < 597) {
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    op.trace[256 + 3 * cta_lin] = gtime_ns();
+    op.trace[256 + 3 * cta_lin + 2] = smid;
+  }
+  unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ((warp == 0 && lane <= 1) || (warp == 1 && lane == 0))) ? op.trace : nullptr;
   if (tid == 0) {
     mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1);
     for (int s = 0; s < NST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), C::kTmemCols);
   if (warp == 0 && lane == 0) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) prefetch_tmap(&op.tm[i]);
@@ -118,6 +125,8 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
   const uint32_t tS = tmem_base, tO = tmem_base + C::kSCols;   // O: two buffers of kOCols columns (tile parity)
   const uint32_t sQ = base + C::kOffQ, sP = base + C::kOffP, sKV = base + C::kOffKV;
 
+  // Warp 0 hosts two independent single-thread roles as divergent lanes (independent thread scheduling): lane 0 streams
+  // the tiles, lane 1 issues the MMAs.  Eight softmax warps + this one = 288 threads, so that four CTAs fit an SM.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -136,10 +145,8 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
         tma_load_3d(dst + 2 * C::kTBytes, &op.tm[4], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
         tma_load_3d(dst + 3 * C::kTBytes, &op.tm[5], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    } else if (lane == 1) {
+      // ===================== MMA issuer =====================
       // Every product is hi*hi + hi*lo + lo*hi.  The hi and lo tiles of K (and of V) are adjacent in shared memory,
       // so X_hi x [Y_hi ; Y_lo] is ONE instruction of twice the N whose result lands in two TMEM column groups;
       // X_lo x Y_hi accumulates into the first group and the softmax warps add the groups.  (A tcgen05.mma of
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
   } else {
     // ===================== softmax warps =====================
     constexpr int OH = DHP / 2;                             // output columns per thread
-    const int qtr = warp & 3, hf = (warp - 2) >> 2;
+    const int qtr = warp & 3, hf = (warp - 1) >> 2;
     const int r = qtr * 32 + lane;                          // query row = TMEM lane
     const uint32_t lane_base = ((uint32_t)(qtr * 32)) << 16;
     float* xch = reinterpret_cast<float*>(smem + C::kOffXch);
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
     pdl_wait();                                             // the mask bias and the output buffers belong to earlier kernels
     if (BIAS) {                                             // additive mask bias * log2(e); -inf past Tk
       const float* bias = op.bias + (long long)b * op.Tk;
-      for (int i = tid - 64; i < ntiles * kKeys; i += 256)
+      for (int i = tid - 32; i < ntiles * kKeys; i += 256)
         bias_s[i] = (i < op.Tk) ? __ldg(bias + i) * 1.4426950408889634f : -INFINITY;
       asm volatile("bar.sync 5, 256;" ::: "memory");
     }
@@ -369,16 +376,24 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16>::kMinCtas) att
   tc_fence_before();
   __syncthreads();
   span_end(op.span);
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (op.trace && tid == 0 && cta_lin < 597) op.trace[256 + 3 * cta_lin + 1] = gtime_ns();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 template <int DHP, int PB, bool BIAS, bool PF16>
 int launch_v2b(const AttnOp& op, cudaStream_t st) {
-  using C = ACfg<DHP, PB, PF16>;
+  using C = ACfg<DHP, PB, PF16, BIAS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_v2_kernel<DHP, PB, BIAS, PF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) { set_error("attention v2: cannot set %d B dynamic smem: %s", C::kSmem, cudaGetErrorString(e)); return -2; }
+    // ask for the largest shared-memory carve-out: the CTA count per SM is what the smem budget above was sized for
+    cudaFuncSetAttribute(attn_v2_kernel<DHP, PB, BIAS, PF16>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (getenv("NS2VC_DEBUG")) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_v2_kernel<DHP, PB, BIAS, PF16>, kThreadsV2, (size_t)C::kSmem);
+      fprintf(stderr, "ns2vc: attn_v2<%d,%d,bias=%d,f16=%d> smem %d B, planned %d CTAs/SM, occupancy API says %d\n", DHP, PB, (int)BIAS, (int)PF16, C::kSmem, C::kMinCtas, nb);
+    }
     attr_set = true;
   }
   dim3 grid(ceil_div(op.Tq, kQ), op.H, op.B);
@@ -392,7 +407,7 @@ bool p_fp16() { return attention_v2_p_fp16(); }
 template <int DHP, int PB>
 int launch_v2(const AttnOp& op, cudaStream_t st) {
   if (op.bias) {
-    if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB, true>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
+    if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB, true, true>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
     return p_fp16() ? launch_v2b<DHP, PB, true, true>(op, st) : launch_v2b<DHP, PB, true, false>(op, st);
   }
   return p_fp16() ? launch_v2b<DHP, PB, false, true>(op, st) : launch_v2b<DHP, PB, false, false>(op, st);

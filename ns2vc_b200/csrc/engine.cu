@@ -837,7 +837,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
         AttnOp a = l.attn;
         if (l.i0 == 1 && !h->has_mask) a.bias = nullptr;
         if (h->span && count < h->span_cap) a.span = h->span + 2 * count;
-        if (h->attn_trace && attn_idx < h->attn_trace_cap) a.trace = h->attn_trace + 256 * attn_idx;
+        if (h->attn_trace && attn_idx < h->attn_trace_cap) a.trace = h->attn_trace + 2048 * attn_idx;
         ++attn_idx;
         rc = (a.v2 && !h->simt) ? launch_attention_v2(a, st) : launch_attention(a, st, h->simt);
         break;
