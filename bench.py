@@ -212,7 +212,7 @@ def ncu_traffic(kernel):
     if not os.path.exists(p):
         return None
     tab = json.load(open(p))
-    pref = "gemm_tc_kernel" if kernel == "gemm_tc" else "attn_tc_kernel"
+    pref = "gemm_tc_kernel" if kernel == "gemm_tc" else "attn_v2_kernel"
     n = sum(v["launches"] for k, v in tab.items() if k.startswith(pref))
     tot = sum(v["launches"] * v["dram_bytes_per_launch"] for k, v in tab.items() if k.startswith(pref))
     return tot / n if n else None
