@@ -189,9 +189,18 @@ __device__ __forceinline__ void prep_finish(const PrepOp& op, int b, int C, cons
 __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   span_begin(op.span);
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
   const int C = op.C1 + op.C2;
+  // GroupNorm gamma / beta are weights: fetch them before griddepcontrol.wait (C <= 4 * 256 per thread slot)
+  float pg[4], pb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = threadIdx.x + k * 256;
+    const bool ok = op.mode != PREP_RAW && !op.scale && c < C;
+    pg[k] = ok ? __ldg(op.gn.gamma + c) : 0.f;
+    pb[k] = ok ? __ldg(op.gn.beta + c) : 0.f;
+  }
+  pdl_wait();
   const int b = blockIdx.y;
   const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
   const int total = op.T_dst * chunks;
@@ -229,10 +238,13 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
         }
       }
       __syncthreads();
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c >= C) break;
         const int grp = c / cpg;
-        float ga = g.gamma[c] * gmean[g.G + grp];
-        float be = g.beta[c] - gmean[grp] * ga;
+        float ga = pg[k] * gmean[g.G + grp];
+        float be = pb[k] - gmean[grp] * ga;
         if (g.film) {
           const float fs = 1.f + g.film[(long long)b * g.film_ld + c];
           const float fb = g.film[(long long)b * g.film_ld + C + c];
@@ -263,7 +275,7 @@ int launch_prep_split(const PrepOp& op, cudaStream_t st) {
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   const size_t smem = (op.mode != PREP_RAW) ? (size_t)(2 * C + 2 * 64) * sizeof(float) : 0;
-  if (smem > 48 * 1024) { set_error("prep_split: C=%d too large", C); return -1; }
+  if (smem > 48 * 1024 || (op.mode != PREP_RAW && !op.scale && C > 1024)) { set_error("prep_split: C=%d too large", C); return -1; }
   cudaError_t e = launch_k(prep_split_kernel, dim3(bx, op.B), dim3(256), smem, st, op);
   if (e != cudaSuccess) { set_error("prep_split launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
@@ -275,12 +287,29 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
                                                        SplitBuf out, unsigned long long* span) {
   span_begin(span);
   pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  constexpr int kMaxChunks = 4;                            // 8-channel chunks per lane: C <= 32*8*4
+  // gamma / beta are weights: fetch them while the producer of x is still running (before griddepcontrol.wait)
+  float gm[kMaxChunks][8], bt[kMaxChunks][8];
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int c0 = (lane + 32 * k) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gm[k][j] = 0.f; bt[k][j] = 0.f; }
+    if (c0 + 8 <= C && ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+      gm[k][0] = g0.x; gm[k][1] = g0.y; gm[k][2] = g0.z; gm[k][3] = g0.w; gm[k][4] = g1.x; gm[k][5] = g1.y; gm[k][6] = g1.z; gm[k][7] = g1.w;
+      bt[k][0] = b0.x; bt[k][1] = b0.y; bt[k][2] = b0.z; bt[k][3] = b0.w; bt[k][4] = b1.x; bt[k][5] = b1.y; bt[k][6] = b1.z; bt[k][7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c0 + j < C) { gm[k][j] = __ldg(gamma + c0 + j); bt[k][j] = __ldg(beta + c0 + j); }
+    }
+  }
+  pdl_wait();
   if (row >= M) { span_end(span); return; }
   const float* xr = x + (long long)row * ld;
-  constexpr int kMaxChunks = 4;                            // 8-channel chunks per lane: C <= 32*8*4
   float v[kMaxChunks][8];
   const int chunks = (C + 7) >> 3;
   float s = 0.f;
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
-        y[j] = (c < C) ? (v[k][j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+        y[j] = (c < C) ? (v[k][j] - mean) * rstd * gm[k][j] + bt[k][j] : 0.f;
       }
       uint4 hi, lo;
       split8(y, hi, lo);
