@@ -445,10 +445,35 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinOp op) {
   float acc[kLinRows];
 #pragma unroll
   for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = __ldg(wr + k);
+  if ((K & 127) == 0 && (reinterpret_cast<uintptr_t>(wr) & 15) == 0) {
+    // the weight row is the only HBM traffic: issue up to four 16-byte loads per lane before the first FMA so a warp
+    // pays one memory latency per 512 weights instead of one per 32
+    for (int k0 = 0; k0 < K; k0 += 512) {
+      float4 w[4];
 #pragma unroll
-    for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(xs[r * K + k], w, acc[r]);
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * 128 + lane * 4;
+        w[u] = (k < K) ? __ldg(reinterpret_cast<const float4*>(wr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * 128 + lane * 4;
+        if (k < K) {
+#pragma unroll
+          for (int r = 0; r < kLinRows; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + r * K + k);
+            acc[r] = fmaf(xv.x, w[u].x, acc[r]); acc[r] = fmaf(xv.y, w[u].y, acc[r]);
+            acc[r] = fmaf(xv.z, w[u].z, acc[r]); acc[r] = fmaf(xv.w, w[u].w, acc[r]);
+          }
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float w = __ldg(wr + k);
+#pragma unroll
+      for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(xs[r * K + k], w, acc[r]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < kLinRows; ++r) acc[r] = warp_sum(acc[r]);

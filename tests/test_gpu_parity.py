@@ -105,9 +105,11 @@ def test_full_forward_matches_reference_fixture(gold, full_model):
     assert ok, msg
 
 
-@pytest.mark.parametrize("B,T,S", [(2, 1024, 256), (1, 1000, 100), (1, 1023, 7), (3, 8, 1)])
+@pytest.mark.parametrize("B,T,S", [(2, 1024, 256), (1, 1000, 100), (1, 1023, 7), (3, 8, 1), (1, 2048, 300), (1, 136, 1100)])
 def test_full_forward_vs_oracle_shapes(full_model, B, T, S):
-    """config-2 sequence length, lengths that are not multiples of 8 (forced-size upsample), T=8 minimum."""
+    """config-2 sequence length, lengths that are not multiples of 8 (forced-size upsample), T=8 minimum, the cfg3
+    length (T=2048: several persistent-GEMM tiles per CTA, 32 key tiles per attention row) and a prompt longer than
+    the staged-bias capacity of the TMA-fed attention kernel (S=1100: the whole model falls back to the v1 kernel)."""
     m, sd = full_model
     inp = make_inputs(B, T, S, ragged=True, seed=40 + T)
     x, ehs, mask = unet_inputs(inp)
