@@ -351,6 +351,8 @@ def main():
         traffic = ncu_traffic(dom)
         out["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                            "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, cold-cache capture in profiles/r01_ncu_launches.md)", "algorithmic": alg, "peak_source": peaks["src"],
+                           "issued_tflops": 3 * ach if dom == "gemm_tc" else ach, "frac_issued": (3 * ach if dom == "gemm_tc" else ach) / peaks["tflops"],
+                           "note": "fp32-level parity forces 3 bf16 MMAs per product term set (hi*hi, hi*lo, lo*hi): issued = 3 x algorithmic; at M=128 tiles a tcgen05.mma costs ~80-110 cycles whatever its N (profiles/r01_*_incta_timeline.txt), so launches of <=148 tiles are bound by instruction count and the 335-launch dependency chain, not by the pipe's FLOP rate",
                            "launch_avg_us": 1e3 * prof[dom][0] / prof[dom][1], "timing": f"CUDA events around each launch, {nprof} forwards, profiling pass outside the timed region"}
         out["kernels"] = kernels
         whole = flops_per_forward(cfg, B, T, S)[0]

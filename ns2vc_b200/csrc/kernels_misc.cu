@@ -414,7 +414,29 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinOp op) {
   const int m0 = blockIdx.y * kLinRows;
   const int rows = min(kLinRows, op.M - m0);
   const int K = op.K;
-  for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
+  const bool vec_in = op.in_mode != LIN_SINUSOID && op.x_ld == K && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(op.x) & 15) == 0;
+  if (vec_in) {
+    // contiguous input rows: all 16-byte loads of this thread are in flight before the first use
+    const float4* xin = reinterpret_cast<const float4*>(op.x + (long long)m0 * K);
+    const int n4 = rows * K / 4;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = (i < n4) ? __ldg(xin + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < n4) {
+          if (op.in_mode == LIN_SILU) {
+            v[u].x = v[u].x / (1.0f + expf(-v[u].x)); v[u].y = v[u].y / (1.0f + expf(-v[u].y));
+            v[u].z = v[u].z / (1.0f + expf(-v[u].z)); v[u].w = v[u].w / (1.0f + expf(-v[u].w));
+          }
+          reinterpret_cast<float4*>(xs)[i] = v[u];
+        }
+      }
+    }
+  }
+  for (int i = threadIdx.x; !vec_in && i < rows * K; i += blockDim.x) {
     int r = i / K, k = i % K;
     float v;
     if (op.in_mode == LIN_SINUSOID) {
