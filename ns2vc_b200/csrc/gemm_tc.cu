@@ -465,7 +465,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
     }
-    if (op.tma_out && lane == 0) bulk_wait_all();           // the bulk stores of this warp have landed
+    // Shared memory must outlive the TMA unit's reads of the staged chunks; the writes themselves are made visible to the
+    // dependent grid by grid completion (griddepcontrol.wait on the other side), as in CUTLASS' tma_store_wait.
+    if (op.tma_out && lane == 0) { if (op.tma_out & 4) bulk_wait_all(); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
   }
 
   if (warp == 2 && lane == 0 && tr0) TRACE(6);
@@ -526,6 +528,8 @@ int encode_tmaps(GemmOp& op) {
   static int tma_st = -1;
   if (tma_st < 0) { const char* e = getenv("NS2VC_TMA_STORE"); tma_st = (e && e[0] == '0') ? 0 : 1; }
   op.tma_out = 0;
+  static int full_wait = -1;                                // NS2VC_TMA_WAIT=full: wait for the bulk stores to land before the CTA exits
+  if (full_wait < 0) { const char* e = getenv("NS2VC_TMA_WAIT"); full_wait = (e && e[0] == 'f') ? 1 : 0; }
   if (tma_st && !(op.flags & EPI_OUT_NCT)) {
     if ((op.flags & EPI_OUT_F32) && op.out && (op.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(op.out) & 15) == 0) {
       int rc = encode_tmap_any(&op.tmap_out[0], op.out, 4, op.n_valid, op.T_out, op.B, op.out_ld, 32, 32, 128);
@@ -541,6 +545,7 @@ int encode_tmaps(GemmOp& op) {
       op.tma_out |= 2;
     }
   }
+  if (op.tma_out && full_wait) op.tma_out |= 4;
   for (int i = 0; i < op.nsrc; ++i) {
     const int box_rows = BM;
     int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);
