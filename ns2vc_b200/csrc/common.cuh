@@ -80,6 +80,9 @@ enum EpiFlags : int {
   EPI_OUT_F32 = 32,   // store fp32 token-major out[m*out_ld + n]
   EPI_OUT_SPLIT = 64, // store bf16 hi/lo token-major (feeds the next GEMM's TMA)
   EPI_STATS = 128,    // accumulate per-(b, column) sum / sum-of-squares of the fp32 output (GroupNorm of the consumer)
+  EPI_LNFOLD = 256,   // the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights:
+                      //   acc <- rstd_row * (acc - mean_row * ln_g[n]);  bias then carries beta.W + bias   (see engine.cu)
+  EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
 };
 
 struct GemmOp {
@@ -108,6 +111,10 @@ struct GemmOp {
   __nv_bfloat16* out_lo;
   int out_split_ld;
   int n_valid;                 // logical output columns written (<= N, or N/2 for GEGLU)
+  const double* ln_stats;      // EPI_LNFOLD: [B*T_out][2] row sum / sum of squares of the LayerNorm input (over ln_C channels)
+  const float* ln_g;           // EPI_LNFOLD: [n logical] sum_c gamma_c W[n, c]  (GEGLU: value rows then gate rows, like bias)
+  int ln_C; float ln_eps;
+  double* row_stats;           // EPI_ROWSTATS: [B*T_out][2], pre-zeroed
   int f16_col0;                // split output columns >= f16_col0 (a multiple of 32) are written as FP16 hi/lo instead of bf16
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
@@ -140,6 +147,7 @@ struct PackSeg {
   int kb0;            // first k-block in the packed K order
   int nkb;
   int geglu_half;     // 0: plain. >0: interleave value/gate (value rows [0,half), gate rows [half,2*half))
+  const float* cscale; // optional per-input-channel multiplier [cin_total] (LayerNorm gamma folded into the weights), or nullptr
 };
 int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, float* w_f32, int Npad,
                   cudaStream_t st);

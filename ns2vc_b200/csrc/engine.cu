@@ -59,6 +59,11 @@ struct XformerSite {
   PackedB proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
   int kv_off = 0;            // column offset of this block's K in the cross K/V cache (all K first ...)
   int v_off = 0;             // ... then all V: column offset of this block's V
+  // LayerNorm folded into the consumer GEMM (norm1 -> qkv, norm2 -> q2, norm3 -> ff1): the packed weights carry gamma,
+  // g[n] = sum_c gamma_c W[n,c] and bf[n] = sum_c beta_c W[n,c] (+ bias[n]) feed the epilogue (EPI_LNFOLD)
+  float* g_qkv = nullptr; float* bf_qkv = nullptr;
+  float* g_q2 = nullptr; float* bf_q2 = nullptr;
+  float* g_ff1 = nullptr; float* bf_ff1 = nullptr;
 };
 struct ConvSite { std::string p; int c; PackedB w; };
 
@@ -126,6 +131,7 @@ struct ns2vc_unet {
   std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
+  bool lnfold = true;        // LayerNorms of the transformer folded into their consumer GEMMs (NS2VC_LNFOLD=0: separate LN kernels)
   unsigned long long* trace = nullptr; int trace_cap = 0;
   unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
   unsigned long long* span = nullptr; int span_cap = 0;   // [launch][2] grid spans
@@ -283,11 +289,32 @@ int alloc_packed(ns2vc_unet* h, PackedB& pb, int n_logical, int n_packed, int nk
 }
 
 // Pack `w` ([n_rows, cin_total, ktaps]) channels [cin0, cin0+ncin) of tap `tap` at k-block kb0, columns n_dst0..
+__global__ void ln_fold_vec_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ bias, float* __restrict__ g, float* __restrict__ bf, int N, int C) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  double sg = 0, sb = 0;                                   // load-time only: accumulate in double
+  for (int c = lane; c < C; c += 32) { const double w = W[(long long)n * C + c]; sg += w * gamma[c]; sb += w * beta[c]; }
+  for (int o = 16; o > 0; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+  if (lane == 0) { g[n] = (float)sg; bf[n] = (float)(sb + (bias ? (double)bias[n] : 0.0)); }
+}
+// g / bf of a [N, C] linear that consumes LayerNorm(gamma, beta) (rows n_dst0.. of the output vectors)
+int ln_fold_vectors(ns2vc_unet* h, const std::string& wname, const std::string& bname, const std::string& norm, int N, int C,
+                    float* g, float* bf, int n_dst0, cudaStream_t st) {
+  const float* W = h->W(wname); const float* ga = h->W(norm + ".weight"); const float* be = h->W(norm + ".bias");
+  NS_REQUIRE(W && ga && be, "ln fold: %s / %s missing", wname.c_str(), norm.c_str());
+  const float* bias = bname.empty() ? nullptr : h->W(bname);
+  ln_fold_vec_kernel<<<ceil_div(N, 8), 256, 0, st>>>(W, ga, be, bias, g + n_dst0, bf + n_dst0, N, C);
+  NS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int pack_seg(ns2vc_unet* h, PackedB& pb, const std::string& wname, int n_rows, int cin_total, int ktaps, int tap, int cin0,
-             int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st) {
+             int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st, const float* cscale = nullptr) {
   const float* w = h->W(wname);
   NS_REQUIRE(w != nullptr, "pack: weight %s missing", wname.c_str());
   PackSeg ps;
+  ps.cscale = cscale;
   ps.w = w; ps.n_rows = n_rows; ps.cin_total = cin_total; ps.ktaps = ktaps; ps.tap = tap; ps.cin0 = cin0; ps.ncin = ncin;
   ps.n_dst0 = n_dst0; ps.kb0 = kb0; ps.nkb = nkb_of(ncin); ps.geglu_half = geglu_half;
   return launch_pack_b(ps, pb.hi, pb.lo, pb.f32, pb.Npad, st);
@@ -344,17 +371,27 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
       if ((rc = pack_seg(h, x.proj_in, x.p + ".proj_in.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.qkv, 3 * C, 3 * C, nk))) return rc;
       const char* qkvn[3] = {".attn1.to_q.weight", ".attn1.to_k.weight", ".attn1.to_v.weight"};
+      const bool fold = h->lnfold;
       for (int i = 0; i < 3; ++i)
-        if ((rc = pack_seg(h, x.qkv, b + qkvn[i], C, C, 1, 0, 0, C, i * C, 0, 0, st))) return rc;
+        if ((rc = pack_seg(h, x.qkv, b + qkvn[i], C, C, 1, 0, 0, C, i * C, 0, 0, st, fold ? h->W(b + ".norm1.weight") : nullptr))) return rc;
+      if (fold) {
+        if (dev_alloc(h, &x.g_qkv, (size_t)3 * C, false) || dev_alloc(h, &x.bf_qkv, (size_t)3 * C, false)) return -2;
+        if (dev_alloc(h, &x.g_q2, (size_t)C, false) || dev_alloc(h, &x.bf_q2, (size_t)C, false)) return -2;
+        if (dev_alloc(h, &x.g_ff1, (size_t)8 * C, false) || dev_alloc(h, &x.bf_ff1, (size_t)8 * C, false)) return -2;
+        for (int i = 0; i < 3; ++i)
+          if ((rc = ln_fold_vectors(h, b + qkvn[i], "", b + ".norm1", C, C, x.g_qkv, x.bf_qkv, i * C, st))) return rc;
+        if ((rc = ln_fold_vectors(h, b + ".attn2.to_q.weight", "", b + ".norm2", C, C, x.g_q2, x.bf_q2, 0, st))) return rc;
+        if ((rc = ln_fold_vectors(h, b + ".ff.net.0.proj.weight", b + ".ff.net.0.proj.bias", b + ".norm3", 8 * C, C, x.g_ff1, x.bf_ff1, 0, st))) return rc;
+      }
       if ((rc = alloc_packed(h, x.out1, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.out1, b + ".attn1.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.q2, C, C, nk))) return rc;
-      if ((rc = pack_seg(h, x.q2, b + ".attn2.to_q.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      if ((rc = pack_seg(h, x.q2, b + ".attn2.to_q.weight", C, C, 1, 0, 0, C, 0, 0, 0, st, fold ? h->W(b + ".norm2.weight") : nullptr))) return rc;
       if ((rc = alloc_packed(h, x.out2, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.out2, b + ".attn2.to_out.0.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
       NS_REQUIRE((4 * C) % 64 == 0, "transformer width %d: 4C must be a multiple of 64", C);
       if ((rc = alloc_packed(h, x.ff1, 4 * C, 8 * C, nk))) return rc;
-      if ((rc = pack_seg(h, x.ff1, b + ".ff.net.0.proj.weight", 8 * C, C, 1, 0, 0, C, 0, 0, 4 * C, st))) return rc;
+      if ((rc = pack_seg(h, x.ff1, b + ".ff.net.0.proj.weight", 8 * C, C, 1, 0, 0, C, 0, 0, 4 * C, st, fold ? h->W(b + ".norm3.weight") : nullptr))) return rc;
       if ((rc = alloc_packed(h, x.ff2, C, C, nkb_of(4 * C)))) return rc;
       if ((rc = pack_seg(h, x.ff2, b + ".ff.net.2.weight", C, 4 * C, 1, 0, 0, 4 * C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.proj_out, C, C, nk))) return rc;
@@ -583,10 +620,12 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
     else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
+    if (o.kind == PlanOp::XFORMER && h->lnfold) stat_doubles += (size_t)3 * 2 * B * Tl[o.level];   // three LayerNorm row-statistics buffers
   }
   double* stat_arena = ar.get<double>(stat_doubles);
   size_t stat_used = 0;
   auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
+  auto new_rowstats = [&](size_t nrows) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += 2 * nrows; return p; };
   auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
   { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
   // activation buffers
@@ -611,6 +650,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   const SplitBuf SP_ATT = scratch_split(max_act);    // attention output
   const SplitBuf SP_FF = scratch_split(max_ff);      // GEGLU output
   const SplitBuf SP_QKV = scratch_split(max_qkv);    // q | k | v of the self-attention (q of the cross-attention)
+  const SplitBuf SP_LN = scratch_split(max_act);     // raw (un-normalised) split of the transformer's residual stream (folded LayerNorms)
 
   // entry: x -> split tokens, time path, conv_in
   { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 1; l.i0 = Cl; l.i1 = T; l.split = s_xin; fwd.push_back(l); }
@@ -701,14 +741,28 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
                        sh2 = Builder::view(SP_H, TL, C);
         auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
         bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
-        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.proj_in); }
-        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
+        // Folded LayerNorms: the producer of each LN input also emits its raw bf16 split and the per-row sums; the consumer
+        // GEMM runs on the raw split with gamma folded into its weights and applies mean / rstd in its epilogue:
+        //   LN(x) W^T = rstd * (x (gamma*W)^T - mean * g) + (beta W^T + bias),   g[n] = sum_c gamma_c W[n,c]
+        // (reference attention.py:83,102,118 nn.LayerNorm eps 1e-5) - no LayerNorm kernel, no extra pass over the rows.
+        const bool fold = h->lnfold;
+        const SplitBuf sln = Builder::view(SP_LN, TL, C);
+        double* rs1 = fold ? new_rowstats(rows) : nullptr; double* rs2 = fold ? new_rowstats(rows) : nullptr; double* rs3 = fold ? new_rowstats(rows) : nullptr;
+        auto emits_ln_input = [&](GemmOp& g, double* rs) { g.flags |= EPI_OUT_SPLIT | EPI_ROWSTATS; g.out_hi = sln.hi; g.out_lo = sln.lo; g.out_split_ld = sln.ld; g.row_stats = rs; };
+        auto consumes_ln = [&](GemmOp& g, const double* rs, const float* gv, const float* bf) {
+          g.flags |= EPI_LNFOLD | EPI_BIAS; g.ln_stats = rs; g.ln_g = gv; g.bias = bf; g.ln_C = C; g.ln_eps = 1e-5f; };
+        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C;
+          if (fold) emits_ln_input(g, rs1);
+          bld.emit_gemm(g, x.proj_in); }
+        if (!fold) bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
+        const SplitBuf& sn = fold ? sln : sx;                // A operand of the LayerNorm consumers
         const bool av2 = !h->simt && attention_v2_supported(dh, TL, false) && attention_v2_supported(dh, S, true);
         const SplitBuf sqkv = Builder::view(SP_QKV, TL, 3 * C), sq2 = Builder::view(SP_QKV, TL, C);
-        { GemmOp g = lin(x.qkv, sx, C);
+        { GemmOp g = lin(x.qkv, sn, C);
           if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sqkv.hi; g.out_lo = sqkv.lo; g.out_split_ld = sqkv.ld;
                      if (attention_v2_p_fp16()) g.f16_col0 = 2 * C; }
           else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = 3 * C; }
+          if (fold) consumes_ln(g, rs1, x.g_qkv, x.bf_qkv);
           bld.emit_gemm(g, x.qkv); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = 3 * C; a.k = QKV + C; a.k_ld = 3 * C; a.v = QKV + 2 * C; a.v_ld = 3 * C;
@@ -717,11 +771,14 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           if (av2) { a.v2 = 1; a.qs = sqkv; a.ks = sqkv; a.vs = sqkv; a.q_c0 = 0; a.k_c0 = C; a.v_c0 = 2 * C;
                      if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
           fwd.push_back(l); }
-        { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C; bld.emit_gemm(g, x.out1); }
-        bld.emit_ln_split(T1, C, (int)rows, C, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"), sx);
-        { GemmOp g = lin(x.q2, sx, C);
+        { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C;
+          if (fold) emits_ln_input(g, rs2);
+          bld.emit_gemm(g, x.out1); }
+        if (!fold) bld.emit_ln_split(T1, C, (int)rows, C, h->W(b + ".norm2.weight"), h->W(b + ".norm2.bias"), sx);
+        { GemmOp g = lin(x.q2, sn, C);
           if (av2) { g.flags = EPI_OUT_SPLIT; g.out_hi = sq2.hi; g.out_lo = sq2.lo; g.out_split_ld = sq2.ld; }
           else { g.flags = EPI_OUT_F32; g.out = QKV; g.out_ld = C; }
+          if (fold) consumes_ln(g, rs2, x.g_q2, x.bf_q2);
           bld.emit_gemm(g, x.q2); }
         { Launch l; l.kind = Launch::ATTN; AttnOp& a = l.attn; memset(&a, 0, sizeof(a));
           a.q = QKV; a.q_ld = C; a.k = kvc + x.kv_off; a.k_ld = h->kv_total; a.v = kvc + x.v_off; a.v_ld = h->kv_total; a.bias = maskbias;
@@ -730,10 +787,14 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           if (av2) { a.v2 = 1; a.qs = sq2; a.ks = kvs; a.vs = kvs; a.q_c0 = 0; a.k_c0 = x.kv_off; a.v_c0 = x.v_off;
                      if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
           fwd.push_back(l); }
-        { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C; bld.emit_gemm(g, x.out2); }
-        bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"), sx);
-        { GemmOp g = lin(x.ff1, sx, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.0.proj.bias");
-          g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld; bld.emit_gemm(g, x.ff1); }
+        { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C;
+          if (fold) emits_ln_input(g, rs3);
+          bld.emit_gemm(g, x.out2); }
+        if (!fold) bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm3.weight"), h->W(b + ".norm3.bias"), sx);
+        { GemmOp g = lin(x.ff1, sn, C); g.flags = EPI_GEGLU | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.0.proj.bias");
+          g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld;
+          if (fold) { consumes_ln(g, rs3, x.g_ff1, x.bf_ff1); g.flags &= ~EPI_BIAS; }   // GEGLU reads its (folded) biases through g.bias itself
+          bld.emit_gemm(g, x.ff1); }
         { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
           g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
         float* outp = next_out(followed_by_push(pi), rows * C);
@@ -990,6 +1051,7 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   h->ted = 4 * cfg->block_out_channels[0];
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
+  { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
   build_plan(h);
   register_weights(h);
   *out = h;

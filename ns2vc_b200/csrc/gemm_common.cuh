@@ -102,9 +102,26 @@ __device__ __forceinline__ float a_fetch_split(const GemmOp& op, const GSeg& s, 
   return __bfloat162float(src.hi[off]) + __bfloat162float(src.lo[off]);
 }
 
+// LayerNorm statistics of row m from the producer's accumulated row sums (biased variance, reference nn.LayerNorm)
+__device__ __forceinline__ void ln_row_stats(const GemmOp& op, long long m, float& mu, float& rstd) {
+  const double s = op.ln_stats[m * 2], q = op.ln_stats[m * 2 + 1];
+  const double mean = s / (double)op.ln_C;
+  double var = q / (double)op.ln_C - mean * mean;
+  if (var < 0) var = 0;
+  mu = (float)mean;
+  rstd = rsqrtf((float)var + op.ln_eps);
+}
+
 // Epilogue for one accumulator value at (m = b*T_out + t, logical column n).  For GEGLU the caller
 // passes the value accumulator in `acc` and the gate accumulator in `acc_gate`.
+template <bool LNF = true>
 __device__ __forceinline__ float epi_value(const GemmOp& op, int b, long long m, int n, float acc, float acc_gate) {
+  if (LNF && (op.flags & EPI_LNFOLD)) {
+    float mu, rstd;
+    ln_row_stats(op, m, mu, rstd);
+    acc = rstd * (acc - mu * __ldg(op.ln_g + n));
+    if (op.flags & EPI_GEGLU) acc_gate = rstd * (acc_gate - mu * __ldg(op.ln_g + op.n_valid + n));
+  }
   float v = acc;
   if (op.flags & EPI_GEGLU) {
     const int half = op.n_valid;   // = 4C

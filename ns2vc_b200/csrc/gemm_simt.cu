@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(256) pack_b_kernel(PackSeg ps, __nv_bfloat16* 
     }
     const int c = kbl * 64 + kk;                          // channel within the segment
     float w = 0.f;
-    if (c < ps.ncin) w = ps.w[((long long)n_src * ps.cin_total + ps.cin0 + c) * ps.ktaps + ps.tap];
+    if (c < ps.ncin) {
+      w = ps.w[((long long)n_src * ps.cin_total + ps.cin0 + c) * ps.ktaps + ps.tap];
+      if (ps.cscale) w *= ps.cscale[ps.cin0 + c];
+    }
     const int n = ps.n_dst0 + nl;
     const int kb = ps.kb0 + kbl;
     const long long row = (long long)kb * Npad + n;
@@ -132,6 +135,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const __grid_constant__ 
       if (op.flags & EPI_STATS) {
         atomicAdd(op.stat_sum + (long long)b * op.n_valid + n, (double)v);
         atomicAdd(op.stat_sq + (long long)b * op.n_valid + n, (double)v * (double)v);
+      }
+      if (op.flags & EPI_ROWSTATS) {
+        atomicAdd(op.row_stats + m * 2, (double)v);
+        atomicAdd(op.row_stats + m * 2 + 1, (double)v * (double)v);
       }
       if (op.flags & EPI_OUT_SPLIT) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);

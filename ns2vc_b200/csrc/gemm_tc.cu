@@ -61,7 +61,8 @@ template <int BN_> struct TileCfg {
   static constexpr int kPipeBytes = (kStagesSingle * kStageBytes > kOffStagingMulti + kStagingBytes) ? kStagesSingle * kStageBytes : kOffStagingMulti + kStagingBytes;
   static constexpr int kOffBar = kPipeBytes;
   static constexpr int kOffDesc = kOffBar + 1024;
-  static constexpr int kSmemBytes = kOffDesc + 2048 /*descriptor copy*/ + 1024 /*alignment slack*/;
+  static constexpr int kOffLnG = kOffDesc + 2048;         // [8 warps][4][32] floats: folded-LayerNorm g and bias vectors of the warp's chunk
+  static constexpr int kSmemBytes = kOffLnG + 4096 + 1024 /*alignment slack*/;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
 };
@@ -164,7 +165,9 @@ __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64
 
 static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descriptor copy");
 
-template <int BN_>
+// LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
+// keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
+template <int BN_, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -321,6 +324,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       float pre[32];                                        // bias + residual of chunk cc0 (plain path); GEGLU: value bias
       float preg[32];                                       // GEGLU: gate bias
       bool pre_ok = false;
+      // folded LayerNorm: this row's mean / rstd (sums accumulated by the producer's epilogue) and the g vectors of the
+      // warp's first chunk (shared by all rows: parked in shared memory, one column per lane)
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      float* sg = reinterpret_cast<float*>(smem + Cfg::kOffLnG) + (warp - 2) * 128;   // g (value | gate) | folded bias (value | gate)
+      if constexpr (LNF) {
+        // LNF instantiation: every per-column vector lives in shared memory (no register copies: the epilogue is register-bound)
+        if (mv) ln_row_stats(op, m, ln_mu, ln_rstd);
+        __syncwarp();
+        if (op.flags & EPI_GEGLU) {
+          const int nb = nt * 64 + cc0 * 32 + lane;
+          const bool ok = nb < op.n_valid;
+          sg[lane] = ok ? __ldg(op.ln_g + nb) : 0.f;
+          sg[32 + lane] = ok ? __ldg(op.ln_g + op.n_valid + nb) : 0.f;
+          sg[64 + lane] = ok ? __ldg(op.bias + nb) : 0.f;
+          sg[96 + lane] = ok ? __ldg(op.bias + op.n_valid + nb) : 0.f;
+          pre_ok = BN == 128 && nt * 64 + cc0 * 32 + 32 <= op.n_valid;
+        } else {
+          const int nb = n0 + cc0 * 32 + lane;
+          const bool ok = nb < op.n_valid;
+          sg[lane] = ok ? __ldg(op.ln_g + nb) : 0.f;
+          sg[64 + lane] = (ok && (op.flags & EPI_BIAS)) ? __ldg(op.bias + nb) : 0.f;
+          pre_ok = mv && n0 + cc0 * 32 + 32 <= op.n_valid && !(op.flags & (EPI_ROWBIAS | EPI_RESIDUAL));
+        }
+        __syncwarp();
+      }
+      if constexpr (!LNF) {
       if (op.flags & EPI_GEGLU) {
         const int nb = nt * 64 + cc0 * 32;
         if (BN == 128 && nb + 32 <= op.n_valid) {
@@ -352,6 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
       }
+      }   // !LNF
       mbar_wait(acc_full(it & 1), (uint32_t)((it >> 1) & 1));
       if (it == 0 && tr0 && warp == 2 && lane == 0) TRACE(5);
       if (it == 0 && tr0) ETRACE(0);
@@ -380,13 +410,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) val[j] = 0.f;
             } else if (pre_ok) {                            // biases were fetched before the accumulator wait
+              if constexpr (LNF) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 2)
-                upk2(fmul2(fadd2(pk2(val[j], val[j + 1]), pk2(pre[j], pre[j + 1])), gelu_erf2(fadd2(pk2(gate[j], gate[j + 1]), pk2(preg[j], preg[j + 1])))),
-                     val[j], val[j + 1]);
+                for (int j = 0; j < 32; j += 2) {
+                  const float v0 = fmaf(ln_rstd, val[j] - ln_mu * sg[j], sg[64 + j]), v1 = fmaf(ln_rstd, val[j + 1] - ln_mu * sg[j + 1], sg[65 + j]);
+                  const float g0 = fmaf(ln_rstd, gate[j] - ln_mu * sg[32 + j], sg[96 + j]), g1 = fmaf(ln_rstd, gate[j + 1] - ln_mu * sg[33 + j], sg[97 + j]);
+                  upk2(fmul2(pk2(v0, v1), gelu_erf2(pk2(g0, g1))), val[j], val[j + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                  upk2(fmul2(fadd2(pk2(val[j], val[j + 1]), pk2(pre[j], pre[j + 1])), gelu_erf2(fadd2(pk2(gate[j], gate[j + 1]), pk2(preg[j], preg[j + 1])))),
+                       val[j], val[j + 1]);
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
+              for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
             }
             wait_staging();
             emit_chunk(op, tmo, st, lane, false, b, t, t_warp0, m, mv, nbase, val);
@@ -412,9 +451,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] = 0.f;
             } else if (cc == cc0 && pre_ok) {
+              if constexpr (LNF) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] += pre[j];
-            } else if (fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
+                for (int j = 0; j < 32; ++j) acc[j] = fmaf(ln_rstd, acc[j] - ln_mu * sg[j], sg[64 + j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += pre[j];
+              }
+            } else if (!LNF && fullc && !(op.flags & EPI_ROWBIAS) && (!(op.flags & EPI_RESIDUAL) || (op.res_ld & 3) == 0)) {
               if (op.flags & EPI_BIAS) {
                 const float4* pb = reinterpret_cast<const float4*>(op.bias + nbase);
 #pragma unroll
@@ -427,9 +471,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
+              for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
             }
             if (it == 0 && tr0) ETRACE(2);
+            if ((op.flags & EPI_ROWSTATS) && mv) {          // LayerNorm statistics of this row for the consumer GEMM
+              float rs = 0.f, rq = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { rs += acc[j]; rq = fmaf(acc[j], acc[j], rq); }   // columns >= n_valid are zero
+              atomicAdd(op.row_stats + m * 2, (double)rs);
+              atomicAdd(op.row_stats + m * 2 + 1, (double)rq);
+            }
             wait_staging();
             emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc);
             staged_once = true;
@@ -566,19 +617,19 @@ static int sm_count() {
   return n;
 }
 
-template <int BN_>
+template <int BN_, bool LNF>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
   // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
   const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  cudaError_t e = launch_k(gemm_tc_kernel<BN_>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
+  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -594,9 +645,10 @@ void plan_gemm(GemmOp& op) {
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
-  if (op.bn == 128) return launch_bn<128>(op, st);
+  const bool lnf = (op.flags & EPI_LNFOLD) != 0;
+  if (op.bn == 128) return lnf ? launch_bn<128, true>(op, st) : launch_bn<128, false>(op, st);
   if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
-  return launch_bn<64>(op, st);
+  return lnf ? launch_bn<64, true>(op, st) : launch_bn<64, false>(op, st);
 }
 
 }  // namespace ns2vc
