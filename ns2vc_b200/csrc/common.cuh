@@ -83,6 +83,9 @@ enum EpiFlags : int {
   EPI_LNFOLD = 256,   // the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights:
                       //   acc <- rstd_row * (acc - mean_row * ln_g[n]);  bias then carries beta.W + bias   (see engine.cu)
   EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
+  EPI_GNAPPLY = 1024, // (with EPI_STATS | EPI_OUT_SPLIT, single-tile CTAs only) the consumer's GroupNorm is applied HERE: after an
+                      // in-kernel barrier among the CTAs of a batch entry (all column sums landed) each CTA normalises its own
+                      // staged tile (affine [+FiLM] [+SiLU]) and writes that as the split output - no prep kernel, no fp32 round trip
 };
 
 struct GemmOp {
@@ -115,6 +118,11 @@ struct GemmOp {
   const float* ln_g;           // EPI_LNFOLD: [n logical] sum_c gamma_c W[n, c]  (GEGLU: value rows then gate rows, like bias)
   int ln_C; float ln_eps;
   double* row_stats;           // EPI_ROWSTATS: [B*T_out][2], pre-zeroed
+  // EPI_GNAPPLY: the consumer's GroupNorm (reference resnet.py:557 norm2 + scale_shift FiLM, :607-612)
+  const float* gn_gamma; const float* gn_beta;
+  const float* gn_film; int gn_film_ld;   // nullptr or [B, gn_film_ld]: scale at [b, c], shift at [b, n_valid + c]
+  int gn_G; float gn_eps; int gn_silu;
+  unsigned int* gn_counter;    // [B] arrival counters of the in-kernel barrier, pre-zeroed
   int f16_col0;                // split output columns >= f16_col0 (a multiple of 32) are written as FP16 hi/lo instead of bf16
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
@@ -127,6 +135,8 @@ struct GemmOp {
 };
 // Choose the N tile and the multicast cluster size for op (fills op.bn / op.cn); must precede encode_tmaps().
 void plan_gemm(GemmOp& op);
+// Can every tile of this (planned) op be resident at once (one CTA per SM)?  Needed by EPI_GNAPPLY's in-kernel barrier.
+bool gemm_tiles_coresident(const GemmOp& op);
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st);

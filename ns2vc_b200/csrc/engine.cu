@@ -131,6 +131,8 @@ struct ns2vc_unet {
   std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
+  bool gnfuse = true;        // GroupNorm(+FiLM)+SiLU between conv1 and conv2 of a resnet applied in conv1's epilogue behind an in-kernel
+                             // barrier (NS2VC_GNFUSE=0: separate prep kernel)
   bool lnfold = true;        // LayerNorms of the transformer folded into their consumer GEMMs (NS2VC_LNFOLD=0: separate LN kernels)
   unsigned long long* trace = nullptr; int trace_cap = 0;
   unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
@@ -620,11 +622,13 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
     else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
+    if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)(B + 1) / 2 + 1;                          // barrier counters of the fused GroupNorm
     if (o.kind == PlanOp::XFORMER && h->lnfold) stat_doubles += (size_t)3 * 2 * B * Tl[o.level];   // three LayerNorm row-statistics buffers
   }
   double* stat_arena = ar.get<double>(stat_doubles);
   size_t stat_used = 0;
   auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
+  auto new_counters = [&](int n) { unsigned int* p = stat_arena ? reinterpret_cast<unsigned int*>(stat_arena + stat_used) : nullptr; stat_used += (size_t)(n + 1) / 2 + 1; return p; };
   auto new_rowstats = [&](size_t nrows) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += 2 * nrows; return p; };
   auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
   { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
@@ -705,6 +709,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         bld.emit_prep_gn(s1, s.c1, cur_st, s2, s.c2, s.c2 ? cat2_st : nullptr, TL, PREP_AFFINE_SILU, c.norm_eps,
                          h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, a_in, s.shortcut ? &a_raw : nullptr);
         double* h1_st = new_stats(s.cout);
+        bool fused_gn = false;
         {
           GemmOp g = bld.gemm_base(s.conv1, TL);
           bld.conv3(g, a_in);
@@ -712,10 +717,23 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
           g.out = H1; g.out_ld = s.cout;
           with_stats(g, h1_st, s.cout);
+          // norm2 (+FiLM) + SiLU applied by conv1 itself once all its tiles' column sums are in (reference resnet.py:602-612):
+          // possible when every tile is resident at once and the channel count divides into the groups
+          fused_gn = h->gnfuse && !(g.flags & EPI_ROWBIAS) && (s.cout % c.norm_num_groups) == 0 && (s.cout / c.norm_num_groups) <= 64 * 32 &&
+                     gemm_tiles_coresident(g);
+          unsigned int* ctr = new_counters(B);
+          if (fused_gn) {
+            g.flags = (g.flags & ~EPI_OUT_F32) | EPI_OUT_SPLIT | EPI_GNAPPLY;
+            g.out = nullptr; g.out_hi = a_h.hi; g.out_lo = a_h.lo; g.out_split_ld = a_h.ld;
+            g.gn_gamma = h->W(s.p + ".norm2.weight"); g.gn_beta = h->W(s.p + ".norm2.bias");
+            g.gn_film = c.time_scale_shift ? film + s.film_off : nullptr; g.gn_film_ld = h->film_total;
+            g.gn_G = c.norm_num_groups; g.gn_eps = c.norm_eps; g.gn_silu = 1; g.gn_counter = ctr;
+          }
           bld.emit_gemm(g, s.conv1);
         }
-        bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
-                         h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
+        if (!fused_gn)
+          bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
+                           h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
         float* outp = next_out(followed_by_push(pi), rows * s.cout);
         double* out_st = new_stats(s.cout);
         {
@@ -1052,6 +1070,8 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
+  { const char* e = getenv("NS2VC_GNFUSE"); const char* t = getenv("NS2VC_TMA_STORE");
+    h->gnfuse = !(e && e[0] == '0') && !h->simt && !(t && t[0] == '0'); }   // the fused GroupNorm writes its split through TMA
   build_plan(h);
   register_weights(h);
   *out = h;

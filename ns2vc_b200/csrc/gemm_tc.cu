@@ -125,12 +125,13 @@ __device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) { 
 }
 // Store one 32-column chunk of this warp's 32 rows.  val: this thread's row (already zero for rows past T_out).
 __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool stage_f32, int b, int t,
-                                           int t_warp0, long long m, bool mv, int nbase, const float* val) {
+                                           int t_warp0, long long m, bool mv, int nbase, const float* val, bool with_split = true) {
   if (stage_f32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage_f32_ptr(st, lane, j)) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
   }
-  if (op.tma_out & 2) {
+  const int tma = with_split ? op.tma_out : (op.tma_out & ~2);
+  if (tma & 2) {
     const bool f16 = nbase >= op.f16_col0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -141,19 +142,19 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
       *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
     }
   }
-  if (op.tma_out) {
+  if (tma & 3) {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
       const uint32_t sa = smem_u32(st);
-      if (op.tma_out & 1) tma_store_3d(&tmo[0], sa, nbase, t_warp0, b);
-      if (op.tma_out & 2) { tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b); tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b); }
+      if (tma & 1) tma_store_3d(&tmo[0], sa, nbase, t_warp0, b);
+      if (tma & 2) { tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b); tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b); }
       bulk_commit();
     }
   }
   // whatever does not go through TMA (channel-major output, unaligned leading dimensions)
   const int direct = ((op.flags & EPI_OUT_NCT) ? EPI_OUT_NCT : 0) | (((op.flags & EPI_OUT_F32) && !(op.tma_out & 1)) ? EPI_OUT_F32 : 0) |
-                     (((op.flags & EPI_OUT_SPLIT) && !(op.tma_out & 2)) ? EPI_OUT_SPLIT : 0);
+                     (((op.flags & EPI_OUT_SPLIT) && with_split && !(op.tma_out & 2)) ? EPI_OUT_SPLIT : 0);
   if (direct && mv) store_chunk(op, direct, b, t, m, nbase, val);
 }
 
@@ -167,7 +168,8 @@ static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descrip
 
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
-template <int BN_, bool LNF>
+// GNA: instantiation for EPI_GNAPPLY (consumer's GroupNorm applied behind an in-kernel barrier).
+template <int BN_, bool LNF, bool GNA>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               atomicAdd(op.row_stats + m * 2 + 1, (double)rq);
             }
             wait_staging();
-            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc);
+            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, !GNA);
             staged_once = true;
             if (it == 0 && tr0) ETRACE(3);
             if (op.flags & EPI_STATS) {
@@ -512,6 +514,105 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int w = 0; w < 4; ++w) { cs += (double)sm_part[(w * BN + col) * 2]; cq += (double)sm_part[(w * BN + col) * 2 + 1]; }
             atomicAdd(op.stat_sum + (long long)b * op.n_valid + n0 + col, cs);
             atomicAdd(op.stat_sq + (long long)b * op.n_valid + n0 + col, cq);
+          }
+        }
+        if constexpr (GNA) {
+          // ---- the consumer's GroupNorm, applied to the tile this CTA still holds in its staging area ----
+          // (b) barrier among the CTAs of batch entry b: every tile's column sums have landed.  All CTAs of the grid are
+          //     resident (one tile per CTA, grid <= SM count - checked on the host), so nobody waits for an unscheduled CTA;
+          //     a bounded spin turns a protocol bug into a trap instead of a hang.
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid == 64) {
+            const unsigned need = (unsigned)(tiles_per_batch * n_tiles);
+            atomicAdd(op.gn_counter + b, 1u);
+            unsigned seen, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(op.gn_counter + b) : "memory");
+              if (++spins > (1u << 22)) { printf("ns2vc: GroupNorm barrier timeout (block %d, batch %d, %u of %u)\n", blockIdx.x, b, seen, need); __trap(); }
+            } while (seen < need);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (c) mean / rstd of the groups this tile's columns belong to (biased variance over T x C/G, reference nn.GroupNorm)
+          const int C = op.n_valid, cpg = C / op.gn_G;
+          const int last = (n0 + BN - 1 < C - 1) ? n0 + BN - 1 : C - 1;
+          const int g0 = n0 / cpg, g1 = last / cpg;
+          float* gst = sm_part;                             // [groups][2]; the partial sums are consumed
+          float* aff = sm_part + 64;                        // [2][BN] scale | shift
+          for (int g = g0 + (warp - 2); g <= g1; g += kEpiWarps) {
+            double sum = 0, sq = 0;
+            for (int ii = lane; ii < cpg; ii += 32) {
+              sum += __ldcg(op.stat_sum + (long long)b * C + g * cpg + ii);
+              sq += __ldcg(op.stat_sq + (long long)b * C + g * cpg + ii);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+            if (lane == 0) {
+              const double inv = 1.0 / ((double)op.T_out * cpg);
+              const double mean = sum * inv;
+              double var = sq * inv - mean * mean;
+              if (var < 0) var = 0;
+              gst[(g - g0) * 2] = (float)mean;
+              gst[(g - g0) * 2 + 1] = rsqrtf((float)var + op.gn_eps);
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (d) per-column scale / shift (+ FiLM), same arithmetic as prep_split_kernel
+          {
+            const int col = tid - 64;
+            if (col < BN) {
+              const int c = n0 + col;
+              float ga = 0.f, be = 0.f;
+              if (c < C) {
+                const int g = c / cpg - g0;
+                ga = __ldg(op.gn_gamma + c) * gst[g * 2 + 1];
+                be = __ldg(op.gn_beta + c) - gst[g * 2] * ga;
+                if (op.gn_film) {
+                  const float fs = 1.f + op.gn_film[(long long)b * op.gn_film_ld + c];
+                  const float fb = op.gn_film[(long long)b * op.gn_film_ld + C + c];
+                  ga = ga * fs;
+                  be = be * fs + fb;
+                }
+              }
+              aff[col] = ga;
+              aff[BN + col] = be;
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (e) normalise this thread's row of the staged chunk(s) and hand the split to the TMA unit
+#pragma unroll 1
+          for (int cc = cc0; cc < BN / 32; cc += 2) {
+            const int nbase = n0 + cc * 32;
+            if (nbase >= op.n_valid) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(stage_f32_ptr(st, lane, j));
+              v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float y = fmaf(v[j], aff[cc * 32 + j], aff[BN + cc * 32 + j]);
+              if (op.gn_silu) y = silu_f(y);
+              v[j] = y;
+            }
+            const bool f16 = nbase >= op.f16_col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 hi, lo;
+              if (f16) split8_f16(v + 8 * j, hi, lo); else split8(v + 8 * j, hi, lo);
+              const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(st + 4096 + off) = hi;
+              *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t sa = smem_u32(st);
+              tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b);
+              tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b);
+              bulk_commit();
+            }
           }
         }
       }
@@ -617,21 +718,27 @@ static int sm_count() {
   return n;
 }
 
-template <int BN_, bool LNF>
+template <int BN_, bool LNF, bool GNA>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF, GNA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
   // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
   const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
+  if (GNA && tiles > grid) { set_error("gemm_tc: EPI_GNAPPLY needs every tile resident (%d tiles, %d SMs)", tiles, grid); return -1; }
+  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF, GNA>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+bool gemm_tiles_coresident(const GemmOp& op) {
+  const int bn = (op.flags & EPI_GEGLU) ? 128 : 64;
+  return op.B * ceil_div(op.T_out, BM) * (op.N / bn) <= sm_count();
 }
 
 void plan_gemm(GemmOp& op) {
@@ -646,9 +753,13 @@ int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
   const bool lnf = (op.flags & EPI_LNFOLD) != 0;
-  if (op.bn == 128) return lnf ? launch_bn<128, true>(op, st) : launch_bn<128, false>(op, st);
+  if (op.bn == 128) return lnf ? launch_bn<128, true, false>(op, st) : launch_bn<128, false, false>(op, st);
   if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
-  return lnf ? launch_bn<64, true>(op, st) : launch_bn<64, false>(op, st);
+  if (op.flags & EPI_GNAPPLY) {
+    if (lnf || !(op.flags & EPI_STATS) || !(op.tma_out & 2)) { set_error("gemm_tc: EPI_GNAPPLY needs EPI_STATS and a TMA split output"); return -1; }
+    return launch_bn<64, false, true>(op, st);
+  }
+  return lnf ? launch_bn<64, true, false>(op, st) : launch_bn<64, false, false>(op, st);
 }
 
 }  // namespace ns2vc
