@@ -287,11 +287,15 @@ class UNet1DConditionModel(nn.Module):
                 _lib.lib().ns2vc_unet_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
-            self._ws = {}
+            # plain __dict__ writes: nn.Module.__setattr__ may already be torn down at interpreter shutdown
+            self.__dict__["_handle"] = None
+            self.__dict__["_ws"] = {}
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def engine(self, device: torch.device) -> int:
         """Opaque engine handle with the current parameter values packed for the tensor cores
