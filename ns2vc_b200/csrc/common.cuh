@@ -100,6 +100,8 @@ struct GemmOp {
   const __nv_bfloat16* w_hi;   // packed [kb][Npad][64] (128B-swizzled rows)
   const __nv_bfloat16* w_lo;
   const float* w_f32;          // debug SIMT backend: [K_pad][Npad] fp32 (nullptr unless enabled)
+  const TMap* dmaps;           // device-memory copy of tmap[0..7] | tmap_out[0..2] (the TMA unit fetches descriptors from global
+                               // memory faster than from the kernel-parameter bank), or nullptr: use the parameter copies
   int N;                       // packed output columns (multiple of 128)
   // epilogue
   int flags;

@@ -133,6 +133,7 @@ struct ns2vc_unet {
   bool profiling = false;
   bool gnfuse = false;       // NS2VC_GNFUSE=1: GroupNorm(+FiLM)+SiLU between conv1 and conv2 of a resnet applied in conv1's epilogue behind an
                              // in-kernel barrier instead of a separate prep kernel (measured slower, kept as an opt-in)
+  bool dev_tmaps = false;    // NS2VC_DEV_TMAPS=1: TMA descriptors fetched from device memory instead of the kernel-parameter bank (measured: no gain)
   bool lnfold = true;        // LayerNorms of the transformer folded into their consumer GEMMs (NS2VC_LNFOLD=0: separate LN kernels)
   unsigned long long* trace = nullptr; int trace_cap = 0;
   unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
@@ -497,6 +498,15 @@ struct Builder {
       if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
       plan_gemm(g);
       if (!h->simt) { int rc = encode_tmaps(g); if (rc) err = rc; }
+    }
+    // descriptors also live in the workspace (device memory): see GemmOp::dmaps
+    TMap* dm = (h->simt || !h->dev_tmaps) ? nullptr : ar.get<TMap>(2 * kMaxSrc + 3);
+    if (!dry && dm) {
+      TMap tmp[2 * kMaxSrc + 3];
+      memcpy(tmp, g.tmap, sizeof(g.tmap));
+      memcpy(tmp + 2 * kMaxSrc, g.tmap_out, sizeof(g.tmap_out));
+      if (cudaMemcpy(dm, tmp, sizeof(tmp), cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
+      g.dmaps = dm;
     }
     l.gemm = g;
     out->push_back(l);
@@ -1070,6 +1080,7 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
+  { const char* e = getenv("NS2VC_DEV_TMAPS"); h->dev_tmaps = (e && e[0] == '1'); }
   { const char* e = getenv("NS2VC_GNFUSE"); const char* t = getenv("NS2VC_TMA_STORE");
     // opt-in: measured r01 at cfg2 3.52 ms per forward fused vs 3.36 ms with the separate prep kernel (the barrier + statistics
     // round trip inside the epilogue costs more than the PDL-overlapped prep launch it removes)

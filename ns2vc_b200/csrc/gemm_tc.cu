@@ -61,7 +61,7 @@ template <int BN_> struct TileCfg {
   static constexpr int kPipeBytes = (kStagesSingle * kStageBytes > kOffStagingMulti + kStagingBytes) ? kStagesSingle * kStageBytes : kOffStagingMulti + kStagingBytes;
   static constexpr int kOffBar = kPipeBytes;
   static constexpr int kOffDesc = kOffBar + 1024;
-  static constexpr int kOffLnG = kOffDesc + 2048;         // [8 warps][4][32] floats: folded-LayerNorm g and bias vectors of the warp's chunk
+  static constexpr int kOffLnG = kOffDesc + 2304;         // [8 warps][4][32] floats: folded-LayerNorm g and bias vectors of the warp's chunk
   static constexpr int kSmemBytes = kOffLnG + 4096 + 1024 /*alignment slack*/;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
@@ -125,7 +125,8 @@ __device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) { 
 }
 // Store one 32-column chunk of this warp's 32 rows.  val: this thread's row (already zero for rows past T_out).
 __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool stage_f32, int b, int t,
-                                           int t_warp0, long long m, bool mv, int nbase, const float* val, bool with_split = true) {
+                                           int t_warp0, long long m, bool mv, int nbase, const float* val, bool with_split = true,
+                                           unsigned long long* stamp = nullptr) {
   if (stage_f32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage_f32_ptr(st, lane, j)) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
@@ -142,13 +143,17 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
       *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
     }
   }
+  if (stamp) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); stamp[12] = t; }     // staging written
   if (tma & 3) {
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
-      const uint32_t sa = smem_u32(st);
-      if (tma & 1) tma_store_3d(&tmo[0], sa, nbase, t_warp0, b);
-      if (tma & 2) { tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b); tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b); }
+    if (stamp) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); stamp[13] = t; }   // fence + syncwarp done
+    // lanes 0 / 1 / 2 issue the fp32 / hi / lo store in ONE warp instruction (a bulk tensor store costs the issuing thread
+    // ~0.4 us; three back-to-back from one lane were the longest step of the epilogue) and own one bulk group each
+    const bool mine = (lane == 0 && (tma & 1)) || ((lane == 1 || lane == 2) && (tma & 2));
+    if (mine) {
+      const uint32_t sa = smem_u32(st) + (lane == 0 ? 0u : lane == 1 ? 4096u : 6144u);
+      tma_store_3d(&tmo[lane], sa, nbase, t_warp0, b);
       bulk_commit();
     }
   }
@@ -164,7 +169,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
 #define ETRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) op.trace[8 + (i)] = gclk(); } while (0)
 
-static_assert(sizeof(GemmOp) <= 2048, "GemmOp must fit the shared-memory descriptor copy");
+static_assert(sizeof(GemmOp) <= 2304, "GemmOp must fit the shared-memory descriptor copy");
 
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
   }
   const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + Cfg::kOffDesc);
-  const TMap* tmaps = op_param.tmap;
+  const TMap* tmaps = op_param.dmaps ? op_param.dmaps : op_param.tmap;
   // Persistent tile loop: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile).
   // A CTA with a single tile keeps all kMaxStages pipeline stages and stages its epilogue output in the (then idle)
   // stage buffers; a CTA with several tiles gives the last stage(s) up for a dedicated staging area, so that the
@@ -223,6 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * op_param.nsrc; ++i) prefetch_tmap(&tmaps[i]);
+    // the store maps too: the first bulk store through a cold descriptor costs a ~0.5 us fetch on the epilogue's critical path
+    const TMap* pm = op_param.dmaps ? op_param.dmaps + 2 * kMaxSrc : op_param.tmap_out;
+    if (op_param.tma_out & 1) prefetch_tmap(&pm[0]);
+    if (op_param.tma_out & 2) { prefetch_tmap(&pm[1]); prefetch_tmap(&pm[2]); }
   }
   pdl_trigger();
   tc_fence_before();
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int r = q * 32 + lane;
     const int cc0 = (warp - 2) >> 2;
     uint8_t* st = stage_area + kStageOff + (warp - 2) * kStagePerWarp;   // this warp's staging area
-    const TMap* tmo = op_param.tmap_out;
+    const TMap* tmo = op_param.dmaps ? op_param.dmaps + 2 * kMaxSrc : op_param.tmap_out;
     bool staged_once = false;
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       };
       auto wait_staging = [&]() {                           // the TMA unit must have read the previous chunk out of the staging area
         if (staged_once && op.tma_out) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (lane < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
         }
       };
@@ -484,7 +493,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               atomicAdd(op.row_stats + m * 2 + 1, (double)rq);
             }
             wait_staging();
-            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, !GNA);
+            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, !GNA,
+                       (it == 0 && tr0 && warp == 2 && lane == 0) ? op.trace : nullptr);
             staged_once = true;
             if (it == 0 && tr0) ETRACE(3);
             if (op.flags & EPI_STATS) {
@@ -607,10 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-              const uint32_t sa = smem_u32(st);
-              tma_store_3d(&tmo[1], sa + 4096, nbase, t_warp0, b);
-              tma_store_3d(&tmo[2], sa + 6144, nbase, t_warp0, b);
+            if (lane == 1 || lane == 2) {
+              tma_store_3d(&tmo[lane], smem_u32(st) + (lane == 1 ? 4096u : 6144u), nbase, t_warp0, b);
               bulk_commit();
             }
           }
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     // Shared memory must outlive the TMA unit's reads of the staged chunks; the writes themselves are made visible to the
     // dependent grid by grid completion (griddepcontrol.wait on the other side), as in CUTLASS' tma_store_wait.
-    if (op.tma_out && lane == 0) { if (op.tma_out & 4) bulk_wait_all(); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+    if (op.tma_out && lane < 3) { if (op.tma_out & 4) bulk_wait_all(); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
   }
 
   if (warp == 2 && lane == 0 && tr0) TRACE(6);

@@ -44,7 +44,7 @@ for i in range(tr.shape[0]):
 print("mean per launch (us since entry):", {k: round(v / tr.shape[0], 2) for k, v in tot.items()}, "mean gap to next gemm entry", round(gaps / tr.shape[0], 2))
 print("forward span us", (int(tr[-1, 7]) - t00) / 1e3, "n gemm", tr.shape[0])
 
-enames = ["acc_ready", "tmem->reg", "bias+res", "stores", "stats_smem", "bar", "atomics/done", "cta_sync"]
+enames = ["acc_ready", "tmem->reg", "bias+res", "stores", "staged", "fenced", "atomics/done", "cta_sync"]
 print("epilogue sub-steps, SM cycles since acc_ready (warp 2 lane 0 of CTA (0,0)):")
 print("idx " + " ".join(f"{n:>12s}" for n in enames[1:]))
 acc = [0.0] * 8; cnt = [0] * 8
