@@ -237,6 +237,22 @@ def test_fused_dpm_50_steps_full_model_vs_oracle(full_model):
     assert ok, msg
 
 
+def test_fused_unipc_30_steps_full_model_vs_oracle(full_model):
+    """cfg3's sampler (UniPC bh2, the reference's default 30 steps, model.py:655-686) on the full architecture."""
+    m, sd = full_model
+    cfg = ns2vc_denoiser_config()
+    inp = make_inputs(2, 72, 24, ragged=True, seed=11)
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 31))
+    sch = sampler_oracle.OracleSchedule(linear_betas(1000))
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    with torch.no_grad():
+        ref = sampler_oracle.unipc_bh(fn, sch, inp["x"], 30)
+    ok, msg = close(out, ref)
+    assert ok, msg
+
+
 def _closure(m, inp):
     """Same call chain as NaturalSpeech2.sample_fun -> Diffusion_Encoder.forward (model.py:520, 403-415)."""
     content, prompt, plen = inp["content"].cuda(), inp["prompt"].cuda(), inp["refer_lengths"].cuda()
