@@ -41,7 +41,7 @@ template <int DHP, int PB, bool PF16, bool BIAS> struct ACfg {
   static constexpr int kOffBar = kOffKV + NST * kStageBytes;
   static constexpr int kOffXch = kOffBar + 256;      // [3: parity 0 / parity 1 / row sums][2 halves][128 rows] floats
   static constexpr int kOffBias = kOffXch + 3072;    // additive bias * log2(e) (or -inf past Tk) for up to kBiasKeys keys
-  static constexpr int kBiasKeys = 1024;
+  static constexpr int kBiasKeys = (PB == 32) ? 768 : 1024;   // d_h = 16: 3 KB so that the biased (cross-attention) variant also fits 4 CTAs / SM
   static constexpr int kSmem = kOffBias + (BIAS ? 4 * kBiasKeys : 0) + 1024 /*alignment slack*/;
   static constexpr int NO = PB / 2;                  // channels per V tile row = width of one O column group
   // TMEM: S = x_hi*[y_hi ; y_lo] lands in two column groups when the K tiles are issued as one N = 128 operand (SC);
@@ -427,7 +427,7 @@ bool attention_v2_supported(int dh, int Tk, bool biased) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("NS2VC_ATTN"); off = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
   if (off || !(dh == 16 || dh == 32 || dh == 48 || dh == 64)) return false;
-  return !biased || ceil_div(Tk, kKeys) * kKeys <= 1024;   // the additive bias of a row of keys is staged in shared memory
+  return !biased || ceil_div(Tk, kKeys) * kKeys <= (dh == 16 ? 768 : 1024);   // the additive bias of a row of keys is staged in shared memory
 }
 
 int encode_attn_tmaps(AttnOp& op) {
