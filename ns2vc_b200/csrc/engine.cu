@@ -81,6 +81,8 @@ struct Launch {
   void* mem = nullptr; size_t mem_bytes = 0;
   int patch = 0;             // 1: x (forward)  2: t  3: out  4: content  5: prompt  6: mask
   int tap_index = -1;
+  int side = 0;              // 1: timestep path (independent of x): may run on the handle's side stream, forked off the caller's stream
+  int join = 0;              // 1: first consumer of the timestep path: the caller's stream waits for the side stream here
 };
 
 struct Arena {           // bump allocator over the caller's workspace (or a dry run when base == nullptr)
@@ -134,6 +136,9 @@ struct ns2vc_unet {
   bool gnfuse = false;       // NS2VC_GNFUSE=1: GroupNorm(+FiLM)+SiLU between conv1 and conv2 of a resnet applied in conv1's epilogue behind an
                              // in-kernel barrier instead of a separate prep kernel (measured slower, kept as an opt-in)
   bool dev_tmaps = false;    // NS2VC_DEV_TMAPS=1: TMA descriptors fetched from device memory instead of the kernel-parameter bank (measured: no gain)
+  bool fork_time = false;    // NS2VC_FORK_TIME=1: the timestep path (sinusoid -> MLP -> FiLM GEMV) of a forward overlaps conv_in / the first
+                             // resnet on a side stream (measured +0.2 %: not worth a second stream by default)
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool lnfold = true;        // LayerNorms of the transformer folded into their consumer GEMMs (NS2VC_LNFOLD=0: separate LN kernels)
   unsigned long long* trace = nullptr; int trace_cap = 0;
   unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
@@ -670,13 +675,13 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 1; l.i0 = Cl; l.i1 = T; l.split = s_xin; fwd.push_back(l); }
   { Launch l; l.kind = Launch::LINEAR; l.patch = 2; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = nullptr; o.x_ld = 1; o.M = B; o.K = c0; o.W = h->W("time_embedding.linear_1.weight"); o.bias = h->W("time_embedding.linear_1.bias");
-    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; fwd.push_back(l); }
+    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; l.side = 1; fwd.push_back(l); }
   { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = temb1; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->W("time_embedding.linear_2.weight"); o.bias = h->W("time_embedding.linear_2.bias");
-    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = aug; o.add_ld = ted; } fwd.push_back(l); }
+    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = aug; o.add_ld = ted; } l.side = 1; fwd.push_back(l); }
   if (h->film_total > 0) {
     Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
-    o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; fwd.push_back(l);
+    o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; l.side = 1; fwd.push_back(l);
   }
 
   struct Skip { float* p; int c; double* st; };
@@ -887,6 +892,11 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
     bld.emit_gemm(g, h->conv_out, 3);
   }
+  // the first launch that reads the timestep path's output (FiLM rows / time row bias) is where the side stream joins
+  for (auto& l : fwd) {
+    const bool reads_film = (l.kind == Launch::PREP && l.prep.gn.film) || (l.kind == Launch::GEMM && ((l.gemm.flags & EPI_ROWBIAS) || l.gemm.gn_film));
+    if (reads_film) { l.join = 1; break; }
+  }
   if (bld.err) return bld.err;
   if (bytes_out) *bytes_out = ar.off + 256;
   if (!dry) {
@@ -901,7 +911,31 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long long x_bstride, const float* t, float* out,
                 const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
   int rc = 0, count = 0, gemm_idx = 0, attn_idx = 0;
-  for (auto& l : prog) {
+  // Fork / join of the timestep path: it depends on t only, so it overlaps the x-dependent head of the forward.  Both
+  // event edges are ordinary stream dependencies, so the pattern is also valid under stream capture (the side stream
+  // joins the capture at the fork and is joined back before the first consumer).
+  const bool fork = h->fork_time && !h->profiling && !h->span && !h->trace;
+  bool forked = false, joined = false;
+  if (fork && !h->side) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { set_error("cannot create the side stream"); return -2; }
+  }
+  cudaStream_t main_st = st;
+  for (size_t li = 0; li < prog.size(); ++li) {
+    Launch& l = prog[li];
+    st = main_st;
+    if (fork && l.side) {
+      if (!forked) {
+        if (cudaEventRecord(h->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork, 0) != cudaSuccess) { set_error("side-stream fork failed"); return -2; }
+        forked = true;
+      }
+      st = h->side;
+    }
+    if (fork && forked && !joined && (l.join || li + 1 == prog.size())) {
+      if (cudaEventRecord(h->ev_join, h->side) != cudaSuccess || cudaStreamWaitEvent(main_st, h->ev_join, 0) != cudaSuccess) { set_error("side-stream join failed"); return -2; }
+      joined = true;
+    }
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     const bool prof = h->profiling && l.kind != Launch::TAP;
     if (prof) {
@@ -1080,6 +1114,7 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
+  { const char* e = getenv("NS2VC_FORK_TIME"); h->fork_time = (e && e[0] == '1'); }
   { const char* e = getenv("NS2VC_DEV_TMAPS"); h->dev_tmaps = (e && e[0] == '1'); }
   { const char* e = getenv("NS2VC_GNFUSE"); const char* t = getenv("NS2VC_TMA_STORE");
     // opt-in: measured r01 at cfg2 3.52 ms per forward fused vs 3.36 ms with the separate prep kernel (the barrier + statistics
@@ -1096,6 +1131,9 @@ void ns2vc_unet_destroy(ns2vc_unet* h) {
   for (auto& w : h->weights) if (w.d) cudaFree(w.d);
   for (void* p : h->owned) cudaFree(p);
   drop_all_programs(h);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
