@@ -69,7 +69,7 @@ struct ConvSite { std::string p; int c; PackedB w; };
 
 // One launch of the per-shape program.
 struct Launch {
-  enum Kind { GEMM, ATTN, GN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, MEMSET, TAP } kind;
+  enum Kind { GEMM, ATTN, LN_SPLIT, LN_APPLY, LINEAR, NCT2SPLIT, POOL_CLS, POOL_ATT, MASKBIAS, PREP, MEMSET, TAP } kind;
   GemmOp gemm;
   AttnOp attn;
   LinOp lin;
@@ -1269,11 +1269,11 @@ int ns2vc_unet_set_profiling(ns2vc_unet* h, int on) {
   h->profiling = on != 0;
   return 0;
 }
-int ns2vc_profile_num_kinds(void) { return 12; }
+int ns2vc_profile_num_kinds(void) { return 11; }
 const char* ns2vc_profile_kind_name(int k) {
-  static const char* names[] = {"gemm_tc", "attention", "gn_affine", "ln_split", "ln_apply", "small_linear", "nct_to_split",
+  static const char* names[] = {"gemm_tc", "attention", "ln_split", "ln_apply", "small_linear", "nct_to_split",     // = Launch::Kind order
                                "pool_class_token", "pool_attend", "mask_bias", "prep_split", "memset"};
-  return (k >= 0 && k < 12) ? names[k] : "";
+  return (k >= 0 && k < 11) ? names[k] : "";
 }
 int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long* launches) {
   NS_REQUIRE(h && ms_total && launches, "null argument");
