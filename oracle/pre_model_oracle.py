@@ -82,35 +82,41 @@ def enc_sa_layer(sd: SD, p: str, x_tbc: Tensor, pad_mask_bt: Tensor) -> Tensor:
     return (r + y) * keep
 
 
-def _encoder(sd: SD, p: str, x_tbc: Tensor, lengths: Tensor, n_layers: int) -> Tensor:
+def _encoder(sd: SD, p: str, x_tbc: Tensor, lengths: Tensor, n_layers: int, tap=None) -> Tensor:
     pad = ~sequence_mask(lengths, x_tbc.shape[0]).to(torch.bool)           # [B, T], True = padding
     keep = (1 - pad.float()).transpose(0, 1)[..., None]
     x = conv_layer(sd, p + ".pre", x_tbc, pad) * keep
+    if tap is not None:
+        tap[p + ".pre"] = x.clone()
     for i in range(n_layers):
         x = enc_sa_layer(sd, f"{p}.layers.{i}.op", x, pad)
+        if tap is not None:
+            tap[f"{p}.layers.{i}"] = x.clone()
     x = conv_layer(sd, p + ".out_proj", x, pad)
     x = F.layer_norm(x, (x.shape[-1],), sd[p + ".layer_norm.weight"], sd[p + ".layer_norm.bias"], 1e-5)
     return x * keep
 
 
-def phone_encoder(sd: SD, p: str, c_bct: Tensor, lengths: Tensor, g_bc1: Tensor, n_layers: int) -> Tensor:
+def phone_encoder(sd: SD, p: str, c_bct: Tensor, lengths: Tensor, g_bc1: Tensor, n_layers: int, tap=None) -> Tensor:
     """PhoneEncoder.forward (model.py:128-148): content + spk_proj(g), then the encoder stack.  Returns [T, B, C_out]."""
     x = c_bct + F.conv1d(g_bc1, sd[p + ".spk_proj.weight"], sd[p + ".spk_proj.bias"])
-    return _encoder(sd, p, x.permute(2, 0, 1), lengths, n_layers)
+    return _encoder(sd, p, x.permute(2, 0, 1), lengths, n_layers, tap)
 
 
-def prompt_encoder(sd: SD, p: str, refer_bct: Tensor, lengths: Tensor, n_layers: int) -> Tensor:
+def prompt_encoder(sd: SD, p: str, refer_bct: Tensor, lengths: Tensor, n_layers: int, tap=None) -> Tensor:
     """PromptEncoder.forward (model.py:173-190).  Returns [S, B, C_out]."""
-    return _encoder(sd, p, refer_bct.permute(2, 0, 1), lengths, n_layers)
+    return _encoder(sd, p, refer_bct.permute(2, 0, 1), lengths, n_layers, tap)
 
 
 def pre_model_infer(sd: SD, c_padded: Tensor, refer_padded: Tensor, lengths: Tensor, refer_lengths: Tensor,
-                    n_layers_phone: int = 6, n_layers_prompt: int = 6) -> Tuple[Tensor, Tensor]:
+                    n_layers_phone: int = 6, n_layers_prompt: int = 6, tap=None) -> Tuple[Tensor, Tensor]:
     """Pre_model.infer (model.py:360-377): returns (content [T,B,C], audio_prompt [S,B,C]) — exactly the two tensors
     Diffusion_Encoder.forward receives (model.py:403-415)."""
     g = text_time_embedding(sd, "ref_enc", refer_padded.transpose(1, 2), 1).unsqueeze(-1)      # [B, 100, 1]
-    audio_prompt = prompt_encoder(sd, "prompt_encoder", refer_padded, refer_lengths, n_layers_prompt)
-    content = phone_encoder(sd, "phoneme_encoder", c_padded, lengths, g, n_layers_phone)
+    if tap is not None:
+        tap["ref_enc"] = g.clone()
+    audio_prompt = prompt_encoder(sd, "prompt_encoder", refer_padded, refer_lengths, n_layers_prompt, tap)
+    content = phone_encoder(sd, "phoneme_encoder", c_padded, lengths, g, n_layers_phone, tap)
     return content, audio_prompt
 
 

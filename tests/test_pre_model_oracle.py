@@ -28,9 +28,12 @@ def test_pre_model_oracle_matches_reference_fixture(name):
         assert g["n_params"] == 34923404                      # demo.ipynb:447 "pre params"
     cfg = g["cfg"]
     c, refer, lengths, refer_lengths = _inputs(g["B"], g["T"], g["S"], cfg["phoneme_encoder"]["in_channels"], g["input_seed"])
+    taps = {}
     with torch.no_grad():
         content, prompt = po.pre_model_infer(sd, c, refer, lengths, refer_lengths, cfg["phoneme_encoder"]["n_layers"],
-                                             cfg["prompt_encoder"]["n_layers"])
+                                             cfg["prompt_encoder"]["n_layers"], taps)
+    for k, v in g["taps"].items():                            # per-layer activations (tiny fixture only)
+        assert torch.allclose(taps[k], v, rtol=0, atol=2e-6), k
     assert content.shape == g["content"].shape and prompt.shape == g["prompt"].shape
     assert torch.allclose(content, g["content"], rtol=0, atol=2e-6)
     assert torch.allclose(prompt, g["prompt"], rtol=0, atol=2e-6)
