@@ -79,6 +79,20 @@ int ns2vc_unet_prepare_cond(ns2vc_unet* h, const float* content, long long conte
 int ns2vc_unet_forward(ns2vc_unet* h, const float* x, long long x_bstride, const float* t, float* out, int B, int T,
                        int S, void* ws, ns2vc_stream stream);
 
+/* The timestep path of many forwards at once (the sampler knows every evaluation time when the run starts):
+ * Timesteps -> TimestepEmbedding (+ the pooled prompt embedding) -> time_emb_proj of all resnets
+ * (reference embeddings.py:24-64, 157-218; unet_1d_condition.py:825-883; resnet.py:619-629).
+ *   t_rows [n_rows] fp32 device, n_rows = steps x B in step-major order (row r belongs to batch entry r % B)
+ *   table  device buffer of ns2vc_unet_time_table_floats(h, n_rows) floats; its first n_rows x film_width floats are the
+ *          FiLM rows, the rest is scratch.  Needs ns2vc_unet_prepare_cond() on the same (B,T,S,workspace) first.        */
+int ns2vc_unet_film_width(const ns2vc_unet* h);
+size_t ns2vc_unet_time_table_floats(const ns2vc_unet* h, int n_rows);
+int ns2vc_unet_time_table(ns2vc_unet* h, const float* t_rows, int n_rows, float* table, int B, int T, int S, void* ws,
+                          ns2vc_stream stream);
+/* ns2vc_unet_forward with the timestep path taken from B rows of such a table (film_rows = table + step * B * film_width). */
+int ns2vc_unet_forward_film(ns2vc_unet* h, const float* x, long long x_bstride, const float* film_rows, float* out, int B,
+                            int T, int S, void* ws, ns2vc_stream stream);
+
 /* Per-step sampler math fused into one element-wise kernel (bit-exact fp32 op order).
  * DPM-Solver++(2M): model_wrapper x_start->noise (sampler/dpm_solver.py:291-292), data_prediction_fn
  * (:437-439), dpm_solver_first_update (:569-576), multistep_dpm_solver_second_update (:813-831). */
@@ -86,8 +100,10 @@ typedef struct ns2vc_dpm_coef {
   float alpha_s, sigma_s, c_x, c_m, c_d, inv_r0;
   int order;                  /* 0: x0 round trip only; 1 / 2: + first / second order update       */
 } ns2vc_dpm_coef;
+/* nan_flag (device int, may be NULL): set to 1 when x holds a NaN - the reference asserts on that every denoiser call
+ * (model.py:404); the fused loop checks the flag once after the run instead of syncing every step. */
 int ns2vc_dpm_step(const float* x, const float* unet_out, const float* m_prev, const ns2vc_dpm_coef* c, float* m_cur,
-                   float* x_next, size_t n, ns2vc_stream stream);
+                   float* x_next, size_t n, int* nan_flag, ns2vc_stream stream);
 
 /* UniPC-bh2 (sampler/uni_pc.py:471-588): corrector at t and predictor to the next time. */
 typedef struct ns2vc_unipc_coef {
@@ -97,7 +113,8 @@ typedef struct ns2vc_unipc_coef {
   int pred_order;
 } ns2vc_unipc_coef;
 int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0, const float* m1,
-                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, ns2vc_stream stream);
+                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, int* nan_flag,
+                     ns2vc_stream stream);
 
 /* Bit-exact index helpers (host, no GPU): nearest-neighbour source index of F.interpolate(size=)
  * (reference resnet.py:160) and the stride-2 conv length rule (resnet.py:200). */
@@ -115,9 +132,10 @@ const char* ns2vc_build_info(void);
 /* Per-kernel-kind device timing (CUDA events around every launch on the caller's stream); used by
  * bench.py for the roofline line.  Off by default; never enable inside a timed region. */
 int ns2vc_unet_set_profiling(ns2vc_unet* h, int on);
-/* In-kernel stamps of CTA (0,0) of every GEMM launch of the next forwards, 16 slots per launch: [0,8) %globaltimer
+/* In-kernel stamps of CTA (0,0) of every GEMM launch of the next forwards, 32 slots per launch: [0,8) %globaltimer
  * (entry, prologue, PDL wait, first stage full, MMAs issued, accumulator ready, epilogue done, exit), [8,16) SM-clock
- * stamps of the epilogue sub-steps.  NULL disables. */
+ * stamps of the epilogue sub-steps, [16,22) %globaltimer stamps of the fused prep (dependency wait done, loads issued,
+ * affine ready, rows stored, all preps done, published to the cluster).  NULL disables. */
 int ns2vc_unet_set_trace(ns2vc_unet* h, unsigned long long* device_buf, int n_gemms);
 /* Diagnostics: attention launch i of the next forward writes per-key-tile SM-clock stamps of its CTA (0,0,0)
  * to device_buf[2048*i ...] ([16 tiles][16 slots], then [start ns, end ns, SM id] of up to 597 CTAs; see attention_v2.cu).

@@ -38,7 +38,7 @@ def model_input_time(ns: NoiseScheduleVP, t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def dpmpp_2m_table(ns: NoiseScheduleVP, ts: torch.Tensor, lower_order_final: bool = True) -> List[DpmStep]:
+def dpmpp_2m_table(ns: NoiseScheduleVP, ts: torch.Tensor, lower_order_final: bool = True, order: int = 2) -> List[DpmStep]:
     """ts: the N+1 CPU time points (fp32).  Entry k = evaluate the model at ts[k] (x0 round trip
     with alpha/sigma at ts[k]) then advance x to ts[k+1] with DPM-Solver++ order 1 (k=0) or 2."""
     ts = ts.detach().to("cpu", torch.float32)
@@ -49,12 +49,13 @@ def dpmpp_2m_table(ns: NoiseScheduleVP, ts: torch.Tensor, lower_order_final: boo
         te = s.expand(1)
         st = DpmStep(t_input=_f(model_input_time(ns, te)), alpha_s=_f(ns.marginal_alpha(te)), sigma_s=_f(ns.marginal_std(te)))
         step = k + 1
-        if step < 2:
-            order = 1
+        max_order = order
+        if step < max_order:
+            k_order = step
         elif lower_order_final and N < 10:
-            order = min(2, N + 1 - step)
+            k_order = min(max_order, N + 1 - step)
         else:
-            order = 2
+            k_order = max_order
         lam_s, lam_t = ns.marginal_lambda(s), ns.marginal_lambda(t)
         h = lam_t - lam_s
         sigma_s, sigma_t = ns.marginal_std(s), ns.marginal_std(t)
@@ -62,8 +63,8 @@ def dpmpp_2m_table(ns: NoiseScheduleVP, ts: torch.Tensor, lower_order_final: boo
         phi_1 = torch.expm1(-h)
         st.c_x = _f(sigma_t / sigma_s)
         st.c_m = _f(alpha_t * phi_1)
-        st.order = order
-        if order == 2:
+        st.order = k_order
+        if k_order == 2:
             h_0 = lam_s - ns.marginal_lambda(ts[k - 1])
             r0 = h_0 / h
             st.inv_r0 = _f(1.0 / r0)

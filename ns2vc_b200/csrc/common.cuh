@@ -53,6 +53,32 @@ struct SplitBuf {
 
 struct alignas(128) TMap { unsigned long long v[16]; };   // CUtensorMap storage (driver-encoded)
 
+// ---------------------------------------------------------------------------------------------
+// Activation prep: (concat of up to two fp32 sources) -> [GroupNorm affine (+FiLM) (+SiLU)] -> split
+// ---------------------------------------------------------------------------------------------
+enum PrepMode : int { PREP_RAW = 0, PREP_AFFINE = 1, PREP_AFFINE_SILU = 2 };
+// GroupNorm source statistics: per-(b, channel) sums accumulated by the producing GEMM epilogues.
+struct GnStats {
+  const double* sum1; const double* sq1;   // [B, C1]
+  const double* sum2; const double* sq2;   // [B, C2]
+  const float* gamma; const float* beta;   // [C1+C2]
+  const float* film; int film_ld;          // nullptr or [B, film_ld]: scale at film[b,c], shift at film[b,C+c]
+  int G; float eps;
+};
+struct PrepOp {
+  const float* src1; int ld1; int C1;
+  const float* src2; int ld2; int C2;     // nullptr / 0 when there is no concat
+  int B, T_src, T_dst;
+  int row_mul, row_add;                   // src row = rowmap ? rowmap[t] : t*row_mul + row_add
+  const int* rowmap;                      // nearest-upsample index table [T_dst] or nullptr
+  int mode;
+  const float* scale; const float* shift; // [B, C1+C2] precomputed affine, or nullptr: derive it from `gn`
+  GnStats gn;
+  SplitBuf out;                           // transformed
+  SplitBuf raw;                           // optional second output without the transform (hi == nullptr: none)
+  unsigned long long* span;               // diagnostics
+};
+
 // GEMM / implicit-conv operator (shared by the tcgen05 kernel and the SIMT debug kernel):
 //
 //   out[b, t, n] = epilogue( sum_seg sum_{c < 64*nkb} A_seg[b, t + tap, c0 + c] * W[kofs_seg + c, n] )
@@ -83,9 +109,6 @@ enum EpiFlags : int {
   EPI_LNFOLD = 256,   // the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights:
                       //   acc <- rstd_row * (acc - mean_row * ln_g[n]);  bias then carries beta.W + bias   (see engine.cu)
   EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
-  EPI_GNAPPLY = 1024, // (with EPI_STATS | EPI_OUT_SPLIT, single-tile CTAs only) the consumer's GroupNorm is applied HERE: after an
-                      // in-kernel barrier among the CTAs of a batch entry (all column sums landed) each CTA normalises its own
-                      // staged tile (affine [+FiLM] [+SiLU]) and writes that as the split output - no prep kernel, no fp32 round trip
 };
 
 struct GemmOp {
@@ -100,8 +123,6 @@ struct GemmOp {
   const __nv_bfloat16* w_hi;   // packed [kb][Npad][64] (128B-swizzled rows)
   const __nv_bfloat16* w_lo;
   const float* w_f32;          // debug SIMT backend: [K_pad][Npad] fp32 (nullptr unless enabled)
-  const TMap* dmaps;           // device-memory copy of tmap[0..7] | tmap_out[0..2] (the TMA unit fetches descriptors from global
-                               // memory faster than from the kernel-parameter bank), or nullptr: use the parameter copies
   int N;                       // packed output columns (multiple of 128)
   // epilogue
   int flags;
@@ -120,11 +141,6 @@ struct GemmOp {
   const float* ln_g;           // EPI_LNFOLD: [n logical] sum_c gamma_c W[n, c]  (GEGLU: value rows then gate rows, like bias)
   int ln_C; float ln_eps;
   double* row_stats;           // EPI_ROWSTATS: [B*T_out][2], pre-zeroed
-  // EPI_GNAPPLY: the consumer's GroupNorm (reference resnet.py:557 norm2 + scale_shift FiLM, :607-612)
-  const float* gn_gamma; const float* gn_beta;
-  const float* gn_film; int gn_film_ld;   // nullptr or [B, gn_film_ld]: scale at [b, c], shift at [b, n_valid + c]
-  int gn_G; float gn_eps; int gn_silu;
-  unsigned int* gn_counter;    // [B] arrival counters of the in-kernel barrier, pre-zeroed
   int f16_col0;                // split output columns >= f16_col0 (a multiple of 32) are written as FP16 hi/lo instead of bf16
   double* stat_sum;            // EPI_STATS: [B, n_valid] each, pre-zeroed
   double* stat_sq;
@@ -133,12 +149,22 @@ struct GemmOp {
   TMap tmap_out[3];            // TMA store maps: fp32 out (box 32 cols x 32 rows, SWIZZLE_128B), out_hi, out_lo (SWIZZLE_64B)
   int tma_out;                 // bit 0: fp32 output goes through tmap_out[0]; bit 1: split output through tmap_out[1..2]
   int bn;                      // N tile (64 / 128), chosen by plan_gemm()
-  int cn;                      // cluster size along N: the cn CTAs of a cluster share the A tile by TMA multicast
+  // Prep fused into the GEMM's prologue ("PIP"): the GroupNorm(+FiLM)(+SiLU) / decimation / upsample pass that turns the
+  // producer's fp32 activations into this GEMM's split A operand runs INSIDE this kernel instead of as a launch of its own.
+  // The cn = N / bn CTAs that share a 128-row block form a thread-block cluster; each converts its share of the channels
+  // for rows [t0 + pre_tap_lo, t0 + 127 + pre_tap_hi], the cluster barrier publishes them, then the tile is a normal TMA GEMM.
+  int npre;                    // 0: the A operand was prepared by an earlier launch
+  const PrepOp* pre;           // [npre] descriptors in device memory (the kernel parameter block stays small: its size is launch latency)
+  const float* pre_film[2];    // FiLM rows of each fused prep (nullptr: none) - kept here because they change per forward
+  int pre_tap_lo[2], pre_tap_hi[2];
+  int cn;                      // cluster size along N (PIP only; 1 otherwise)
 };
-// Choose the N tile and the multicast cluster size for op (fills op.bn / op.cn); must precede encode_tmaps().
+// Choose the N tile for op (fills op.bn / op.cn); must precede encode_tmaps().
 void plan_gemm(GemmOp& op);
-// Can every tile of this (planned) op be resident at once (one CTA per SM)?  Needed by EPI_GNAPPLY's in-kernel barrier.
-bool gemm_tiles_coresident(const GemmOp& op);
+// Largest cluster the fused-prep path may use (N tiles of one row block)
+constexpr int kMaxPipCluster = 8;
+constexpr int kPrepFuseMaxC = 1280;   // channels a fused prep may normalise (affine slots per thread x threads of the GEMM CTA)
+int gemm_sm_count();
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st);
@@ -164,31 +190,6 @@ struct PackSeg {
 int launch_pack_b(const PackSeg& ps, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, float* w_f32, int Npad,
                   cudaStream_t st);
 
-// ---------------------------------------------------------------------------------------------
-// Activation prep: (concat of up to two fp32 sources) -> [GroupNorm affine (+FiLM) (+SiLU)] -> split
-// ---------------------------------------------------------------------------------------------
-enum PrepMode : int { PREP_RAW = 0, PREP_AFFINE = 1, PREP_AFFINE_SILU = 2 };
-// GroupNorm source statistics: per-(b, channel) sums accumulated by the producing GEMM epilogues.
-struct GnStats {
-  const double* sum1; const double* sq1;   // [B, C1]
-  const double* sum2; const double* sq2;   // [B, C2]
-  const float* gamma; const float* beta;   // [C1+C2]
-  const float* film; int film_ld;          // nullptr or [B, film_ld]: scale at film[b,c], shift at film[b,C+c]
-  int G; float eps;
-};
-struct PrepOp {
-  const float* src1; int ld1; int C1;
-  const float* src2; int ld2; int C2;     // nullptr / 0 when there is no concat
-  int B, T_src, T_dst;
-  int row_mul, row_add;                   // src row = rowmap ? rowmap[t] : t*row_mul + row_add
-  const int* rowmap;                      // nearest-upsample index table [T_dst] or nullptr
-  int mode;
-  const float* scale; const float* shift; // [B, C1+C2] precomputed affine, or nullptr: derive it from `gn`
-  GnStats gn;
-  SplitBuf out;                           // transformed
-  SplitBuf raw;                           // optional second output without the transform (hi == nullptr: none)
-  unsigned long long* span;               // diagnostics
-};
 int launch_prep_split(const PrepOp& op, cudaStream_t st);
 
 // LayerNorm + split in one pass (one warp per row): out = ((x-mean)*rstd*gamma + beta) as bf16 hi/lo
@@ -255,6 +256,7 @@ struct LinOp {
   const float* x; int x_ld; int M; int K;
   const float* W; const float* bias; int N;
   const float* add; int add_ld;
+  int add_rows;                // > 0: row m reads add row (m % add_rows)  (the timestep table: rows = steps x batch entries)
   float* out; int out_ld;
   int in_mode; int flip_sin_to_cos; float freq_shift;
   int out_silu;
@@ -278,7 +280,7 @@ struct DpmStepCoef {   // DPM-Solver++(2M): one post-UNet step
   int order;                   // 0: round trip only, 1: first-order update, 2: second-order update
 };
 int launch_dpm_step(const float* x, const float* unet_out, const float* m_prev, const DpmStepCoef& c,
-                    float* m_cur, float* x_next, size_t n, cudaStream_t st);
+                    float* m_cur, float* x_next, size_t n, int* nan_flag, cudaStream_t st);
 
 struct UniPcStepCoef {  // UniPC-bh2, data prediction: corrector at t (+ predictor to t_next)
   float alpha_t, sigma_t;      // x0 round trip at t
@@ -294,7 +296,7 @@ struct UniPcStepCoef {  // UniPC-bh2, data prediction: corrector at t (+ predict
 };
 int launch_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0,
                       const float* m1, const UniPcStepCoef& c, float* m_t, float* x_t, float* x_pred, size_t n,
-                      cudaStream_t st);
+                      int* nan_flag, cudaStream_t st);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -57,6 +57,10 @@ struct XformerSite {
   std::string p;
   int c;
   PackedB proj_in, qkv, out1, q2, out2, ff1, ff2, proj_out;
+  // ff.net.2 and proj_out have no non-linearity between them (reference attention.py:203 -> transformer_1d.py:289-295):
+  //   proj_out(ff2(g) + b2 + h) + bp = g (Wp W2)^T + h Wp^T + (Wp b2 + bp)
+  // so both run as ONE GEMM over K = [GEGLU output (4C) | residual stream h (C)] with the product matrix packed at load time.
+  PackedB ff2p; float* bias_ff2p = nullptr;
   int kv_off = 0;            // column offset of this block's K in the cross K/V cache (all K first ...)
   int v_off = 0;             // ... then all V: column offset of this block's V
   // LayerNorm folded into the consumer GEMM (norm1 -> qkv, norm2 -> q2, norm3 -> ff1): the packed weights carry gamma,
@@ -81,8 +85,8 @@ struct Launch {
   void* mem = nullptr; size_t mem_bytes = 0;
   int patch = 0;             // 1: x (forward)  2: t  3: out  4: content  5: prompt  6: mask
   int tap_index = -1;
-  int side = 0;              // 1: timestep path (independent of x): may run on the handle's side stream, forked off the caller's stream
-  int join = 0;              // 1: first consumer of the timestep path: the caller's stream waits for the side stream here
+  int reads_film = 0;        // 1: reads the FiLM rows (pointers are rebased when the caller supplies precomputed rows)
+  int time_path = 0;         // 1: timestep path (sinusoid -> MLP -> FiLM rows): skipped when the caller supplies precomputed FiLM rows
 };
 
 struct Arena {           // bump allocator over the caller's workspace (or a dry run when base == nullptr)
@@ -119,26 +123,24 @@ struct ns2vc_unet {
 
   // cached program
   int pB = 0, pT = 0, pS = 0; void* pws = nullptr; bool has_mask = false; bool cond_ready = false;
+  float* aug = nullptr;                                   // add_embedding output [B, ted] of the active program (workspace)
   std::vector<Launch> prog_cond, prog_fwd;
-  std::vector<int*> rowmaps;                              // device index tables owned by the program
   std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch;
   std::vector<float*> tap_dst;
   // Inactive programs (other (B,T,S,workspace) keys, e.g. the sub-batch lanes of a multi-stream sampler):
   // the fields above are the ACTIVE program; activate() swaps them with an entry of this list.
   struct Stash {
     int pB, pT, pS; void* pws; bool has_mask, cond_ready;
-    std::vector<Launch> prog_cond, prog_fwd; std::vector<int*> rowmaps;
+    std::vector<Launch> prog_cond, prog_fwd; float* film_base; float* aug;
     std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch; std::vector<float*> tap_dst;
   };
   std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
-  bool gnfuse = false;       // NS2VC_GNFUSE=1: GroupNorm(+FiLM)+SiLU between conv1 and conv2 of a resnet applied in conv1's epilogue behind an
-                             // in-kernel barrier instead of a separate prep kernel (measured slower, kept as an opt-in)
-  bool dev_tmaps = false;    // NS2VC_DEV_TMAPS=1: TMA descriptors fetched from device memory instead of the kernel-parameter bank (measured: no gain)
-  bool fork_time = false;    // NS2VC_FORK_TIME=1: the timestep path (sinusoid -> MLP -> FiLM GEMV) of a forward overlaps conv_in / the first
-                             // resnet on a side stream (measured +0.2 %: not worth a second stream by default)
-  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pip = true;           // GroupNorm / resample prep passes fused into the consuming GEMM's prologue (NS2VC_PIP=0: separate prep launches)
+  bool merge_ff = true;      // ff.net.2 + proj_out as one GEMM (NS2VC_MERGE_FF=0: two launches)
+  float* film_base = nullptr;        // FiLM rows of the active program (workspace), and the caller-supplied replacement for one forward
+  const float* film_ext = nullptr;
   bool lnfold = true;        // LayerNorms of the transformer folded into their consumer GEMMs (NS2VC_LNFOLD=0: separate LN kernels)
   unsigned long long* trace = nullptr; int trace_cap = 0;
   unsigned long long* attn_trace = nullptr; int attn_trace_cap = 0;
@@ -317,15 +319,39 @@ int ln_fold_vectors(ns2vc_unet* h, const std::string& wname, const std::string& 
   return 0;
 }
 
+int pack_seg_ptr(ns2vc_unet* h, PackedB& pb, const float* w, int n_rows, int cin_total, int ktaps, int tap, int cin0,
+                 int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st, const float* cscale = nullptr);
 int pack_seg(ns2vc_unet* h, PackedB& pb, const std::string& wname, int n_rows, int cin_total, int ktaps, int tap, int cin0,
              int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st, const float* cscale = nullptr) {
   const float* w = h->W(wname);
   NS_REQUIRE(w != nullptr, "pack: weight %s missing", wname.c_str());
+  return pack_seg_ptr(h, pb, w, n_rows, cin_total, ktaps, tap, cin0, ncin, n_dst0, kb0, geglu_half, st, cscale);
+}
+int pack_seg_ptr(ns2vc_unet* h, PackedB& pb, const float* w, int n_rows, int cin_total, int ktaps, int tap, int cin0,
+                 int ncin, int n_dst0, int kb0, int geglu_half, cudaStream_t st, const float* cscale) {
+  (void)h;
   PackSeg ps;
   ps.cscale = cscale;
   ps.w = w; ps.n_rows = n_rows; ps.cin_total = cin_total; ps.ktaps = ktaps; ps.tap = tap; ps.cin0 = cin0; ps.ncin = ncin;
   ps.n_dst0 = n_dst0; ps.kb0 = kb0; ps.nkb = nkb_of(ncin); ps.geglu_half = geglu_half;
   return launch_pack_b(ps, pb.hi, pb.lo, pb.f32, pb.Npad, st);
+}
+
+// Wm[n, k] = sum_c Wp[n, c] W2[c, k]  (load time; double accumulation): the product matrix of ff.net.2 followed by proj_out
+__global__ void matmul_nn_kernel(const float* __restrict__ Wp, const float* __restrict__ W2, float* __restrict__ Wm, int N, int Cmid, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (k >= K || n >= N) return;
+  double acc = 0;
+  for (int c = 0; c < Cmid; ++c) acc += (double)Wp[(long long)n * Cmid + c] * (double)W2[(long long)c * K + k];
+  Wm[(long long)n * K + k] = (float)acc;
+}
+// bm[n] = sum_c Wp[n, c] b2[c] + bp[n]
+__global__ void matvec_bias_kernel(const float* __restrict__ Wp, const float* __restrict__ b2, const float* __restrict__ bp, float* __restrict__ bm, int N, int Cmid) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double acc = bp[n];
+  for (int c = 0; c < Cmid; ++c) acc += (double)Wp[(long long)n * Cmid + c] * (double)b2[c];
+  bm[n] = (float)acc;
 }
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
@@ -404,6 +430,18 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
       if ((rc = pack_seg(h, x.ff2, b + ".ff.net.2.weight", C, 4 * C, 1, 0, 0, 4 * C, 0, 0, 0, st))) return rc;
       if ((rc = alloc_packed(h, x.proj_out, C, C, nk))) return rc;
       if ((rc = pack_seg(h, x.proj_out, x.p + ".proj_out.weight", C, C, 1, 0, 0, C, 0, 0, 0, st))) return rc;
+      if (h->merge_ff && fold) {
+        // proj_out o ff.net.2 as one operator: K blocks [Wp W2 over the 4C GEGLU channels | Wp over the C residual channels]
+        const float* Wp = h->W(x.p + ".proj_out.weight"); const float* W2 = h->W(b + ".ff.net.2.weight");
+        NS_REQUIRE(Wp && W2, "pack: %s feed-forward / proj_out weights missing", x.p.c_str());
+        float* Wm = nullptr;
+        if (dev_alloc(h, &Wm, (size_t)C * 4 * C, false) || dev_alloc(h, &x.bias_ff2p, (size_t)C, false)) return -2;
+        matmul_nn_kernel<<<dim3(ceil_div(4 * C, 128), C), 128, 0, st>>>(Wp, W2, Wm, C, C, 4 * C);
+        matvec_bias_kernel<<<ceil_div(C, 128), 128, 0, st>>>(Wp, h->W(b + ".ff.net.2.bias"), h->W(x.p + ".proj_out.bias"), x.bias_ff2p, C, C);
+        if ((rc = alloc_packed(h, x.ff2p, C, C, nkb_of(4 * C) + nk))) return rc;
+        if ((rc = pack_seg_ptr(h, x.ff2p, Wm, C, 4 * C, 1, 0, 0, 4 * C, 0, 0, 0, st))) return rc;
+        if ((rc = pack_seg(h, x.ff2p, x.p + ".proj_out.weight", C, C, 1, 0, 0, C, 0, nkb_of(4 * C), 0, st))) return rc;
+      }
       x.kv_off = kv_off;
       kv_off += C;
       h->xformers.push_back(x);
@@ -461,6 +499,17 @@ int pack_all(ns2vc_unet* h, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // Program construction
 // ---------------------------------------------------------------------------------------------
+// ATen nearest_idx (UpSample.h), as ns2vc_nearest_index() below; IEEE fp32 division / product / floor: bit-identical on host and device
+__global__ void nearest_index_kernel(int t_in, int t_out, int* idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t_out) return;
+  int s;
+  if (t_out == t_in) s = i;
+  else if (t_out == 2 * t_in) s = i >> 1;
+  else { const float scale = __fdiv_rn((float)t_in, (float)t_out); s = min((int)floorf(__fmul_rn((float)i, scale)), t_in - 1); }
+  idx[i] = s;
+}
+
 struct Builder {
   ns2vc_unet* h;
   Arena ar;
@@ -497,25 +546,54 @@ struct Builder {
     const int i = add_src(g, s);
     for (int j = 0; j < 3; ++j) seg(g, i, 0, s.C, j - 1);
   }
+  // Prep passes emitted since the last GEMM.  emit_gemm() folds them into the GEMM's prologue when the fused path applies
+  // (tcgen05 backend, <= 8 N tiles, <= 2 preps, every prep output is an A source of this GEMM); otherwise they are flushed
+  // as launches of their own, in order.
+  std::vector<Launch> pending;
+  void flush_pending() { for (auto& l : pending) out->push_back(l); pending.clear(); }
   void emit_gemm(GemmOp& g, const PackedB& w, int patch = 0) {
     Launch l; l.kind = Launch::GEMM; l.patch = patch;
+    bool fuse = h->pip && !h->simt && !pending.empty() && pending.size() <= 2 && !(g.flags & EPI_GEGLU) && w.Npad / 64 <= kMaxPipCluster;
+    if (fuse) {
+      for (size_t i = 0; i < pending.size() && fuse; ++i) {
+        const PrepOp& p = pending[i].prep;
+        if (pending[i].kind != Launch::PREP || pending[i].patch != 0) { fuse = false; break; }
+        if (p.mode != PREP_RAW && !p.scale && ((p.C1 + p.C2) > kPrepFuseMaxC || p.gn.G > 64)) { fuse = false; break; }
+        int lo = 1 << 30, hi = -(1 << 30);
+        for (int si = 0; si < g.nseg; ++si) {
+          const SplitBuf& sb = g.src[g.seg[si].src];
+          if (sb.hi == p.out.hi || (p.raw.hi && sb.hi == p.raw.hi)) { lo = std::min(lo, g.seg[si].tap); hi = std::max(hi, g.seg[si].tap); }
+        }
+        // a prep whose outputs this GEMM does not read at all (the shortcut operand is read by conv2) rides along with tap range 0
+        if (lo > hi) { fuse = false; break; }
+        g.pre_film[i] = p.gn.film; g.pre_tap_lo[i] = lo; g.pre_tap_hi[i] = hi;
+        // the prep's rows are indexed by the tile's output rows (the odd-row copy of a stride-2 conv may be one row shorter)
+        if (p.T_dst > g.T_out || p.B != g.B) { fuse = false; break; }
+      }
+      if (fuse) g.npre = (int)pending.size();
+    }
+    if (fuse) {
+      // the prep descriptors live in the workspace (device memory): the kernel parameter block stays small
+      PrepOp* pd = ar.get<PrepOp>(2);
+      g.pre = pd;
+      if (!dry) {
+        PrepOp tmp[2];
+        for (int i = 0; i < g.npre; ++i) { tmp[i] = pending[i].prep; tmp[i].gn.film = nullptr; }
+        if (cudaMemcpy(pd, tmp, sizeof(PrepOp) * g.npre, cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
+      }
+      pending.clear();
+    } else { g.npre = 0; g.pre = nullptr; flush_pending(); }
     if (!dry) {
       if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
       plan_gemm(g);
       if (!h->simt) { int rc = encode_tmaps(g); if (rc) err = rc; }
     }
-    // descriptors also live in the workspace (device memory): see GemmOp::dmaps
-    TMap* dm = (h->simt || !h->dev_tmaps) ? nullptr : ar.get<TMap>(2 * kMaxSrc + 3);
-    if (!dry && dm) {
-      TMap tmp[2 * kMaxSrc + 3];
-      memcpy(tmp, g.tmap, sizeof(g.tmap));
-      memcpy(tmp + 2 * kMaxSrc, g.tmap_out, sizeof(g.tmap_out));
-      if (cudaMemcpy(dm, tmp, sizeof(tmp), cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
-      g.dmaps = dm;
-    }
     l.gemm = g;
+    for (int i = 0; i < g.npre; ++i) if (g.pre_film[i]) l.reads_film = 1;
+    if (g.flags & EPI_ROWBIAS) l.reads_film = 1;
     out->push_back(l);
   }
+  void push(const Launch& l) { flush_pending(); out->push_back(l); }
   void emit_prep(const float* s1, int C1, const float* s2, int C2, int T_src, int T_dst, int mode, const float* scale,
                  const float* shift, const SplitBuf& o, const SplitBuf* raw = nullptr, int row_mul = 1, int row_add = 0,
                  const int* rowmap = nullptr, int patch = 0) {
@@ -524,25 +602,26 @@ struct Builder {
     p.src1 = s1; p.ld1 = C1; p.C1 = C1; p.src2 = s2; p.ld2 = C2; p.C2 = C2; p.B = B; p.T_src = T_src; p.T_dst = T_dst;
     p.row_mul = row_mul; p.row_add = row_add; p.rowmap = rowmap; p.mode = mode; p.scale = scale; p.shift = shift; p.out = o;
     if (raw) p.raw = *raw;
-    out->push_back(l);
+    pending.push_back(l);
   }
   // GroupNorm(+FiLM)(+SiLU) prep whose statistics come from the producers' epilogues
   void emit_prep_gn(const float* s1, int C1, const double* st1, const float* s2, int C2, const double* st2, int Tn, int mode,
                     float eps, const float* gamma, const float* beta, const float* film, int film_ld, const SplitBuf& o,
                     const SplitBuf* raw = nullptr) {
     emit_prep(s1, C1, s2, C2, Tn, Tn, mode, nullptr, nullptr, o, raw);
-    PrepOp& p = out->back().prep;
+    PrepOp& p = pending.back().prep;
+    if (film) pending.back().reads_film = 1;
     p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
     p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
     p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film = film; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
   }
   void emit_ln_split(const float* x, int ld, int M, int C, const float* gamma, const float* beta, const SplitBuf& o) {
     Launch l; l.kind = Launch::LN_SPLIT; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.b = gamma; l.c = beta; l.split = o;
-    out->push_back(l);
+    push(l);
   }
   void emit_tap(const std::string& name, const float* src, int level, int C, int Tl) {
     if (!dry && taps) {
-      Launch l; l.kind = Launch::TAP; l.a = src; l.i0 = B * Tl * C; l.tap_index = (int)h->tap_names.size(); out->push_back(l);
+      Launch l; l.kind = Launch::TAP; l.a = src; l.i0 = B * Tl * C; l.tap_index = (int)h->tap_names.size(); push(l);
       h->tap_names.push_back(name); h->tap_level.push_back(level); h->tap_ch.push_back(C);
     }
   }
@@ -561,8 +640,6 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 
   std::vector<Launch> cond, fwd;
   if (!dry) {
-    for (int* p : h->rowmaps) cudaFree(p);
-    h->rowmaps.clear();
     h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear();
   }
   Builder bld{h, Arena{(uint8_t*)ws, 0}, B, T, S, &cond, dry};
@@ -637,13 +714,11 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   for (auto& o : h->plan) {
     if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)4 * B * o.cout;
     else if (o.kind == PlanOp::XFORMER || o.kind == PlanOp::DOWN || o.kind == PlanOp::UP) stat_doubles += (size_t)2 * B * o.cout;
-    if (o.kind == PlanOp::RESNET) stat_doubles += (size_t)(B + 1) / 2 + 1;                          // barrier counters of the fused GroupNorm
     if (o.kind == PlanOp::XFORMER && h->lnfold) stat_doubles += (size_t)3 * 2 * B * Tl[o.level];   // three LayerNorm row-statistics buffers
   }
   double* stat_arena = ar.get<double>(stat_doubles);
   size_t stat_used = 0;
   auto new_stats = [&](int C) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += (size_t)2 * B * C; return p; };
-  auto new_counters = [&](int n) { unsigned int* p = stat_arena ? reinterpret_cast<unsigned int*>(stat_arena + stat_used) : nullptr; stat_used += (size_t)(n + 1) / 2 + 1; return p; };
   auto new_rowstats = [&](size_t nrows) { double* p = stat_arena ? stat_arena + stat_used : nullptr; stat_used += 2 * nrows; return p; };
   auto with_stats = [&](GemmOp& g, double* st_, int C) { g.flags |= EPI_STATS; g.stat_sum = st_; g.stat_sq = st_ ? st_ + (size_t)B * C : nullptr; };
   { Launch l; l.kind = Launch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); fwd.push_back(l); }
@@ -675,13 +750,13 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   { Launch l; l.kind = Launch::NCT2SPLIT; l.patch = 1; l.i0 = Cl; l.i1 = T; l.split = s_xin; fwd.push_back(l); }
   { Launch l; l.kind = Launch::LINEAR; l.patch = 2; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = nullptr; o.x_ld = 1; o.M = B; o.K = c0; o.W = h->W("time_embedding.linear_1.weight"); o.bias = h->W("time_embedding.linear_1.bias");
-    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; l.side = 1; fwd.push_back(l); }
+    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1; l.time_path = 1; fwd.push_back(l); }
   { Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = temb1; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->W("time_embedding.linear_2.weight"); o.bias = h->W("time_embedding.linear_2.bias");
-    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = aug; o.add_ld = ted; } l.side = 1; fwd.push_back(l); }
+    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = aug; o.add_ld = ted; } l.time_path = 1; fwd.push_back(l); }
   if (h->film_total > 0) {
     Launch l; l.kind = Launch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
-    o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; l.side = 1; fwd.push_back(l);
+    o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; l.time_path = 1; fwd.push_back(l);
   }
 
   struct Skip { float* p; int c; double* st; };
@@ -724,7 +799,6 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         bld.emit_prep_gn(s1, s.c1, cur_st, s2, s.c2, s.c2 ? cat2_st : nullptr, TL, PREP_AFFINE_SILU, c.norm_eps,
                          h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, a_in, s.shortcut ? &a_raw : nullptr);
         double* h1_st = new_stats(s.cout);
-        bool fused_gn = false;
         {
           GemmOp g = bld.gemm_base(s.conv1, TL);
           bld.conv3(g, a_in);
@@ -732,23 +806,11 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
           g.out = H1; g.out_ld = s.cout;
           with_stats(g, h1_st, s.cout);
-          // norm2 (+FiLM) + SiLU applied by conv1 itself once all its tiles' column sums are in (reference resnet.py:602-612):
-          // possible when every tile is resident at once and the channel count divides into the groups
-          fused_gn = h->gnfuse && !(g.flags & EPI_ROWBIAS) && (s.cout % c.norm_num_groups) == 0 && (s.cout / c.norm_num_groups) <= 64 * 32 &&
-                     gemm_tiles_coresident(g);
-          unsigned int* ctr = new_counters(B);
-          if (fused_gn) {
-            g.flags = (g.flags & ~EPI_OUT_F32) | EPI_OUT_SPLIT | EPI_GNAPPLY;
-            g.out = nullptr; g.out_hi = a_h.hi; g.out_lo = a_h.lo; g.out_split_ld = a_h.ld;
-            g.gn_gamma = h->W(s.p + ".norm2.weight"); g.gn_beta = h->W(s.p + ".norm2.bias");
-            g.gn_film = c.time_scale_shift ? film + s.film_off : nullptr; g.gn_film_ld = h->film_total;
-            g.gn_G = c.norm_num_groups; g.gn_eps = c.norm_eps; g.gn_silu = 1; g.gn_counter = ctr;
-          }
           bld.emit_gemm(g, s.conv1);
         }
-        if (!fused_gn)
-          bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
-                           h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
+        // norm2 (+FiLM scale/shift) + SiLU (reference resnet.py:602-612)
+        bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
+                         h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
         float* outp = next_out(followed_by_push(pi), rows * s.cout);
         double* out_st = new_stats(s.cout);
         {
@@ -803,7 +865,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           a.B = B; a.H = H; a.Tq = TL; a.Tk = TL; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh);
           if (av2) { a.v2 = 1; a.qs = sqkv; a.ks = sqkv; a.vs = sqkv; a.q_c0 = 0; a.k_c0 = C; a.v_c0 = 2 * C;
                      if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
-          fwd.push_back(l); }
+          bld.push(l); }
         { GemmOp g = lin(x.out1, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn1.to_out.0.bias"); g.res = T0; g.res_ld = C; g.out = T1; g.out_ld = C;
           if (fold) emits_ln_input(g, rs2);
           bld.emit_gemm(g, x.out1); }
@@ -819,7 +881,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           a.B = B; a.H = H; a.Tq = TL; a.Tk = S; a.dh = dh; a.scale = 1.0f / sqrtf((float)dh); l.i0 = 1 /*cross*/;
           if (av2) { a.v2 = 1; a.qs = sq2; a.ks = kvs; a.vs = kvs; a.q_c0 = 0; a.k_c0 = x.kv_off; a.v_c0 = x.v_off;
                      if (!dry) { int rc = encode_attn_tmaps(a); if (rc) bld.err = rc; } }
-          fwd.push_back(l); }
+          bld.push(l); }
         { GemmOp g = lin(x.out2, satt, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(b + ".attn2.to_out.0.bias"); g.res = T1; g.res_ld = C; g.out = T0; g.out_ld = C;
           if (fold) emits_ln_input(g, rs3);
           bld.emit_gemm(g, x.out2); }
@@ -828,11 +890,20 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld;
           if (fold) { consumes_ln(g, rs3, x.g_ff1, x.bf_ff1); g.flags &= ~EPI_BIAS; }   // GEGLU reads its (folded) biases through g.bias itself
           bld.emit_gemm(g, x.ff1); }
-        { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
-          g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
         float* outp = next_out(followed_by_push(pi), rows * C);
-        { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
-          cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.proj_out); }
+        if (h->merge_ff && fold) {
+          // ff.net.2 + proj_out as one GEMM over K = [GEGLU output | residual stream]:  out = g (Wp W2)^T + h Wp^T + (Wp b2 + bp) + x_in
+          GemmOp g = bld.gemm_base(x.ff2p, TL);
+          const int i0 = bld.add_src(g, sff); bld.seg(g, i0, 0, 4 * C, 0);
+          const int i1 = bld.add_src(g, sln); bld.seg(g, i1, 0, C, 0);          // raw split of the residual stream, written by out2's epilogue
+          g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = x.bias_ff2p; g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
+          cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.ff2p);
+        } else {
+          { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
+            g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
+          { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
+            cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.proj_out); }
+        }
         cur = outp;
         bld.emit_tap(x.p, cur, o.level, C, TL);
         break;
@@ -860,14 +931,12 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
       case PlanOp::UP: {
         const ConvSite& s = h->resamplers[si++];
         const int Tin = Tl[o.level + 1];
-        int* map_d = nullptr;
+        // nearest-neighbour source rows of F.interpolate(size=TL) (reference resnet.py:160): a table in the workspace, filled on
+        // the device with the same fp32 rule as ns2vc_nearest_index() (stream-ordered: no allocation, no host sync)
+        int* map_d = ar.get<int>((size_t)TL);
         if (!dry) {
-          std::vector<int> idx(TL);
-          ns2vc_nearest_index(Tin, TL, idx.data());
-          NS_CHECK_CUDA(cudaMalloc(&map_d, (size_t)TL * sizeof(int)));
-          NS_CHECK_CUDA(cudaMemcpyAsync(map_d, idx.data(), (size_t)TL * sizeof(int), cudaMemcpyHostToDevice, st));
-          NS_CHECK_CUDA(cudaStreamSynchronize(st));
-          h->rowmaps.push_back(map_d);
+          nearest_index_kernel<<<ceil_div(TL, 256), 256, 0, st>>>(Tin, TL, map_d);
+          NS_CHECK_CUDA(cudaGetLastError());
         }
         const SplitBuf up = Builder::view(SP_A, TL, s.c);
         bld.emit_prep(cur, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, up, nullptr, 1, 0, map_d);
@@ -892,11 +961,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
     bld.emit_gemm(g, h->conv_out, 3);
   }
-  // the first launch that reads the timestep path's output (FiLM rows / time row bias) is where the side stream joins
-  for (auto& l : fwd) {
-    const bool reads_film = (l.kind == Launch::PREP && l.prep.gn.film) || (l.kind == Launch::GEMM && ((l.gemm.flags & EPI_ROWBIAS) || l.gemm.gn_film));
-    if (reads_film) { l.join = 1; break; }
-  }
+  bld.flush_pending();
   if (bld.err) return bld.err;
   if (bytes_out) *bytes_out = ar.off + 256;
   if (!dry) {
@@ -904,6 +969,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     h->prog_fwd = std::move(fwd);
     h->tap_dst.assign(h->tap_names.size(), nullptr);
     h->pB = B; h->pT = T; h->pS = S; h->pws = ws; h->cond_ready = false;
+    h->film_base = film; h->aug = aug;
   }
   return 0;
 }
@@ -911,31 +977,12 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
 int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long long x_bstride, const float* t, float* out,
                 const float* content, long long content_bstride, const float* prompt, const uint8_t* mask, cudaStream_t st) {
   int rc = 0, count = 0, gemm_idx = 0, attn_idx = 0;
-  // Fork / join of the timestep path: it depends on t only, so it overlaps the x-dependent head of the forward.  Both
-  // event edges are ordinary stream dependencies, so the pattern is also valid under stream capture (the side stream
-  // joins the capture at the fork and is joined back before the first consumer).
-  const bool fork = h->fork_time && !h->profiling && !h->span && !h->trace;
-  bool forked = false, joined = false;
-  if (fork && !h->side) {
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { set_error("cannot create the side stream"); return -2; }
-  }
-  cudaStream_t main_st = st;
+  // Precomputed FiLM rows (ns2vc_unet_time_table): the timestep path of this forward is skipped and every reader is rebased.
+  const float* film_ext = h->film_ext;
+  auto rebase = [&](const float* p) { return (film_ext && p) ? film_ext + (p - h->film_base) : p; };
   for (size_t li = 0; li < prog.size(); ++li) {
     Launch& l = prog[li];
-    st = main_st;
-    if (fork && l.side) {
-      if (!forked) {
-        if (cudaEventRecord(h->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork, 0) != cudaSuccess) { set_error("side-stream fork failed"); return -2; }
-        forked = true;
-      }
-      st = h->side;
-    }
-    if (fork && forked && !joined && (l.join || li + 1 == prog.size())) {
-      if (cudaEventRecord(h->ev_join, h->side) != cudaSuccess || cudaStreamWaitEvent(main_st, h->ev_join, 0) != cudaSuccess) { set_error("side-stream join failed"); return -2; }
-      joined = true;
-    }
+    if (film_ext && l.time_path) continue;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     const bool prof = h->profiling && l.kind != Launch::TAP;
     if (prof) {
@@ -944,11 +991,15 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
     }
     switch (l.kind) {
       case Launch::GEMM: {
-        if (l.patch == 3 || h->trace || h->span) {
+        if (l.patch == 3 || h->trace || h->span || (film_ext && l.reads_film)) {
           GemmOp g = l.gemm;
           if (l.patch == 3) g.out = out;
+          if (film_ext && l.reads_film) {
+            g.rowbias = rebase(g.rowbias);
+            for (int i = 0; i < g.npre; ++i) g.pre_film[i] = rebase(g.pre_film[i]);
+          }
           if (h->span && count < h->span_cap) g.span = h->span + 2 * count;
-          if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 16 * gemm_idx;
+          if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 32 * gemm_idx;
           ++gemm_idx;
           rc = h->simt ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
         } else {
@@ -986,6 +1037,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       case Launch::PREP: {
         PrepOp p = l.prep;
         if (l.patch == 5) p.src1 = prompt;
+        if (film_ext && l.reads_film) p.gn.film = rebase(p.gn.film);
         if (h->span && count < h->span_cap) p.span = h->span + 2 * count;
         rc = launch_prep_split(p, st);
         break;
@@ -1027,21 +1079,15 @@ void stash_active(ns2vc_unet* h) {
   if (!h->pws) return;
   ns2vc_unet::Stash s;
   s.pB = h->pB; s.pT = h->pT; s.pS = h->pS; s.pws = h->pws; s.has_mask = h->has_mask; s.cond_ready = h->cond_ready;
-  s.prog_cond = std::move(h->prog_cond); s.prog_fwd = std::move(h->prog_fwd); s.rowmaps = std::move(h->rowmaps);
+  s.prog_cond = std::move(h->prog_cond); s.prog_fwd = std::move(h->prog_fwd); s.film_base = h->film_base; s.aug = h->aug;
   s.tap_names = std::move(h->tap_names); s.tap_level = std::move(h->tap_level); s.tap_ch = std::move(h->tap_ch); s.tap_dst = std::move(h->tap_dst);
-  h->prog_cond.clear(); h->prog_fwd.clear(); h->rowmaps.clear(); h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear(); h->tap_dst.clear();
+  h->prog_cond.clear(); h->prog_fwd.clear(); h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear(); h->tap_dst.clear();
   h->pB = h->pT = h->pS = 0; h->pws = nullptr; h->cond_ready = false;
-  if (h->stash.size() >= 16) {                       // bounded: drop the oldest program
-    for (int* p : h->stash.front().rowmaps) cudaFree(p);
-    h->stash.erase(h->stash.begin());
-  }
+  if (h->stash.size() >= 16) h->stash.erase(h->stash.begin());   // bounded: drop the oldest program (it owns no device memory: everything lives in its workspace)
   h->stash.push_back(std::move(s));
 }
 
 void drop_all_programs(ns2vc_unet* h) {
-  for (int* p : h->rowmaps) cudaFree(p);
-  h->rowmaps.clear();
-  for (auto& s : h->stash) for (int* p : s.rowmaps) cudaFree(p);
   h->stash.clear();
   h->prog_cond.clear(); h->prog_fwd.clear();
   h->pB = h->pT = h->pS = 0; h->pws = nullptr; h->cond_ready = false;
@@ -1057,7 +1103,7 @@ int ensure_program(ns2vc_unet* h, int B, int T, int S, void* ws, cudaStream_t st
     ns2vc_unet::Stash& s = h->stash[i];
     if (s.pB == B && s.pT == T && s.pS == S && s.pws == ws) {
       h->pB = s.pB; h->pT = s.pT; h->pS = s.pS; h->pws = s.pws; h->has_mask = s.has_mask; h->cond_ready = s.cond_ready;
-      h->prog_cond = std::move(s.prog_cond); h->prog_fwd = std::move(s.prog_fwd); h->rowmaps = std::move(s.rowmaps);
+      h->prog_cond = std::move(s.prog_cond); h->prog_fwd = std::move(s.prog_fwd); h->film_base = s.film_base; h->aug = s.aug;
       h->tap_names = std::move(s.tap_names); h->tap_level = std::move(s.tap_level); h->tap_ch = std::move(s.tap_ch); h->tap_dst = std::move(s.tap_dst);
       h->stash.erase(h->stash.begin() + i);
       return 0;
@@ -1114,12 +1160,8 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
-  { const char* e = getenv("NS2VC_FORK_TIME"); h->fork_time = (e && e[0] == '1'); }
-  { const char* e = getenv("NS2VC_DEV_TMAPS"); h->dev_tmaps = (e && e[0] == '1'); }
-  { const char* e = getenv("NS2VC_GNFUSE"); const char* t = getenv("NS2VC_TMA_STORE");
-    // opt-in: measured r01 at cfg2 3.52 ms per forward fused vs 3.36 ms with the separate prep kernel (the barrier + statistics
-    // round trip inside the epilogue costs more than the PDL-overlapped prep launch it removes)
-    h->gnfuse = (e && e[0] == '1') && !h->simt && !(t && t[0] == '0'); }   // the fused GroupNorm writes its split through TMA
+  { const char* e = getenv("NS2VC_PIP"); h->pip = (e && e[0] == '1'); }   // measured r02: 3.67 vs 3.44 ms per forward (the prep phase runs at 10 warps per SM) - off
+  { const char* e = getenv("NS2VC_MERGE_FF"); h->merge_ff = !(e && e[0] == '0'); }
   build_plan(h);
   register_weights(h);
   *out = h;
@@ -1131,9 +1173,6 @@ void ns2vc_unet_destroy(ns2vc_unet* h) {
   for (auto& w : h->weights) if (w.d) cudaFree(w.d);
   for (void* p : h->owned) cudaFree(p);
   drop_all_programs(h);
-  if (h->side) cudaStreamDestroy(h->side);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -1204,17 +1243,67 @@ int ns2vc_unet_forward(ns2vc_unet* h, const float* x, long long x_bstride, const
   return run_program(h, h->prog_fwd, x, x_bstride, t, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+int ns2vc_unet_film_width(const ns2vc_unet* h) { return h ? h->film_total : -1; }
+
+size_t ns2vc_unet_time_table_floats(const ns2vc_unet* h, int n_rows) {
+  if (!h || n_rows <= 0) return 0;
+  return (size_t)n_rows * ((size_t)std::max(h->film_total, 1) + 2 * (size_t)h->ted);
+}
+
+int ns2vc_unet_time_table(ns2vc_unet* h, const float* t_rows, int n_rows, float* table, int B, int T, int S, void* ws, ns2vc_stream stream) {
+  NS_REQUIRE(h && t_rows && table, "null argument");
+  NS_REQUIRE(n_rows > 0 && n_rows % B == 0, "time table: %d rows is not a multiple of the batch %d", n_rows, B);
+  int rc = ensure_program(h, B, T, S, ws, (cudaStream_t)stream);
+  if (rc) return rc;
+  NS_REQUIRE(h->cond_ready || !h->cfg.add_embed_text, "ns2vc_unet_prepare_cond() must precede ns2vc_unet_time_table() (the pooled prompt embedding is added to every row)");
+  const ns2vc_unet_cfg& c = h->cfg;
+  const int ted = h->ted, c0 = c.block_out_channels[0];
+  float* film = table;
+  float* temb1 = table + (size_t)n_rows * std::max(h->film_total, 1);
+  float* emb = temb1 + (size_t)n_rows * ted;
+  cudaStream_t st = (cudaStream_t)stream;
+  // reference embeddings.py:24-64, 157-218 (sinusoid -> linear_1 -> SiLU -> linear_2), unet_1d_condition.py:869-883 (+ aug_emb),
+  // resnet.py:619-629 (time_emb_proj of SiLU(emb) for all 22 resnets at once)
+  { LinOp o; memset(&o, 0, sizeof(o));
+    o.x = t_rows; o.x_ld = 1; o.M = n_rows; o.K = c0; o.W = h->W("time_embedding.linear_1.weight"); o.bias = h->W("time_embedding.linear_1.bias");
+    o.N = ted; o.out = temb1; o.out_ld = ted; o.in_mode = LIN_SINUSOID; o.flip_sin_to_cos = c.flip_sin_to_cos; o.freq_shift = c.freq_shift; o.out_silu = 1;
+    if ((rc = launch_small_linear(o, st))) return rc; }
+  { LinOp o; memset(&o, 0, sizeof(o));
+    o.x = temb1; o.x_ld = ted; o.M = n_rows; o.K = ted; o.W = h->W("time_embedding.linear_2.weight"); o.bias = h->W("time_embedding.linear_2.bias");
+    o.N = ted; o.out = emb; o.out_ld = ted; if (c.add_embed_text) { o.add = h->aug; o.add_ld = ted; o.add_rows = B; }
+    if ((rc = launch_small_linear(o, st))) return rc; }
+  if (h->film_total > 0) {
+    LinOp o; memset(&o, 0, sizeof(o));
+    o.x = emb; o.x_ld = ted; o.M = n_rows; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU;
+    if ((rc = launch_small_linear(o, st))) return rc;
+  }
+  return 0;
+}
+
+int ns2vc_unet_forward_film(ns2vc_unet* h, const float* x, long long x_bstride, const float* film_rows, float* out, int B, int T, int S,
+                            void* ws, ns2vc_stream stream) {
+  NS_REQUIRE(h && x && film_rows && out, "null argument");
+  int rc0 = ensure_program(h, B, T, S, ws, (cudaStream_t)stream);
+  if (rc0) return rc0;
+  NS_REQUIRE(h->cond_ready, "ns2vc_unet_prepare_cond() must be called with the same (B,T,S,workspace) before forward");
+  NS_REQUIRE(h->film_total > 0, "the model has no FiLM rows");
+  h->film_ext = film_rows;
+  const int rc = run_program(h, h->prog_fwd, x, x_bstride, nullptr, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+  h->film_ext = nullptr;
+  return rc;
+}
+
 int ns2vc_dpm_step(const float* x, const float* unet_out, const float* m_prev, const ns2vc_dpm_coef* c, float* m_cur, float* x_next,
-                   size_t n, ns2vc_stream stream) {
+                   size_t n, int* nan_flag, ns2vc_stream stream) {
   NS_REQUIRE(x && unet_out && c && m_cur, "null argument");
   NS_REQUIRE(c->order == 0 || x_next, "x_next is NULL");
   NS_REQUIRE(c->order < 2 || m_prev, "m_prev is NULL for a second-order step");
   DpmStepCoef k; k.alpha_s = c->alpha_s; k.sigma_s = c->sigma_s; k.c_x = c->c_x; k.c_m = c->c_m; k.c_d = c->c_d; k.inv_r0 = c->inv_r0; k.order = c->order;
-  return launch_dpm_step(x, unet_out, m_prev, k, m_cur, x_next, n, (cudaStream_t)stream);
+  return launch_dpm_step(x, unet_out, m_prev, k, m_cur, x_next, n, nan_flag, (cudaStream_t)stream);
 }
 
 int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0, const float* m1,
-                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, ns2vc_stream stream) {
+                     const ns2vc_unipc_coef* c, float* m_t, float* x_t, float* x_pred, size_t n, int* nan_flag, ns2vc_stream stream) {
   NS_REQUIRE(x_eval && unet_out && c && m_t, "null argument");
   NS_REQUIRE(c->corr_order == 0 || (x_prev && m0 && x_t), "corrector inputs missing");
   NS_REQUIRE(c->corr_order < 2 || m1, "m1 is NULL for an order-2 corrector");
@@ -1223,7 +1312,7 @@ int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet
   UniPcStepCoef k;
   k.alpha_t = c->alpha_t; k.sigma_t = c->sigma_t; k.c_x = c->c_x; k.c_m = c->c_m; k.ab = c->ab; k.rk = c->rk; k.rho0 = c->rho0; k.rho1 = c->rho1;
   k.corr_order = c->corr_order; k.n_c_x = c->n_c_x; k.n_c_m = c->n_c_m; k.nab = c->nab; k.nrk = c->nrk; k.pred_order = c->pred_order;
-  return launch_unipc_step(x_prev, x_eval, unet_out, m0, m1, k, m_t, x_t, x_pred, n, (cudaStream_t)stream);
+  return launch_unipc_step(x_prev, x_eval, unet_out, m0, m1, k, m_t, x_t, x_pred, n, nan_flag, (cudaStream_t)stream);
 }
 
 int ns2vc_unet_num_taps(const ns2vc_unet* h) { return h ? (int)h->tap_names.size() : -1; }

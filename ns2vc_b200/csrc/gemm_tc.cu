@@ -28,6 +28,7 @@
 //              -> bias / GEGLU / residual -> staged 32x32 chunks -> TMA bulk stores (fp32 token-major, 16-bit hi/lo
 //              split for the next GEMM / attention), or direct channel-major stores for the output head
 #include "gemm_common.cuh"
+#include "prep_common.cuh"
 #include "tc_common.cuh"
 #include "launch.cuh"
 #include <cuda.h>
@@ -61,7 +62,7 @@ template <int BN_> struct TileCfg {
   static constexpr int kPipeBytes = (kStagesSingle * kStageBytes > kOffStagingMulti + kStagingBytes) ? kStagesSingle * kStageBytes : kOffStagingMulti + kStagingBytes;
   static constexpr int kOffBar = kPipeBytes;
   static constexpr int kOffDesc = kOffBar + 1024;
-  static constexpr int kOffLnG = kOffDesc + 2304;         // [8 warps][4][32] floats: folded-LayerNorm g and bias vectors of the warp's chunk
+  static constexpr int kOffLnG = kOffDesc + 3072;         // [8 warps][4][32] floats: folded-LayerNorm g and bias vectors of the warp's chunk
   static constexpr int kSmemBytes = kOffLnG + 4096 + 1024 /*alignment slack*/;
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BM, BN_);
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
@@ -164,17 +165,19 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
 }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// fused-prep stamps of thread 0 of CTA 0: slots 16.. of the 32-slot trace record
+#define PTRACE(i) do { if (op_param.trace && blockIdx.x == 0 && tid == 0) op_param.trace[16 + (i)] = gtime(); } while (0)
 #define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
 // epilogue sub-steps of warp 2 / lane 0 of CTA (0,0), SM clock: slots 8..15 of the 16-slot trace record
 __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
 #define ETRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) op.trace[8 + (i)] = gclk(); } while (0)
 
-static_assert(sizeof(GemmOp) <= 2304, "GemmOp must fit the shared-memory descriptor copy");
+static_assert(kPrepSlots * kThreads >= kPrepFuseMaxC && prep_affine_floats(kPrepFuseMaxC) * 4 <= 2 * kATileBytes, "fused prep: affine table");
+static_assert(sizeof(GemmOp) <= 2432 && sizeof(PrepOp) <= 320, "GemmOp must fit the shared-memory descriptor copy");
 
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
-// GNA: instantiation for EPI_GNAPPLY (consumer's GroupNorm applied behind an in-kernel barrier).
-template <int BN_, bool LNF, bool GNA>
+template <int BN_, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -201,9 +204,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint4* src = reinterpret_cast<const uint4*>(&op_param);
     uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc);
     for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
+    // fused-prep descriptors (device memory, static): parked behind the operator copy
+    if (op_param.npre > 0) {
+      const uint4* ps = reinterpret_cast<const uint4*>(op_param.pre);
+      uint4* pd = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc + 2432);
+      for (int i = tid; i < op_param.npre * (int)(sizeof(PrepOp) / 16); i += kThreads) pd[i] = __ldg(ps + i);
+    }
   }
   const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + Cfg::kOffDesc);
-  const TMap* tmaps = op_param.dmaps ? op_param.dmaps : op_param.tmap;
+  const TMap* tmaps = op_param.tmap;
   // Persistent tile loop: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (tile = m_tile * n_tiles + n_tile).
   // A CTA with a single tile keeps all kMaxStages pipeline stages and stages its epilogue output in the (then idle)
   // stage buffers; a CTA with several tiles gives the last stage(s) up for a dedicated staging area, so that the
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * op_param.nsrc; ++i) prefetch_tmap(&tmaps[i]);
     // the store maps too: the first bulk store through a cold descriptor costs a ~0.5 us fetch on the epilogue's critical path
-    const TMap* pm = op_param.dmaps ? op_param.dmaps + 2 * kMaxSrc : op_param.tmap_out;
+    const TMap* pm = op_param.tmap_out;
     if (op_param.tma_out & 1) prefetch_tmap(&pm[0]);
     if (op_param.tma_out & 2) { prefetch_tmap(&pm[1]); prefetch_tmap(&pm[2]); }
   }
@@ -240,22 +249,79 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && tr0) TRACE(1);
 
+  // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
+  // griddepcontrol.wait; the activations (written by the previous kernel, or by the fused prep below) only after it.
+  const int npf = nkb < nst ? nkb : nst;
+  if (warp == 0 && lane == 0) {
+    const int n0 = ((int)blockIdx.x % n_tiles) * BN;
+    for (int kb = 0; kb < npf; ++kb) {
+      const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
+      mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
+      const size_t eoff = ((size_t)kb * op.N + n0) * 64;
+      bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(kb));
+      bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
+    }
+  }
+  __syncwarp();
+
+  if constexpr (BN == 64) if (op_param.npre > 0) {
+    // ===================== fused prep (whole CTA; grid == tile count, cluster = the N tiles of one row block) =====================
+    // GroupNorm(+FiLM)(+SiLU) / decimation / nearest-upsample of the producer's fp32 activations into the split A operand
+    // (reference resnet.py:597-612, transformer_1d.py:256-262, resnet.py:160,214-223): this CTA converts its share of the
+    // channels for the rows its tile's taps touch; halo rows are also written (with identical values) by the neighbouring
+    // cluster.  Generic-proxy global stores -> cluster barrier (release / acquire) -> proxy fence -> TMA loads.
+    const int tile = (int)blockIdx.x, mtile = tile / n_tiles, part = tile % n_tiles;
+    const int pb_ = mtile / tiles_per_batch, pt0 = (mtile % tiles_per_batch) * BM;
+    float* aff = reinterpret_cast<float*>(smem);             // stage 0's A tiles are idle until the first activation load
+    for (int p = 0; p < op_param.npre; ++p) {
+      const PrepOp& pr = reinterpret_cast<const PrepOp*>(smem + Cfg::kOffDesc + 2432)[p];
+      const int C = pr.C1 + pr.C2;
+      float pg[kPrepSlots], pbv[kPrepSlots], fs[kPrepSlots], fbv[kPrepSlots];
+      prep_fetch_norm_weights(pr, C, pg, pbv);
+      if (p == 0) { pdl_wait(); PTRACE(0); }
+      prep_fetch_film(pr, op.pre_film[p], pb_, C, fs, fbv);
+      const int chunks = pr.out.ld >> 3, per = (chunks + n_tiles - 1) / n_tiles;
+      const int ck_lo = part * per, ck_hi = (ck_lo + per < chunks) ? ck_lo + per : chunks, nck = ck_hi - ck_lo;
+      const int r_lo = (pt0 + op.pre_tap_lo[p] > 0) ? pt0 + op.pre_tap_lo[p] : 0;
+      const int r_hi = (pt0 + BM + op.pre_tap_hi[p] < pr.T_dst) ? pt0 + BM + op.pre_tap_hi[p] : pr.T_dst;
+      const int total = (nck > 0 && r_hi > r_lo) ? (r_hi - r_lo) * nck : 0;
+      constexpr int kWave = 4;                              // independent work items per thread: their loads are in flight together
+      PrepChunk kc[kWave];
+#pragma unroll
+      for (int u = 0; u < kWave; ++u) {                     // the first wave's loads fly while the affine is derived
+        const int i = tid + u * kThreads;
+        if (i < total) prep_load_at(pr, pb_, C, r_lo + i / nck, ck_lo + i % nck, kc[u]);
+      }
+      if (p == 0) PTRACE(1);
+      prep_affine(pr, pb_, C, aff, pg, pbv, fs, fbv);
+      if (p == 0) PTRACE(2);
+#pragma unroll
+      for (int u = 0; u < kWave; ++u)
+        if (tid + u * kThreads < total) prep_finish(pr, pb_, C, aff, kc[u]);
+      for (int i0 = tid + kWave * kThreads; i0 < total; i0 += kWave * kThreads) {
+#pragma unroll
+        for (int u = 0; u < kWave; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < total) prep_load_at(pr, pb_, C, r_lo + i / nck, ck_lo + i % nck, kc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kWave; ++u)
+          if (i0 + u * kThreads < total) prep_finish(pr, pb_, C, aff, kc[u]);
+      }
+      if (p == 0) PTRACE(3);
+      __syncthreads();                                      // aff is rewritten by the next prep / handed to the pipeline
+    }
+    PTRACE(4);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    if (op_param.cn > 1) cluster_sync_all(); else __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    PTRACE(5);
+  }
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
-      // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
-      const int npre = nkb < nst ? nkb : nst;
-      {
-        const int n0 = ((int)blockIdx.x % n_tiles) * BN;
-        for (int kb = 0; kb < npre; ++kb) {
-          const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
-          mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
-          const size_t eoff = ((size_t)kb * op.N + n0) * 64;
-          bulk_g2s(b_hi, op.w_hi + eoff, Cfg::kBTileBytes, full_bar(kb));
-          bulk_g2s(b_hi + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, full_bar(kb));
-        }
-      }
+      const int npre = npf;
       pdl_wait();
       if (tr0) TRACE(2);
       int g = 0;                                            // k-block counter across this CTA's tiles
@@ -319,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int r = q * 32 + lane;
     const int cc0 = (warp - 2) >> 2;
     uint8_t* st = stage_area + kStageOff + (warp - 2) * kStagePerWarp;   // this warp's staging area
-    const TMap* tmo = op_param.dmaps ? op_param.dmaps + 2 * kMaxSrc : op_param.tmap_out;
+    const TMap* tmo = op_param.tmap_out;
     bool staged_once = false;
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -493,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               atomicAdd(op.row_stats + m * 2 + 1, (double)rq);
             }
             wait_staging();
-            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, !GNA,
+            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, true,
                        (it == 0 && tr0 && warp == 2 && lane == 0) ? op.trace : nullptr);
             staged_once = true;
             if (it == 0 && tr0) ETRACE(3);
@@ -526,108 +592,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             atomicAdd(op.stat_sq + (long long)b * op.n_valid + n0 + col, cq);
           }
         }
-        if constexpr (GNA) {
-          // ---- the consumer's GroupNorm, applied to the tile this CTA still holds in its staging area ----
-          // (b) barrier among the CTAs of batch entry b: every tile's column sums have landed.  All CTAs of the grid are
-          //     resident (one tile per CTA, grid <= SM count - checked on the host), so nobody waits for an unscheduled CTA;
-          //     a bounded spin turns a protocol bug into a trap instead of a hang.
-          __threadfence();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (tid == 64) {
-            const unsigned need = (unsigned)(tiles_per_batch * n_tiles);
-            atomicAdd(op.gn_counter + b, 1u);
-            unsigned seen, spins = 0;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(op.gn_counter + b) : "memory");
-              if (++spins > (1u << 22)) { printf("ns2vc: GroupNorm barrier timeout (block %d, batch %d, %u of %u)\n", blockIdx.x, b, seen, need); __trap(); }
-            } while (seen < need);
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          // (c) mean / rstd of the groups this tile's columns belong to (biased variance over T x C/G, reference nn.GroupNorm)
-          const int C = op.n_valid, cpg = C / op.gn_G;
-          const int last = (n0 + BN - 1 < C - 1) ? n0 + BN - 1 : C - 1;
-          const int g0 = n0 / cpg, g1 = last / cpg;
-          float* gst = sm_part;                             // [groups][2]; the partial sums are consumed
-          float* aff = sm_part + 64;                        // [2][BN] scale | shift
-          for (int g = g0 + (warp - 2); g <= g1; g += kEpiWarps) {
-            double sum = 0, sq = 0;
-            for (int ii = lane; ii < cpg; ii += 32) {
-              sum += __ldcg(op.stat_sum + (long long)b * C + g * cpg + ii);
-              sq += __ldcg(op.stat_sq + (long long)b * C + g * cpg + ii);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
-            if (lane == 0) {
-              const double inv = 1.0 / ((double)op.T_out * cpg);
-              const double mean = sum * inv;
-              double var = sq * inv - mean * mean;
-              if (var < 0) var = 0;
-              gst[(g - g0) * 2] = (float)mean;
-              gst[(g - g0) * 2 + 1] = rsqrtf((float)var + op.gn_eps);
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          // (d) per-column scale / shift (+ FiLM), same arithmetic as prep_split_kernel
-          {
-            const int col = tid - 64;
-            if (col < BN) {
-              const int c = n0 + col;
-              float ga = 0.f, be = 0.f;
-              if (c < C) {
-                const int g = c / cpg - g0;
-                ga = __ldg(op.gn_gamma + c) * gst[g * 2 + 1];
-                be = __ldg(op.gn_beta + c) - gst[g * 2] * ga;
-                if (op.gn_film) {
-                  const float fs = 1.f + op.gn_film[(long long)b * op.gn_film_ld + c];
-                  const float fb = op.gn_film[(long long)b * op.gn_film_ld + C + c];
-                  ga = ga * fs;
-                  be = be * fs + fb;
-                }
-              }
-              aff[col] = ga;
-              aff[BN + col] = be;
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          // (e) normalise this thread's row of the staged chunk(s) and hand the split to the TMA unit
-#pragma unroll 1
-          for (int cc = cc0; cc < BN / 32; cc += 2) {
-            const int nbase = n0 + cc * 32;
-            if (nbase >= op.n_valid) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 x = *reinterpret_cast<const float4*>(stage_f32_ptr(st, lane, j));
-              v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = fmaf(v[j], aff[cc * 32 + j], aff[BN + cc * 32 + j]);
-              if (op.gn_silu) y = silu_f(y);
-              v[j] = y;
-            }
-            const bool f16 = nbase >= op.f16_col0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 hi, lo;
-              if (f16) split8_f16(v + 8 * j, hi, lo); else split8(v + 8 * j, hi, lo);
-              const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-              *reinterpret_cast<uint4*>(st + 4096 + off) = hi;
-              *reinterpret_cast<uint4*>(st + 6144 + off) = lo;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 1 || lane == 2) {
-              tma_store_3d(&tmo[lane], smem_u32(st) + (lane == 1 ? 4096u : 6144u), nbase, t_warp0, b);
-              bulk_commit();
-            }
-          }
-        }
       }
     }
     // Shared memory must outlive the TMA unit's reads of the staged chunks; the writes themselves are made visible to the
     // dependent grid by grid completion (griddepcontrol.wait on the other side), as in CUTLASS' tma_store_wait.
-    if (op.tma_out && lane < 3) { if (op.tma_out & 4) bulk_wait_all(); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+    if (op.tma_out && lane < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   if (warp == 2 && lane == 0 && tr0) TRACE(6);
@@ -685,12 +654,8 @@ static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, i
 int encode_tmaps(GemmOp& op) {
   // Outputs: the epilogue stages each warp's 32 x 32 chunk in shared memory and hands it to the TMA unit
   // (thread = row straight out of TMEM would cost 32 LSU wavefronts per 128-bit store instruction).
-  static int tma_st = -1;
-  if (tma_st < 0) { const char* e = getenv("NS2VC_TMA_STORE"); tma_st = (e && e[0] == '0') ? 0 : 1; }
   op.tma_out = 0;
-  static int full_wait = -1;                                // NS2VC_TMA_WAIT=full: wait for the bulk stores to land before the CTA exits
-  if (full_wait < 0) { const char* e = getenv("NS2VC_TMA_WAIT"); full_wait = (e && e[0] == 'f') ? 1 : 0; }
-  if (tma_st && !(op.flags & EPI_OUT_NCT)) {
+  if (!(op.flags & EPI_OUT_NCT)) {
     if ((op.flags & EPI_OUT_F32) && op.out && (op.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(op.out) & 15) == 0) {
       int rc = encode_tmap_any(&op.tmap_out[0], op.out, 4, op.n_valid, op.T_out, op.B, op.out_ld, 32, 32, 128);
       if (rc) return rc;
@@ -705,7 +670,6 @@ int encode_tmaps(GemmOp& op) {
       op.tma_out |= 2;
     }
   }
-  if (op.tma_out && full_wait) op.tma_out |= 4;
   for (int i = 0; i < op.nsrc; ++i) {
     const int box_rows = BM;
     int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);
@@ -726,48 +690,48 @@ static int sm_count() {
   return n;
 }
 
-template <int BN_, bool LNF, bool GNA>
+template <int BN_, bool LNF>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF, GNA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
-  // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
   const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (GNA && tiles > grid) { set_error("gemm_tc: EPI_GNAPPLY needs every tile resident (%d tiles, %d SMs)", tiles, grid); return -1; }
-  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF, GNA>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
+  int grid = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
+  dim3 cluster(1, 1, 1);
+  if (op.npre > 0) {
+    // fused prep: one tile per CTA, the N tiles of a row block are one cluster (any number of waves is fine: clusters are independent)
+    if (op.cn != op.N / BN_ || op.cn > kMaxPipCluster) { set_error("gemm_tc: fused prep needs the %d N tiles of a row block in one cluster", op.N / BN_); return -1; }
+    grid = tiles;
+    cluster.x = (unsigned)op.cn;
+  }
+  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, LNF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, cluster, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
-bool gemm_tiles_coresident(const GemmOp& op) {
-  const int bn = (op.flags & EPI_GEGLU) ? 128 : 64;
-  return op.B * ceil_div(op.T_out, BM) * (op.N / bn) <= sm_count();
-}
+int gemm_sm_count() { return sm_count(); }
 
 void plan_gemm(GemmOp& op) {
   // N tile: 64 wide (more, smaller tiles balance better over the persistent CTAs); the GEGLU epilogue pairs
   // value|gate inside a 128-column block and needs BN = 128.
-  // (TMA multicast clusters along N were measured slower in r01 — 4.65 vs 4.54 ms per forward — and were removed.)
   op.bn = (op.flags & EPI_GEGLU) ? 128 : 64;
-  op.cn = 1;
+  op.cn = op.npre > 0 ? op.N / op.bn : 1;
 }
 
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
   const bool lnf = (op.flags & EPI_LNFOLD) != 0;
-  if (op.bn == 128) return lnf ? launch_bn<128, true, false>(op, st) : launch_bn<128, false, false>(op, st);
-  if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
-  if (op.flags & EPI_GNAPPLY) {
-    if (lnf || !(op.flags & EPI_STATS) || !(op.tma_out & 2)) { set_error("gemm_tc: EPI_GNAPPLY needs EPI_STATS and a TMA split output"); return -1; }
-    return launch_bn<64, false, true>(op, st);
+  if (op.bn == 128) {
+    if (op.npre) { set_error("gemm_tc: fused prep is not available for GEGLU tiles"); return -1; }
+    return lnf ? launch_bn<128, true>(op, st) : launch_bn<128, false>(op, st);
   }
-  return lnf ? launch_bn<64, true, false>(op, st) : launch_bn<64, false, false>(op, st);
+  if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
+  return lnf ? launch_bn<64, true>(op, st) : launch_bn<64, false>(op, st);
 }
 
 }  // namespace ns2vc

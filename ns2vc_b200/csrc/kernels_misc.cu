@@ -2,6 +2,7 @@
 // statistics, the timestep/FiLM GEMV, AttentionPooling pieces, and the fused sampler updates.
 // All are coalesced/vectorised; none is worth tensor cores.
 #include "gemm_common.cuh"
+#include "prep_common.cuh"
 #include "launch.cuh"
 #include <cstdarg>
 #include <cstdio>
@@ -130,76 +131,13 @@ int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float
 // row (two 16-byte loads, 16-byte hi + lo stores); rows may be remapped (stride-2 decimation for
 // the downsample convs, nearest-upsample index table).
 // ---------------------------------------------------------------------------------------------
-struct PrepChunk { float v[8]; int t, c0; bool rowok; };
-
-__device__ __forceinline__ void prep_load(const PrepOp& op, int b, int C, int chunks, int i, PrepChunk& k) {
-  const int ck = i % chunks;
-  k.t = i / chunks;
-  k.c0 = ck * 8;
-  const int ts = op.rowmap ? __ldg(op.rowmap + k.t) : k.t * op.row_mul + op.row_add;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) k.v[j] = 0.f;
-  k.rowok = ts >= 0 && ts < op.T_src;
-  if (k.rowok && k.c0 < C) {
-    const int c0 = k.c0;
-    const bool in1 = c0 < op.C1;
-    const float* p = in1 ? op.src1 + ((long long)b * op.T_src + ts) * op.ld1 + c0
-                         : op.src2 + ((long long)b * op.T_src + ts) * op.ld2 + (c0 - op.C1);
-    const int lim = in1 ? op.C1 - c0 : C - c0;             // channels left in this source
-    const int ldx = in1 ? op.ld1 : op.ld2;
-    if (lim >= 8 && ((ldx | (in1 ? c0 : c0 - op.C1)) & 3) == 0) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = c4.x; k.v[5] = c4.y; k.v[6] = c4.z; k.v[7] = c4.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        if (c < C) k.v[j] = (c < op.C1) ? op.src1[((long long)b * op.T_src + ts) * op.ld1 + c]
-                                        : op.src2[((long long)b * op.T_src + ts) * op.ld2 + (c - op.C1)];
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void prep_finish(const PrepOp& op, int b, int C, const float* aff, PrepChunk& k) {
-  const long long orow = (long long)b * op.T_dst + k.t;
-  if (op.raw.hi) {
-    uint4 hi, lo;
-    split8(k.v, hi, lo);
-    *reinterpret_cast<uint4*>(op.raw.hi + orow * op.raw.ld + k.c0) = hi;
-    *reinterpret_cast<uint4*>(op.raw.lo + orow * op.raw.ld + k.c0) = lo;
-  }
-  if (op.mode != PREP_RAW && k.rowok) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = k.c0 + j;
-      if (c < C) {
-        float y = fmaf(k.v[j], aff[c], aff[C + c]);
-        if (op.mode == PREP_AFFINE_SILU) y = silu_f(y);
-        k.v[j] = y;
-      }
-    }
-  }
-  uint4 hi, lo;
-  split8(k.v, hi, lo);
-  *reinterpret_cast<uint4*>(op.out.hi + orow * op.out.ld + k.c0) = hi;
-  *reinterpret_cast<uint4*>(op.out.lo + orow * op.out.ld + k.c0) = lo;
-}
-
 __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   span_begin(op.span);
   pdl_trigger();
   extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
   const int C = op.C1 + op.C2;
-  // GroupNorm gamma / beta are weights: fetch them before griddepcontrol.wait (C <= 4 * 256 per thread slot)
-  float pg[4], pb[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = threadIdx.x + k * 256;
-    const bool ok = op.mode != PREP_RAW && !op.scale && c < C;
-    pg[k] = ok ? __ldg(op.gn.gamma + c) : 0.f;
-    pb[k] = ok ? __ldg(op.gn.beta + c) : 0.f;
-  }
+  float pg[kPrepSlots], pb[kPrepSlots];
+  prep_fetch_norm_weights(op, C, pg, pb);                // weights: before griddepcontrol.wait
   pdl_wait();
   const int b = blockIdx.y;
   const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
@@ -209,58 +147,14 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   // the first chunk's loads are in flight while the block derives the GroupNorm affine
   PrepChunk k0;
   const bool have = i < total;
-  if (have) prep_load(op, b, C, chunks, i, k0);
-  if (op.mode != PREP_RAW) {
-    if (op.scale) {
-      for (int c = threadIdx.x; c < C; c += blockDim.x) { aff[c] = op.scale[(long long)b * C + c]; aff[C + c] = op.shift[(long long)b * C + c]; }
-    } else {
-      // GroupNorm finalise from the per-channel sums the producer epilogues accumulated
-      // (reference nn.GroupNorm: biased variance over T x C/G elements; resnet.py:536,557, transformer_1d.py:134)
-      const GnStats& g = op.gn;
-      const int cpg = C / g.G;
-      float* gmean = aff + 2 * C;                        // [G] mean | [G] rstd
-      for (int grp = threadIdx.x >> 5; grp < g.G; grp += blockDim.x >> 5) {
-        double s = 0, q = 0;
-        for (int ii = threadIdx.x & 31; ii < cpg; ii += 32) {
-          const int c = grp * cpg + ii;
-          s += (c < op.C1) ? g.sum1[(long long)b * op.C1 + c] : g.sum2[(long long)b * op.C2 + (c - op.C1)];
-          q += (c < op.C1) ? g.sq1[(long long)b * op.C1 + c] : g.sq2[(long long)b * op.C2 + (c - op.C1)];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-        if ((threadIdx.x & 31) == 0) {
-          const double inv = 1.0 / ((double)op.T_src * cpg);
-          const double mean = s * inv;
-          double var = q * inv - mean * mean;
-          if (var < 0) var = 0;
-          gmean[grp] = (float)mean;
-          gmean[g.G + grp] = rsqrtf((float)var + g.eps);
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = threadIdx.x + k * 256;
-        if (c >= C) break;
-        const int grp = c / cpg;
-        float ga = pg[k] * gmean[g.G + grp];
-        float be = pb[k] - gmean[grp] * ga;
-        if (g.film) {
-          const float fs = 1.f + g.film[(long long)b * g.film_ld + c];
-          const float fb = g.film[(long long)b * g.film_ld + C + c];
-          ga = ga * fs;
-          be = be * fs + fb;
-        }
-        aff[c] = ga;
-        aff[C + c] = be;
-      }
-    }
-    __syncthreads();
-  }
+  if (have) prep_load_at(op, b, C, i / chunks, i % chunks, k0);
+  float fs[kPrepSlots], fb[kPrepSlots];
+  prep_fetch_film(op, op.gn.film, b, C, fs, fb);
+  prep_affine(op, b, C, aff, pg, pb, fs, fb);
   if (have) prep_finish(op, b, C, aff, k0);
   for (i += stride; i < total; i += stride) {
     PrepChunk k;
-    prep_load(op, b, C, chunks, i, k);
+    prep_load_at(op, b, C, i / chunks, i % chunks, k);
     prep_finish(op, b, C, aff, k);
   }
   span_end(op.span);
@@ -274,8 +168,8 @@ int launch_prep_split(const PrepOp& op, cudaStream_t st) {
   const int cap = (148 * 8 + op.B - 1) / op.B;           // ~8 blocks per SM over the whole grid
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  const size_t smem = (op.mode != PREP_RAW) ? (size_t)(2 * C + 2 * 64) * sizeof(float) : 0;
-  if (smem > 48 * 1024 || (op.mode != PREP_RAW && !op.scale && C > 1024)) { set_error("prep_split: C=%d too large", C); return -1; }
+  const size_t smem = (op.mode != PREP_RAW) ? (size_t)prep_affine_floats(C) * sizeof(float) : 0;
+  if (smem > 48 * 1024 || (op.mode != PREP_RAW && !op.scale && (C > kPrepSlots * 256 || op.gn.G > 64))) { set_error("prep_split: C=%d too large", C); return -1; }
   cudaError_t e = launch_k(prep_split_kernel, dim3(bx, op.B), dim3(256), smem, st, op);
   if (e != cudaSuccess) { set_error("prep_split launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
@@ -503,7 +397,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinOp op) {
     const float bv = op.bias ? op.bias[n] : 0.f;
     for (int r = 0; r < rows; ++r) {
       float v = acc[r] + bv;
-      if (op.add) v += op.add[(long long)(m0 + r) * op.add_ld + n];
+      if (op.add) v += op.add[(long long)(op.add_rows > 0 ? (m0 + r) % op.add_rows : (m0 + r)) * op.add_ld + n];
       if (op.out_silu) v = v / (1.0f + expf(-v));
       op.out[(long long)(m0 + r) * op.out_ld + n] = v;
     }
@@ -603,13 +497,15 @@ __device__ __forceinline__ float x0_round_trip(float x, float o, float alpha, fl
 
 __global__ void __launch_bounds__(256) dpm_step_kernel(const float* __restrict__ x, const float* __restrict__ o,
                                                        const float* __restrict__ mp, DpmStepCoef c,
-                                                       float* __restrict__ mc, float* __restrict__ xn, size_t n) {
+                                                       float* __restrict__ mc, float* __restrict__ xn, size_t n, int* nan_flag) {
   pdl_trigger();
   pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
   for (; i < n; i += stride) {
     const float xv = x[i];
+    bad |= (xv != xv);                                     // the reference asserts on NaN in the denoiser input every call (model.py:404)
     const float m0 = x0_round_trip(xv, o[i], c.alpha_s, c.sigma_s);
     mc[i] = m0;
     if (c.order == 0) continue;
@@ -620,12 +516,13 @@ __global__ void __launch_bounds__(256) dpm_step_kernel(const float* __restrict__
     }
     xn[i] = r;
   }
+  if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 int launch_dpm_step(const float* x, const float* unet_out, const float* m_prev, const DpmStepCoef& c, float* m_cur,
-                    float* x_next, size_t n, cudaStream_t st) {
+                    float* x_next, size_t n, int* nan_flag, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(dpm_step_kernel, dim3(blocks), dim3(256), 0, st, x, unet_out, m_prev, c, m_cur, x_next, n);
+  launch_k(dpm_step_kernel, dim3(blocks), dim3(256), 0, st, x, unet_out, m_prev, c, m_cur, x_next, n, nan_flag);
   NS_LAUNCH_CHECK();
   return 0;
 }
@@ -634,13 +531,15 @@ __global__ void __launch_bounds__(256) unipc_step_kernel(const float* __restrict
                                                          const float* __restrict__ o, const float* __restrict__ m0p,
                                                          const float* __restrict__ m1p, UniPcStepCoef c,
                                                          float* __restrict__ mt_out, float* __restrict__ xt_out,
-                                                         float* __restrict__ xpred_out, size_t n) {
+                                                         float* __restrict__ xpred_out, size_t n, int* nan_flag) {
   pdl_trigger();
   pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
   for (; i < n; i += stride) {
     const float xev = xe[i];
+    bad |= (xev != xev);                                   // NaN guard of the denoiser input (model.py:404)
     const float mt = x0_round_trip(xev, o[i], c.alpha_t, c.sigma_t);
     mt_out[i] = mt;
     float xt = xev;
@@ -670,13 +569,14 @@ __global__ void __launch_bounds__(256) unipc_step_kernel(const float* __restrict
       xpred_out[i] = xpred;
     }
   }
+  if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 int launch_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0,
                       const float* m1, const UniPcStepCoef& c, float* m_t, float* x_t, float* x_pred, size_t n,
-                      cudaStream_t st) {
+                      int* nan_flag, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(unipc_step_kernel, dim3(blocks), dim3(256), 0, st, x_prev, x_eval, unet_out, m0, m1, c, m_t, x_t, x_pred, n);
+  launch_k(unipc_step_kernel, dim3(blocks), dim3(256), 0, st, x_prev, x_eval, unet_out, m0, m1, c, m_t, x_t, x_pred, n, nan_flag);
   NS_LAUNCH_CHECK();
   return 0;
 }

@@ -11,7 +11,9 @@ tracing the first model call), so ``model.py:621-686`` benefits unchanged.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import hashlib
 import os
 from typing import Optional
 
@@ -21,14 +23,33 @@ from . import _lib, coefs
 from .unet import UNet1DConditionModel, trace_calls
 
 
+_HOIST = os.environ.get("NS2VC_HOIST", "1") != "0"     # diagnostic: 0 = timestep path recomputed inside every forward
+
+
+def schedule_signature(ns) -> tuple:
+    """Content key of a noise schedule.  The reference builds a NEW NoiseScheduleVP inside every ``sample()``
+    (model.py:621-622, 655-656), so object identity is useless as a cache key (and a recycled ``id()`` could
+    alias a different beta table); two schedules with the same knots share tables and captured graphs."""
+    if getattr(ns, "schedule", None) == "discrete":
+        la = ns.log_alpha_array.detach().to("cpu", torch.float32).contiguous()
+        return ("discrete", int(ns.total_N), hashlib.sha1(la.numpy().tobytes()).hexdigest())
+    return (str(getattr(ns, "schedule", "?")), float(getattr(ns, "beta_0", 0.0)), float(getattr(ns, "beta_1", 0.0)), int(getattr(ns, "total_N", 0)))
+
+
 class DenoiserSession:
     """One utterance-batch shape (B, T, S) on one GPU: UNet engine, static input buffers, prepared
-    conditioning and (optionally) the whole sampling loop captured as one CUDA graph.
+    conditioning and the whole sampling loop captured as one CUDA graph.
 
-    The C calls are stream-ordered and allocation-free, so the N-step loop (prepare_cond + N x (UNet
-    forward + fused sampler step), ~335 kernels per step linked by programmatic dependent launch) is
-    captured once per (sampler, steps) and replayed; new inputs are copied into the static buffers.
-    ``NS2VC_GRAPH=0`` disables the capture (eager launches)."""
+    The C calls are stream-ordered and allocation-free, so the N-step loop (prepare_cond + the timestep
+    table of all N evaluation times + N x (UNet forward + fused sampler step), every kernel linked to its
+    predecessor by programmatic dependent launch) is captured once per (sampler, time grid, schedule) and
+    replayed; new inputs are copied into the static buffers.  ``NS2VC_GRAPH=0`` disables the capture.
+
+    The reference asserts ``not isnan(x)`` on the host before every denoiser call (model.py:404: one
+    device->host sync per step).  Here the sampler-step kernel accumulates a device flag and the host checks
+    it ONCE after the run, raising the same ``AssertionError``."""
+
+    MAX_GRAPHS = 4                                           # LRU bound of captured loops per session
 
     def __init__(self, unet: UNet1DConditionModel, content_BCT: Optional[torch.Tensor], prompt_BSC: torch.Tensor,
                  prompt_mask: Optional[torch.Tensor], T: Optional[int] = None):
@@ -54,24 +75,12 @@ class DenoiserSession:
         self.h = unet.engine(self.dev)
         self.Cl, self.Co = unet.latent_channels, unet.cfg.out_channels
         self.x_in = torch.empty((self.B, self.Cl, self.T), **f32)
-        # Lanes: the utterances of a batch are independent, and every kernel of the step is a short
-        # dependent-latency chain that leaves most SMs idle, so the batch is cut into sub-batches whose
-        # whole sampling loops run concurrently on separate streams (own workspace + launch program each,
-        # shared packed weights).  Off by default: GEMM CTAs own a whole SM (198 KB smem), so lanes do not overlap yet.
-        want = int(os.environ.get("NS2VC_LANES", "1"))   # measured r01 (cfg2): 1 lane 1678, 2 lanes 1608, 4 lanes 1595, 8 lanes 1540 steps/s
-        n_lanes = max(1, min(want, self.B))
-        while self.B % n_lanes:
-            n_lanes -= 1
-        per = self.B // n_lanes
-        self.lanes = []
-        for g in range(n_lanes):
-            n = C.c_size_t()
-            _lib.check(self.L.ns2vc_unet_workspace_bytes(self.h, per, self.T, self.S, C.byref(n)))
-            self.lanes.append(dict(sl=slice(g * per, (g + 1) * per), B=per,
-                                   ws=torch.empty(int(n.value), dtype=torch.uint8, device=self.dev),
-                                   stream=torch.cuda.Stream(device=self.dev) if n_lanes > 1 else None))
-        self.ws = self.lanes[0]["ws"]
-        self._graphs = {}
+        self.first_out = torch.empty((self.B, self.Co, self.T), **f32)   # step-0 model output handed in by the drop-in samplers
+        self.nan_flag = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        n = C.c_size_t()
+        _lib.check(self.L.ns2vc_unet_workspace_bytes(self.h, self.B, self.T, self.S, C.byref(n)))
+        self.ws = torch.empty(int(n.value), dtype=torch.uint8, device=self.dev)
+        self._graphs = collections.OrderedDict()
         self._wsig = unet._wsig
         self.set_cond(content_BCT, prompt_BSC, prompt_mask)
 
@@ -89,66 +98,68 @@ class DenoiserSession:
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def _prepare_lane(self, lane):
-        sl = lane["sl"]
+    def prepare(self):
         with torch.cuda.device(self.dev):
             _lib.check(self.L.ns2vc_unet_prepare_cond(
-                self.h, self.content[sl].data_ptr() if self.content is not None else None,
-                (self.Cc * self.T) if self.content is not None else 0, self.prompt[sl].data_ptr(),
-                self.mask[sl].data_ptr() if self.mask is not None else None, lane["B"], self.T, self.S, lane["ws"].data_ptr(), self._stream()))
-
-    def _forward_lane(self, lane, x, t, out):
-        with torch.cuda.device(self.dev):
-            _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
-                                                 lane["B"], self.T, self.S, lane["ws"].data_ptr(), self._stream()))
-
-    def prepare(self):
-        for lane in self.lanes:
-            self._prepare_lane(lane)
+                self.h, self.content.data_ptr() if self.content is not None else None,
+                (self.Cc * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
+                self.mask.data_ptr() if self.mask is not None else None, self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
         self._prepared = True
 
-    def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor):
-        """x [B,Cl,T] fp32 contiguous, t [B] fp32, out [B,Co,T] fp32 — all on the session device."""
+    def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor, film_rows: Optional[torch.Tensor] = None):
+        """x [B,Cl,T] fp32 contiguous, t [B] fp32 (or B precomputed FiLM rows), out [B,Co,T] fp32 — all on the session device."""
         if not self._prepared:
             self.prepare()
-        for lane in self.lanes:
-            sl = lane["sl"]
-            self._forward_lane(lane, x[sl], t[sl], out[sl])
+        with torch.cuda.device(self.dev):
+            if film_rows is not None:
+                _lib.check(self.L.ns2vc_unet_forward_film(self.h, x.data_ptr(), self.Cl * self.T, film_rows.data_ptr(), out.data_ptr(),
+                                                          self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+            else:
+                _lib.check(self.L.ns2vc_unet_forward(self.h, x.data_ptr(), self.Cl * self.T, t.data_ptr(), out.data_ptr(),
+                                                     self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
+
+    def time_table(self, tvals: torch.Tensor, table: torch.Tensor):
+        """FiLM rows of every evaluation time of a run (tvals [steps, B] fp32) into ``table`` (needs prepare())."""
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.ns2vc_unet_time_table(self.h, tvals.data_ptr(), tvals.numel(), table.data_ptr(), self.B, self.T, self.S,
+                                                    self.ws.data_ptr(), self._stream()))
 
     # ------------------------------------------------------------------ loop bodies (eager or under capture)
-    def _lane_dpm(self, lane, table, tvals, first_out, result):
-        sl = lane["sl"]
-        x = self.x_in[sl].clone()
+    def _film(self, ent, k):
+        fw = ent["film_width"]
+        return ent["table"][k * self.B * fw:(k + 1) * self.B * fw]
+
+    def _body_dpm(self, ent, use_first):
+        x = self.x_in.clone()
         n = x.numel()
         x_next, out = torch.empty_like(x), torch.empty_like(x)
         m_a, m_b = torch.empty_like(x), torch.empty_like(x)
         stream = self._stream()
-        for k, st in enumerate(table):
-            if k == 0 and first_out is not None:
-                out.copy_(first_out[sl])
+        for k, st in enumerate(ent["steps"]):
+            if k == 0 and use_first:
+                out.copy_(self.first_out)
             else:
-                self._forward_lane(lane, x, tvals[k][sl], out)
+                self.forward(x, ent["tvals"][k], out, film_rows=self._film(ent, k) if _HOIST else None)
             c = _lib.DpmCoef(st.alpha_s, st.sigma_s, st.c_x, st.c_m, st.c_d, st.inv_r0, st.order)
             with torch.cuda.device(self.dev):
                 _lib.check(self.L.ns2vc_dpm_step(x.data_ptr(), out.data_ptr(), m_b.data_ptr(), C.byref(c), m_a.data_ptr(),
-                                                 x_next.data_ptr(), n, stream))
+                                                 x_next.data_ptr(), n, self.nan_flag.data_ptr(), stream))
             x, x_next = x_next, x
             m_a, m_b = m_b, m_a
-        result[sl].copy_(x)
+        return x
 
-    def _lane_unipc(self, lane, table, tvals, first_out, result):
-        sl = lane["sl"]
-        x_prev = self.x_in[sl]                             # x at the previous time point (corrector base); never written
+    def _body_unipc(self, ent, use_first):
+        x_prev = self.x_in                                 # x at the previous time point (corrector base); never written
         x_eval = x_prev                                    # where the model is evaluated
         n = x_prev.numel()
         out = torch.empty_like(x_prev)
         m0 = m1 = None
         stream = self._stream()
-        for k, st in enumerate(table):
-            if k == 0 and first_out is not None:
-                out.copy_(first_out[sl])
+        for k, st in enumerate(ent["steps"]):
+            if k == 0 and use_first:
+                out.copy_(self.first_out)
             else:
-                self._forward_lane(lane, x_eval, tvals[k][sl], out)
+                self.forward(x_eval, ent["tvals"][k], out, film_rows=self._film(ent, k) if _HOIST else None)
             m_t = torch.empty_like(x_prev)
             x_t = torch.empty_like(x_prev) if st.corr_order > 0 else None
             x_pred = torch.empty_like(x_prev)
@@ -158,32 +169,25 @@ class DenoiserSession:
                 _lib.check(self.L.ns2vc_unipc_step(
                     x_prev.data_ptr(), x_eval.data_ptr(), out.data_ptr(), m0.data_ptr() if m0 is not None else None,
                     m1.data_ptr() if m1 is not None else None, C.byref(c), m_t.data_ptr(),
-                    x_t.data_ptr() if x_t is not None else None, x_pred.data_ptr(), n, stream))
+                    x_t.data_ptr() if x_t is not None else None, x_pred.data_ptr(), n, self.nan_flag.data_ptr(), stream))
             # history m1 <- m0 <- m_t ; corrector base <- corrected x_t (x_eval itself at k = 0)
             m1, m0 = m0, m_t
             x_prev = x_t if x_t is not None else x_eval
             x_eval = x_pred
-        result[sl].copy_(x_eval)
+        return x_eval
 
-    def _loop(self, kind, table, tvals, first_out=None):
-        """prepare_cond + the N-step loop of every lane; lanes run concurrently on their own streams."""
-        body = self._lane_dpm if kind == "dpm" else self._lane_unipc
-        result = torch.empty_like(self.x_in)
-        cur = torch.cuda.current_stream(self.dev)
-        for lane in self.lanes:
-            if lane["stream"] is None:
-                self._prepare_lane(lane)
-                body(lane, table, tvals, first_out, result)
-            else:
-                lane["stream"].wait_stream(cur)
-                with torch.cuda.stream(lane["stream"]):
-                    self._prepare_lane(lane)
-                    body(lane, table, tvals, first_out, result)
-        for lane in self.lanes:
-            if lane["stream"] is not None:
-                cur.wait_stream(lane["stream"])
-        self._prepared = True
-        return result
+    def _loop(self, kind, ent, use_first):
+        """prepare_cond + timestep table + the N-step loop; returns the final latents (a fresh tensor)."""
+        self.nan_flag.zero_()
+        self.prepare()
+        self.time_table(ent["tvals"], ent["table"])
+        res = self._body_dpm(ent, use_first) if kind == "dpm" else self._body_unipc(ent, use_first)
+        return res.clone()
+
+    def _check_nan(self):
+        if int(self.nan_flag.item()) != 0:
+            # same exception type as the reference's per-call guard (model.py:404)
+            raise AssertionError("NaN in the denoiser input during the fused sampling run (reference model.py:404)")
 
     def _run(self, kind, x_T, ns, ts, first_out, extra):
         assert self.Cl == self.Co, "x_start parameterisation needs out_channels == latent channels"
@@ -193,36 +197,49 @@ class DenoiserSession:
             self._wsig = self.unet._wsig
             self._prepared = False
         self.x_in.copy_(x_T, non_blocking=True)
-        key = (kind, tuple(float(v) for v in ts), extra, id(ns))
+        use_first = first_out is not None
+        if use_first:
+            self.first_out.copy_(first_out, non_blocking=True)
+        key = (kind, tuple(float(v) for v in ts), extra, schedule_signature(ns), use_first)
         use_graph = os.environ.get("NS2VC_GRAPH", "1") != "0"
         ent = self._graphs.get(key)
         if ent is None:
-            table = coefs.dpmpp_2m_table(ns, ts, extra) if kind == "dpm" else coefs.unipc_bh2_table(ns, ts, extra)
-            tvals = torch.tensor([[st.t_input] * self.B for st in table], dtype=torch.float32).to(self.dev)
-            ent = {"table": table, "tvals": tvals, "graph": None, "out": None, "warm": False}
+            steps = coefs.dpmpp_2m_table(ns, ts, extra) if kind == "dpm" else coefs.unipc_bh2_table(ns, ts, extra)
+            tvals = torch.tensor([[st.t_input] * self.B for st in steps], dtype=torch.float32).to(self.dev)
+            nrows = tvals.numel()
+            table = torch.empty(int(self.L.ns2vc_unet_time_table_floats(self.h, nrows)), dtype=torch.float32, device=self.dev)
+            ent = {"steps": steps, "tvals": tvals, "table": table, "film_width": int(self.L.ns2vc_unet_film_width(self.h)),
+                   "graph": None, "out": None, "warm": False}
             self._graphs[key] = ent
+            while len(self._graphs) > self.MAX_GRAPHS:     # LRU: the oldest captured loop (graph + tables) is dropped
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
         if not use_graph:
-            return self._loop(kind, ent["table"], ent["tvals"], first_out)
-        if ent["graph"] is None:
-            if not ent["warm"]:
-                # first run eagerly: builds the launch programs, sets kernel attributes, warms the allocator
-                res = self._loop(kind, ent["table"], ent["tvals"], first_out)
-                ent["warm"] = True
-                return res
-            torch.cuda.synchronize(self.dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ent["out"] = self._loop(kind, ent["table"], ent["tvals"], None)
-            ent["graph"] = g
-        ent["graph"].replay()
-        self._prepared = True
-        return ent["out"].clone()
+            res = self._loop(kind, ent, use_first)
+        elif ent["graph"] is None and not ent["warm"]:
+            # first run eagerly: builds the launch program, sets kernel attributes, warms the allocator
+            res = self._loop(kind, ent, use_first)
+            ent["warm"] = True
+        else:
+            if ent["graph"] is None:
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["out"] = self._loop(kind, ent, use_first)
+                ent["graph"] = g
+            ent["graph"].replay()
+            self._prepared = True
+            res = ent["out"].clone()
+        self._check_nan()
+        return res
 
     # ------------------------------------------------------------------ public samplers
     def sample_dpmpp_2m(self, x_T: torch.Tensor, ns, ts: torch.Tensor, lower_order_final: bool = True,
                         first_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """DPM-Solver++ multistep order 2 over time points ``ts`` (N+1 values), x_start model.
-        Equivalent to reference DPM_Solver.sample(method='multistep', order=2) (dpm_solver.py:1171-1213)."""
+        Equivalent to reference DPM_Solver.sample(method='multistep', order=2) (dpm_solver.py:1171-1213).
+        ``first_out``: the model output at ts[0] if the caller already evaluated it (saves one forward)."""
         return self._run("dpm", x_T, ns, ts, first_out, bool(lower_order_final))
 
     def sample_unipc(self, x_T: torch.Tensor, ns, ts: torch.Tensor, variant: str = "bh2",
@@ -291,27 +308,26 @@ def _session_from_record(r) -> DenoiserSession:
     return get_session(u, content, r.ehs, r.mask, T=r.sample.shape[2])
 
 
-def try_fused_dpm(solver, x, steps, skip_type, t_T, t_0):
+def _try_fused(solver, x, steps, skip_type, t_T, t_0, kind):
+    """(latents, None) when the fused path ran; (None, first_noise) when the closure is not ours — first_noise is the
+    model output of the solver's first evaluation (already paid for by the trace), or None if nothing was evaluated."""
     if not (_fast_path_enabled() and x.is_cuda and skip_type in ("time_uniform", "time_quadratic", "logSNR")):
-        return None
+        return None, None
     ns = solver.noise_schedule
     ts = solver.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device="cpu")
     with torch.no_grad():
-        rec, _ = _trace_first_call(solver, x, ts[0].to(x.device))
+        rec, noise = _trace_first_call(solver, x, ts[0].to(x.device))
         if rec is None:
-            return None
+            return None, noise
         sess = _session_from_record(rec)
-        return sess.sample_dpmpp_2m(x, ns, ts, lower_order_final=True, first_out=rec.output)
+        if kind == "dpm":
+            return sess.sample_dpmpp_2m(x, ns, ts, lower_order_final=True, first_out=rec.output), None
+        return sess.sample_unipc(x, ns, ts, variant=solver.variant, first_out=rec.output), None
+
+
+def try_fused_dpm(solver, x, steps, skip_type, t_T, t_0):
+    return _try_fused(solver, x, steps, skip_type, t_T, t_0, "dpm")
 
 
 def try_fused_unipc(solver, x, steps, skip_type, t_T, t_0):
-    if not (_fast_path_enabled() and x.is_cuda and skip_type in ("time_uniform", "time_quadratic", "logSNR")):
-        return None
-    ns = solver.noise_schedule
-    ts = solver.get_time_steps(skip_type=skip_type, t_T=t_T, t_0=t_0, N=steps, device="cpu")
-    with torch.no_grad():
-        rec, _ = _trace_first_call(solver, x, ts[0].to(x.device))
-        if rec is None:
-            return None
-        sess = _session_from_record(rec)
-        return sess.sample_unipc(x, ns, ts, variant=solver.variant, first_out=rec.output)
+    return _try_fused(solver, x, steps, skip_type, t_T, t_0, "unipc")

@@ -11,7 +11,7 @@ def chain(k):
     s = torch.cuda.current_stream().cuda_stream
     a, b = x, y
     for _ in range(k):
-        _lib.check(L.ns2vc_dpm_step(a.data_ptr(), o.data_ptr(), m.data_ptr(), C.byref(c), m.data_ptr(), b.data_ptr(), n, s))
+        _lib.check(L.ns2vc_dpm_step(a.data_ptr(), o.data_ptr(), m.data_ptr(), C.byref(c), m.data_ptr(), b.data_ptr(), n, None, s))
         a, b = b, a
 K = 500
 chain(K); torch.cuda.synchronize()

@@ -20,14 +20,14 @@ for _ in range(3): sess.forward(x, t, o)
 torch.cuda.synchronize()
 L = _lib.lib(); h = unet.engine(torch.device("cuda", 0))
 n = 200
-buf = torch.zeros(n * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(n * 32, dtype=torch.int64, device="cuda")
 _lib.check(L.ns2vc_unet_set_trace(h, buf.data_ptr(), n))
 sess.forward(x, t, o); torch.cuda.synchronize()
 _lib.check(L.ns2vc_unet_set_trace(h, None, 0))
-full = buf.view(n, 16).cpu()
+full = buf.view(n, 32).cpu()
 tr = full[:, :8]
 keep = tr[:, 0] > 0
-tr = tr[keep]; ep = full[keep][:, 8:]
+tr = tr[keep]; ep = full[keep][:, 8:16]; pp = full[keep][:, 16:22]
 t00 = int(tr[0, 0])
 names = ["entry", "prologue_done", "pdl_wait_done", "first_full", "mma_issued", "acc_ready", "epi_done", "exit"]
 print("idx start_us " + " ".join(f"d_{n}" for n in names[1:]) + " gap_from_prev_exit")
@@ -55,3 +55,13 @@ for i in range(ep.shape[0]):
     for j in range(8):
         if e[j]: acc[j] += d[j]; cnt[j] += 1
 print("mean " + " ".join(f"{(acc[j] / cnt[j] if cnt[j] else 0):12.0f}" for j in range(1, 8)))
+
+pn = ["wait_done", "loads_issued", "affine_ready", "rows_stored", "preps_done", "published"]
+print("fused prep (us since kernel entry; thread 0 of CTA 0), then first_full / acc_ready / exit of the same launch:")
+print("idx " + " ".join(f"{n:>13s}" for n in pn) + "    first_full    acc_ready         exit")
+k = 0
+for i in range(tr.shape[0]):
+    if int(pp[i, 0]) == 0: continue
+    r0 = int(tr[i, 0])
+    if k < 70: print(f"{i:3d} " + " ".join(f"{(int(v) - r0) / 1e3:13.2f}" for v in pp[i]) + " ".join(f"{(int(tr[i, j]) - r0) / 1e3:13.2f}" for j in (3, 5, 7)))
+    k += 1

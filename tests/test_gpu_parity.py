@@ -152,7 +152,7 @@ def test_dpm_step_kernel_bit_exact():
     for order in (0, 1, 2):
         c = _lib.DpmCoef(0.37, 0.929, 0.9571, -0.0123, -0.00615, 1.0231, order)
         mc, xn = torch.empty_like(x), torch.zeros_like(x)
-        _lib.check(L.ns2vc_dpm_step(x.data_ptr(), o.data_ptr(), mp.data_ptr(), C.byref(c), mc.data_ptr(), xn.data_ptr(), x.numel(), None))
+        _lib.check(L.ns2vc_dpm_step(x.data_ptr(), o.data_ptr(), mp.data_ptr(), C.byref(c), mc.data_ptr(), xn.data_ptr(), x.numel(), None, None))
         torch.cuda.synchronize()
         m0 = _rt(x, o, f(c.alpha_s), f(c.sigma_s))
         assert torch.equal(mc, m0)
@@ -172,7 +172,7 @@ def test_unipc_step_kernel_bit_exact():
         c = _lib.UniPcCoef(0.41, 0.912, 0.961, -0.0131, -0.0127, -1.07, 0.4931, 0.5069, corr, 0.957, -0.0141, -0.0139, -0.97, pred)
         mt, xt, xq = torch.empty_like(xp), torch.empty_like(xp), torch.empty_like(xp)
         _lib.check(L.ns2vc_unipc_step(xp.data_ptr(), xe.data_ptr(), o.data_ptr(), m0.data_ptr(), m1.data_ptr(), C.byref(c),
-                                      mt.data_ptr(), xt.data_ptr(), xq.data_ptr(), xp.numel(), None))
+                                      mt.data_ptr(), xt.data_ptr(), xq.data_ptr(), xp.numel(), None, None))
         torch.cuda.synchronize()
         mt_ref = _rt(xe, o, f(c.alpha_t), f(c.sigma_t))
         assert torch.equal(mt, mt_ref)
