@@ -111,6 +111,18 @@ enum EpiFlags : int {
   EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
 };
 
+// One panel segment of a panel-mode GEMM: `ncb` 64-channel blocks of one raw split source
+constexpr int kMaxXSeg = 4;
+struct XSeg {
+  int src;            // index into GemmOp::src
+  int c0;             // first channel within the source (multiple of 64)
+  int ncb;            // 64-channel blocks
+  int ntap;           // 3: k=3 conv (panel rows t0-1 .. t0+128), 1: 1x1 operand (rows t0 .. t0+127)
+  int kb_tap[3];      // packed-weight k-block of tap j for channel block 0 (block cb: + cb)
+  int xf;             // 1: normalise the panel in shared memory, 0: raw operand (1x1 shortcut)
+  int aff_c0;         // channel of the affine table that corresponds to c0
+};
+
 struct GemmOp {
   TMap tmap[2 * kMaxSrc];      // [2*i] = hi, [2*i+1] = lo of src[i]; box = {64 ch, 128 rows, 1}
   SplitBuf src[kMaxSrc];
@@ -149,21 +161,22 @@ struct GemmOp {
   TMap tmap_out[3];            // TMA store maps: fp32 out (box 32 cols x 32 rows, SWIZZLE_128B), out_hi, out_lo (SWIZZLE_64B)
   int tma_out;                 // bit 0: fp32 output goes through tmap_out[0]; bit 1: split output through tmap_out[1..2]
   int bn;                      // N tile (64 / 128), chosen by plan_gemm()
-  // Prep fused into the GEMM's prologue ("PIP"): the GroupNorm(+FiLM)(+SiLU) / decimation / upsample pass that turns the
-  // producer's fp32 activations into this GEMM's split A operand runs INSIDE this kernel instead of as a launch of its own.
-  // The cn = N / bn CTAs that share a 128-row block form a thread-block cluster; each converts its share of the channels
-  // for rows [t0 + pre_tap_lo, t0 + 127 + pre_tap_hi], the cluster barrier publishes them, then the tile is a normal TMA GEMM.
-  int npre;                    // 0: the A operand was prepared by an earlier launch
-  const PrepOp* pre;           // [npre] descriptors in device memory (the kernel parameter block stays small: its size is launch latency)
-  const float* pre_film[2];    // FiLM rows of each fused prep (nullptr: none) - kept here because they change per forward
-  int pre_tap_lo[2], pre_tap_hi[2];
-  int cn;                      // cluster size along N (PIP only; 1 otherwise)
+  // Panel mode (xmode = 1): the GroupNorm(+FiLM)(+SiLU) of the A operand is applied INSIDE this kernel (reference
+  // resnet.py:597-612, transformer_1d.py:256-262).  The A sources are the RAW bf16 hi/lo splits the producers' epilogues wrote.
+  // Per 64-channel block the TMA unit drops ONE panel of 130 rows (t0-1 .. t0+128; 128 rows for a 1x1 operand) of each split
+  // into shared memory; the eight epilogue warps (idle during the main loop: one tile per CTA) normalise the panel in place
+  // (x = hi + lo, y = silu(x * scale[b,c] + shift[b,c]), re-split; rows outside [0, T) stay zero = the conv's zero padding);
+  // the three taps of a k=3 conv are three row-shifted views of the same panel (descriptor start address + 128 B per row:
+  // the 128B swizzle is a function of the shared-memory address bits), so a conv reads and normalises each activation once.
+  int xmode;
+  int nxs;
+  XSeg xs[kMaxXSeg];
+  const PrepOp* pre;           // GroupNorm parameters of the normalised segments (device memory; only the affine part is used)
+  const float* pre_film;       // FiLM rows read by that affine (nullptr: none) - kept here because they change per forward
 };
-// Choose the N tile for op (fills op.bn / op.cn); must precede encode_tmaps().
+// Choose the N tile for op (fills op.bn); must precede encode_tmaps().
 void plan_gemm(GemmOp& op);
-// Largest cluster the fused-prep path may use (N tiles of one row block)
-constexpr int kMaxPipCluster = 8;
-constexpr int kPrepFuseMaxC = 1280;   // channels a fused prep may normalise (affine slots per thread x threads of the GEMM CTA)
+constexpr int kXfMaxC = 1024;         // channels a panel-mode GEMM may normalise (affine slots per thread x the 256 transform threads)
 int gemm_sm_count();
 
 // Launchers (each returns 0 or a negative error code; all stream-ordered, no host sync).

@@ -137,7 +137,7 @@ struct ns2vc_unet {
   std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
-  bool pip = true;           // GroupNorm / resample prep passes fused into the consuming GEMM's prologue (NS2VC_PIP=0: separate prep launches)
+  bool xf = true;            // GroupNorm(+FiLM)(+SiLU) of the conv / proj_in inputs applied inside the GEMM (panel mode; NS2VC_XF=0: prep launches)
   bool merge_ff = true;      // ff.net.2 + proj_out as one GEMM (NS2VC_MERGE_FF=0: two launches)
   float* film_base = nullptr;        // FiLM rows of the active program (workspace), and the caller-supplied replacement for one forward
   const float* film_ext = nullptr;
@@ -546,54 +546,38 @@ struct Builder {
     const int i = add_src(g, s);
     for (int j = 0; j < 3; ++j) seg(g, i, 0, s.C, j - 1);
   }
-  // Prep passes emitted since the last GEMM.  emit_gemm() folds them into the GEMM's prologue when the fused path applies
-  // (tcgen05 backend, <= 8 N tiles, <= 2 preps, every prep output is an A source of this GEMM); otherwise they are flushed
-  // as launches of their own, in order.
-  std::vector<Launch> pending;
-  void flush_pending() { for (auto& l : pending) out->push_back(l); pending.clear(); }
   void emit_gemm(GemmOp& g, const PackedB& w, int patch = 0) {
     Launch l; l.kind = Launch::GEMM; l.patch = patch;
-    bool fuse = h->pip && !h->simt && !pending.empty() && pending.size() <= 2 && !(g.flags & EPI_GEGLU) && w.Npad / 64 <= kMaxPipCluster;
-    if (fuse) {
-      for (size_t i = 0; i < pending.size() && fuse; ++i) {
-        const PrepOp& p = pending[i].prep;
-        if (pending[i].kind != Launch::PREP || pending[i].patch != 0) { fuse = false; break; }
-        if (p.mode != PREP_RAW && !p.scale && ((p.C1 + p.C2) > kPrepFuseMaxC || p.gn.G > 64)) { fuse = false; break; }
-        int lo = 1 << 30, hi = -(1 << 30);
-        for (int si = 0; si < g.nseg; ++si) {
-          const SplitBuf& sb = g.src[g.seg[si].src];
-          if (sb.hi == p.out.hi || (p.raw.hi && sb.hi == p.raw.hi)) { lo = std::min(lo, g.seg[si].tap); hi = std::max(hi, g.seg[si].tap); }
-        }
-        // a prep whose outputs this GEMM does not read at all (the shortcut operand is read by conv2) rides along with tap range 0
-        if (lo > hi) { fuse = false; break; }
-        g.pre_film[i] = p.gn.film; g.pre_tap_lo[i] = lo; g.pre_tap_hi[i] = hi;
-        // the prep's rows are indexed by the tile's output rows (the odd-row copy of a stride-2 conv may be one row shorter)
-        if (p.T_dst > g.T_out || p.B != g.B) { fuse = false; break; }
-      }
-      if (fuse) g.npre = (int)pending.size();
-    }
-    if (fuse) {
-      // the prep descriptors live in the workspace (device memory): the kernel parameter block stays small
-      PrepOp* pd = ar.get<PrepOp>(2);
-      g.pre = pd;
-      if (!dry) {
-        PrepOp tmp[2];
-        for (int i = 0; i < g.npre; ++i) { tmp[i] = pending[i].prep; tmp[i].gn.film = nullptr; }
-        if (cudaMemcpy(pd, tmp, sizeof(PrepOp) * g.npre, cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
-      }
-      pending.clear();
-    } else { g.npre = 0; g.pre = nullptr; flush_pending(); }
     if (!dry) {
       if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
       plan_gemm(g);
       if (!h->simt) { int rc = encode_tmaps(g); if (rc) err = rc; }
     }
     l.gemm = g;
-    for (int i = 0; i < g.npre; ++i) if (g.pre_film[i]) l.reads_film = 1;
-    if (g.flags & EPI_ROWBIAS) l.reads_film = 1;
+    if (g.pre_film || (g.flags & EPI_ROWBIAS)) l.reads_film = 1;
     out->push_back(l);
   }
-  void push(const Launch& l) { flush_pending(); out->push_back(l); }
+  // ---- panel mode (GemmOp::xmode): raw split sources normalised inside the GEMM
+  void xseg(GemmOp& g, int src, int c0, int nch, int ntap, int kb0, int kb_stride, int xf, int aff_c0) {
+    XSeg& x = g.xs[g.nxs++];
+    x.src = src; x.c0 = c0; x.ncb = nkb_of(nch); x.ntap = ntap; x.xf = xf; x.aff_c0 = aff_c0;
+    for (int j = 0; j < 3; ++j) x.kb_tap[j] = kb0 + j * kb_stride;
+    g.nkb_total += x.ncb * ntap;
+    g.xmode = 1;
+  }
+  // GroupNorm parameters of a panel-mode GEMM (statistics of up to two concatenated producers), parked in the workspace
+  const PrepOp* affine_desc(const double* st1, int C1, const double* st2, int C2, int Tn, int mode, float eps, const float* gamma,
+                            const float* beta, int film_ld) {
+    PrepOp p; memset(&p, 0, sizeof(p));
+    p.C1 = C1; p.C2 = C2; p.B = B; p.T_src = Tn; p.T_dst = Tn; p.mode = mode;
+    p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
+    p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
+    p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
+    PrepOp* d = ar.get<PrepOp>(1);
+    if (!dry && cudaMemcpy(d, &p, sizeof(p), cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
+    return d;
+  }
+  void push(const Launch& l) { out->push_back(l); }
   void emit_prep(const float* s1, int C1, const float* s2, int C2, int T_src, int T_dst, int mode, const float* scale,
                  const float* shift, const SplitBuf& o, const SplitBuf* raw = nullptr, int row_mul = 1, int row_add = 0,
                  const int* rowmap = nullptr, int patch = 0) {
@@ -602,15 +586,15 @@ struct Builder {
     p.src1 = s1; p.ld1 = C1; p.C1 = C1; p.src2 = s2; p.ld2 = C2; p.C2 = C2; p.B = B; p.T_src = T_src; p.T_dst = T_dst;
     p.row_mul = row_mul; p.row_add = row_add; p.rowmap = rowmap; p.mode = mode; p.scale = scale; p.shift = shift; p.out = o;
     if (raw) p.raw = *raw;
-    pending.push_back(l);
+    out->push_back(l);
   }
   // GroupNorm(+FiLM)(+SiLU) prep whose statistics come from the producers' epilogues
   void emit_prep_gn(const float* s1, int C1, const double* st1, const float* s2, int C2, const double* st2, int Tn, int mode,
                     float eps, const float* gamma, const float* beta, const float* film, int film_ld, const SplitBuf& o,
                     const SplitBuf* raw = nullptr) {
     emit_prep(s1, C1, s2, C2, Tn, Tn, mode, nullptr, nullptr, o, raw);
-    PrepOp& p = pending.back().prep;
-    if (film) pending.back().reads_film = 1;
+    PrepOp& p = out->back().prep;
+    if (film) out->back().reads_film = 1;
     p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
     p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
     p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film = film; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
@@ -759,73 +743,123 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     o.x = emb; o.x_ld = ted; o.M = B; o.K = ted; o.W = h->film_W; o.bias = h->film_b; o.N = h->film_total; o.out = film; o.out_ld = h->film_total; o.in_mode = LIN_SILU; l.time_path = 1; fwd.push_back(l);
   }
 
-  struct Skip { float* p; int c; double* st; };
-  std::vector<Skip> skips;
+  // An activation that leaves a block: fp32 token-major tensor, its raw bf16 hi/lo split (the A operand of the panel-mode
+  // GEMMs that consume it; written by the same epilogue) and the per-(b, channel) sums for the consumer's GroupNorm.
+  struct Act { float* p = nullptr; SplitBuf sp{}; int c = 0; double* st = nullptr; };
+  const bool xf_on = h->xf && !h->simt;
+  SplitBuf rot_sp[3];
+  for (int i = 0; i < 3; ++i) rot_sp[i] = xf_on ? scratch_split(max_act) : SplitBuf{};
+  std::vector<Act> skips;
   int rot_i = 0;
-  auto next_out = [&](bool is_skip, size_t elems) -> float* {
-    if (is_skip) return ar.get<float>(elems);
-    float* p = rot[rot_i]; rot_i = (rot_i + 1) % 3; return p;
+  auto next_out = [&](bool is_skip, int TLn, int C) -> Act {
+    Act a; a.c = C;
+    const size_t elems = (size_t)B * TLn * C;
+    if (is_skip) { a.p = ar.get<float>(elems); if (xf_on) a.sp = Builder::view(scratch_split((size_t)B * TLn * pad_to(C, 8)), TLn, C); }
+    else { a.p = rot[rot_i]; if (xf_on) a.sp = Builder::view(rot_sp[rot_i], TLn, C); rot_i = (rot_i + 1) % 3; }
+    return a;
   };
+  auto emits_block_out = [&](GemmOp& g, const Act& a) {       // fp32 + (panel mode) raw split of a block output
+    g.flags |= EPI_OUT_F32; g.out = a.p; g.out_ld = a.c;
+    if (xf_on) { g.flags |= EPI_OUT_SPLIT; g.out_hi = a.sp.hi; g.out_lo = a.sp.lo; g.out_split_ld = a.sp.ld; }
+  };
+  // Can the GroupNorm in front of a GEMM over (cur [+ skip]) channels run inside the GEMM?  (64-channel blocks may not
+  // straddle the concat seam; the affine table holds kXfMaxC channels)
+  auto xf_ok = [&](int c1, int c2) { return xf_on && (c2 == 0 || c1 % 64 == 0) && c1 + c2 <= kXfMaxC && c.norm_num_groups <= 64; };
   auto followed_by_push = [&](size_t i) { return i + 1 < h->plan.size() && h->plan[i + 1].kind == PlanOp::PUSH; };
 
-  float* cur = nullptr; int cur_c = c0; double* cur_st = nullptr;
+  Act cur;
   {
-    float* o = next_out(true, (size_t)B * T * c0);      // conv_in output is the first skip
+    Act o = next_out(true, T, c0);                      // conv_in output is the first skip
     GemmOp g = bld.gemm_base(h->convin_lat, T);
     bld.conv3(g, s_xin);
-    g.flags = EPI_OUT_F32;
     if (Cc > 0) { g.flags |= EPI_RESIDUAL; g.res = P; g.res_ld = c0; }
     else { g.flags |= EPI_BIAS; g.bias = h->W("conv_in.bias"); }
-    g.out = o; g.out_ld = c0;
-    cur_st = new_stats(c0);
-    with_stats(g, cur_st, c0);
+    emits_block_out(g, o);
+    o.st = new_stats(c0);
+    with_stats(g, o.st, c0);
     bld.emit_gemm(g, h->convin_lat);
     cur = o;
-    bld.emit_tap("conv_in", cur, 0, c0, T);
+    bld.emit_tap("conv_in", cur.p, 0, c0, T);
   }
-  const float* cat2 = nullptr; const double* cat2_st = nullptr;   // pending concat source
+  Act cat2;                                              // pending concat source
   size_t ri = 0, xi = 0, si = 0;
   for (size_t pi = 0; pi < h->plan.size(); ++pi) {
     const PlanOp& o = h->plan[pi];
     const int TL = Tl[o.level];
     const size_t rows = (size_t)B * TL;
     switch (o.kind) {
-      case PlanOp::PUSH: skips.push_back({cur, cur_c, cur_st}); break;
-      case PlanOp::POP_CAT: cat2 = skips.back().p; cat2_st = skips.back().st; skips.pop_back(); break;
+      case PlanOp::PUSH: skips.push_back(cur); break;
+      case PlanOp::POP_CAT: cat2 = skips.back(); skips.pop_back(); break;
       case PlanOp::RESNET: {
         const ResnetSite& s = h->resnets[ri++];
-        const float* s1 = cur; const float* s2 = s.c2 ? cat2 : nullptr;
-        const SplitBuf a_in = Builder::view(SP_A, TL, s.cin), a_raw = Builder::view(SP_R, TL, s.cin), a_h = Builder::view(SP_H, TL, s.cout);
-        bld.emit_prep_gn(s1, s.c1, cur_st, s2, s.c2, s.c2 ? cat2_st : nullptr, TL, PREP_AFFINE_SILU, c.norm_eps,
-                         h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, a_in, s.shortcut ? &a_raw : nullptr);
+        const float* s1 = cur.p; const float* s2 = s.c2 ? cat2.p : nullptr;
+        const SplitBuf a_h = Builder::view(SP_H, TL, s.cout);
         double* h1_st = new_stats(s.cout);
-        {
-          GemmOp g = bld.gemm_base(s.conv1, TL);
-          bld.conv3(g, a_in);
-          g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv1.bias");
-          if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
-          g.out = H1; g.out_ld = s.cout;
-          with_stats(g, h1_st, s.cout);
-          bld.emit_gemm(g, s.conv1);
+        Act outp = next_out(followed_by_push(pi), TL, s.cout);
+        outp.st = new_stats(s.cout);
+        if (xf_ok(s.c1, s.c2) && s.cout <= kXfMaxC) {
+          // Panel mode: norm1 + SiLU inside conv1, norm2 (+FiLM) + SiLU inside conv2 (reference resnet.py:597-612); the
+          // 1x1 shortcut reads the raw splits of the block input(s) as extra 1-tap segments.  No prep launch, no fp32 h.
+          const int ni = nkb_of(s.cin), n1 = nkb_of(s.c1), no = nkb_of(s.cout);
+          {
+            GemmOp g = bld.gemm_base(s.conv1, TL);
+            const int i0 = bld.add_src(g, cur.sp);
+            bld.xseg(g, i0, 0, s.c1, 3, 0, ni, 1, 0);
+            if (s.c2) { const int i1 = bld.add_src(g, cat2.sp); bld.xseg(g, i1, 0, s.c2, 3, n1, ni, 1, s.c1); }
+            g.pre = bld.affine_desc(cur.st, s.c1, s.c2 ? cat2.st : nullptr, s.c2, TL, PREP_AFFINE_SILU, c.norm_eps,
+                                    h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), 0);
+            g.flags = EPI_BIAS | EPI_OUT_SPLIT; g.bias = h->W(s.p + ".conv1.bias");
+            if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
+            g.out_hi = a_h.hi; g.out_lo = a_h.lo; g.out_split_ld = a_h.ld;
+            with_stats(g, h1_st, s.cout);
+            bld.emit_gemm(g, s.conv1);
+          }
+          {
+            GemmOp g = bld.gemm_base(s.conv2, TL);
+            const int j0 = bld.add_src(g, a_h);
+            bld.xseg(g, j0, 0, s.cout, 3, 0, no, 1, 0);
+            g.flags = EPI_BIAS; g.bias = s.bias2;
+            if (s.shortcut) {
+              const int a0 = bld.add_src(g, cur.sp);
+              bld.xseg(g, a0, 0, s.c1, 1, 3 * no, 0, 0, 0);
+              if (s.c2) { const int a1 = bld.add_src(g, cat2.sp); bld.xseg(g, a1, 0, s.c2, 1, 3 * no + n1, 0, 0, 0); }
+            } else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
+            g.pre = bld.affine_desc(h1_st, s.cout, nullptr, 0, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
+                                    h->W(s.p + ".norm2.bias"), h->film_total);
+            g.pre_film = c.time_scale_shift ? film + s.film_off : nullptr;
+            emits_block_out(g, outp);
+            with_stats(g, outp.st, s.cout);
+            bld.emit_gemm(g, s.conv2);
+          }
+        } else {
+          const SplitBuf a_in = Builder::view(SP_A, TL, s.cin), a_raw = Builder::view(SP_R, TL, s.cin);
+          bld.emit_prep_gn(s1, s.c1, cur.st, s2, s.c2, s.c2 ? cat2.st : nullptr, TL, PREP_AFFINE_SILU, c.norm_eps,
+                           h->W(s.p + ".norm1.weight"), h->W(s.p + ".norm1.bias"), nullptr, 0, a_in, s.shortcut ? &a_raw : nullptr);
+          {
+            GemmOp g = bld.gemm_base(s.conv1, TL);
+            bld.conv3(g, a_in);
+            g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv1.bias");
+            if (!c.time_scale_shift) { g.flags |= EPI_ROWBIAS; g.rowbias = film + s.film_off; g.rowbias_ld = h->film_total; }
+            g.out = H1; g.out_ld = s.cout;
+            with_stats(g, h1_st, s.cout);
+            bld.emit_gemm(g, s.conv1);
+          }
+          // norm2 (+FiLM scale/shift) + SiLU (reference resnet.py:602-612)
+          bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
+                           h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
+          {
+            GemmOp g = bld.gemm_base(s.conv2, TL);
+            bld.conv3(g, a_h);
+            g.flags = EPI_BIAS; g.bias = s.bias2;
+            if (s.shortcut) { const int i = bld.add_src(g, a_raw); bld.seg(g, i, 0, s.cin, 0); }
+            else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
+            emits_block_out(g, outp);
+            with_stats(g, outp.st, s.cout);
+            bld.emit_gemm(g, s.conv2);
+          }
         }
-        // norm2 (+FiLM scale/shift) + SiLU (reference resnet.py:602-612)
-        bld.emit_prep_gn(H1, s.cout, h1_st, nullptr, 0, nullptr, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
-                         h->W(s.p + ".norm2.bias"), c.time_scale_shift ? film + s.film_off : nullptr, h->film_total, a_h);
-        float* outp = next_out(followed_by_push(pi), rows * s.cout);
-        double* out_st = new_stats(s.cout);
-        {
-          GemmOp g = bld.gemm_base(s.conv2, TL);
-          bld.conv3(g, a_h);
-          g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = s.bias2;
-          if (s.shortcut) { const int i = bld.add_src(g, a_raw); bld.seg(g, i, 0, s.cin, 0); }
-          else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
-          g.out = outp; g.out_ld = s.cout;
-          with_stats(g, out_st, s.cout);
-          bld.emit_gemm(g, s.conv2);
-        }
-        cur_st = out_st;
-        cur = outp; cur_c = s.cout; cat2 = nullptr; cat2_st = nullptr;
-        bld.emit_tap(s.p, cur, o.level, cur_c, TL);
+        cur = outp; cat2 = Act{};
+        bld.emit_tap(s.p, cur.p, o.level, cur.c, TL);
         break;
       }
       case PlanOp::XFORMER: {
@@ -835,7 +869,8 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const SplitBuf sx = Builder::view(SP_X, TL, C), satt = Builder::view(SP_ATT, TL, C), sff = Builder::view(SP_FF, TL, 4 * C),
                        sh2 = Builder::view(SP_H, TL, C);
         auto lin = [&](const PackedB& w, const SplitBuf& in, int nch) { GemmOp g = bld.gemm_base(w, TL); const int i = bld.add_src(g, in); bld.seg(g, i, 0, nch, 0); return g; };
-        bld.emit_prep_gn(cur, C, cur_st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
+        const bool xin = xf_ok(C, 0);                        // GroupNorm(eps 1e-6) of the block input applied inside proj_in
+        if (!xin) bld.emit_prep_gn(cur.p, C, cur.st, nullptr, 0, nullptr, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), nullptr, 0, sx);
         // Folded LayerNorms: the producer of each LN input also emits its raw bf16 split and the per-row sums; the consumer
         // GEMM runs on the raw split with gamma folded into its weights and applies mean / rstd in its epilogue:
         //   LN(x) W^T = rstd * (x (gamma*W)^T - mean * g) + (beta W^T + bias),   g[n] = sum_c gamma_c W[n,c]
@@ -846,7 +881,13 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         auto emits_ln_input = [&](GemmOp& g, double* rs) { g.flags |= EPI_OUT_SPLIT | EPI_ROWSTATS; g.out_hi = sln.hi; g.out_lo = sln.lo; g.out_split_ld = sln.ld; g.row_stats = rs; };
         auto consumes_ln = [&](GemmOp& g, const double* rs, const float* gv, const float* bf) {
           g.flags |= EPI_LNFOLD | EPI_BIAS; g.ln_stats = rs; g.ln_g = gv; g.bias = bf; g.ln_C = C; g.ln_eps = 1e-5f; };
-        { GemmOp g = lin(x.proj_in, sx, C); g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C;
+        { GemmOp g = xin ? bld.gemm_base(x.proj_in, TL) : lin(x.proj_in, sx, C);
+          if (xin) {
+            const int i0 = bld.add_src(g, cur.sp);
+            bld.xseg(g, i0, 0, C, 1, 0, 0, 1, 0);
+            g.pre = bld.affine_desc(cur.st, C, nullptr, 0, TL, PREP_AFFINE, 1e-6f, h->W(x.p + ".norm.weight"), h->W(x.p + ".norm.bias"), 0);
+          }
+          g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_in.bias"); g.out = T0; g.out_ld = C;
           if (fold) emits_ln_input(g, rs1);
           bld.emit_gemm(g, x.proj_in); }
         if (!fold) bld.emit_ln_split(T0, C, (int)rows, C, h->W(b + ".norm1.weight"), h->W(b + ".norm1.bias"), sx);
@@ -890,22 +931,23 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           g.out_hi = sff.hi; g.out_lo = sff.lo; g.out_split_ld = sff.ld;
           if (fold) { consumes_ln(g, rs3, x.g_ff1, x.bf_ff1); g.flags &= ~EPI_BIAS; }   // GEGLU reads its (folded) biases through g.bias itself
           bld.emit_gemm(g, x.ff1); }
-        float* outp = next_out(followed_by_push(pi), rows * C);
+        Act outp = next_out(followed_by_push(pi), TL, C);
+        outp.st = new_stats(C);
         if (h->merge_ff && fold) {
           // ff.net.2 + proj_out as one GEMM over K = [GEGLU output | residual stream]:  out = g (Wp W2)^T + h Wp^T + (Wp b2 + bp) + x_in
           GemmOp g = bld.gemm_base(x.ff2p, TL);
           const int i0 = bld.add_src(g, sff); bld.seg(g, i0, 0, 4 * C, 0);
           const int i1 = bld.add_src(g, sln); bld.seg(g, i1, 0, C, 0);          // raw split of the residual stream, written by out2's epilogue
-          g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = x.bias_ff2p; g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
-          cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.ff2p);
+          g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = x.bias_ff2p; g.res = cur.p; g.res_ld = C;
+          emits_block_out(g, outp); with_stats(g, outp.st, C); bld.emit_gemm(g, x.ff2p);
         } else {
           { GemmOp g = lin(x.ff2, sff, 4 * C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_SPLIT; g.bias = h->W(b + ".ff.net.2.bias"); g.res = T0; g.res_ld = C;
             g.out_hi = sh2.hi; g.out_lo = sh2.lo; g.out_split_ld = sh2.ld; bld.emit_gemm(g, x.ff2); }
-          { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL | EPI_OUT_F32; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur; g.res_ld = C; g.out = outp; g.out_ld = C;
-            cur_st = new_stats(C); with_stats(g, cur_st, C); bld.emit_gemm(g, x.proj_out); }
+          { GemmOp g = lin(x.proj_out, sh2, C); g.flags = EPI_BIAS | EPI_RESIDUAL; g.bias = h->W(x.p + ".proj_out.bias"); g.res = cur.p; g.res_ld = C;
+            emits_block_out(g, outp); with_stats(g, outp.st, C); bld.emit_gemm(g, x.proj_out); }
         }
         cur = outp;
-        bld.emit_tap(x.p, cur, o.level, C, TL);
+        bld.emit_tap(x.p, cur.p, o.level, C, TL);
         break;
       }
       case PlanOp::DOWN: {
@@ -915,17 +957,18 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const int Tin = Tl[o.level - 1];
         const int To = Tin / 2;                                  // odd-row count
         const SplitBuf ev = Builder::view(SP_A, TL, s.c), od = Builder::view(SP_R, std::max(To, 1), s.c);
-        bld.emit_prep(cur, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, ev, nullptr, 2, 0);
-        bld.emit_prep(cur, s.c, nullptr, 0, Tin, std::max(To, 1), PREP_RAW, nullptr, nullptr, od, nullptr, 2, 1);
-        float* outp = next_out(followed_by_push(pi), rows * s.c);
+        bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, ev, nullptr, 2, 0);
+        bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, std::max(To, 1), PREP_RAW, nullptr, nullptr, od, nullptr, 2, 1);
+        Act outp = next_out(followed_by_push(pi), TL, s.c);
+        outp.st = new_stats(s.c);
         GemmOp g = bld.gemm_base(s.w, TL);
         const int ie = bld.add_src(g, ev), io = bld.add_src(g, od);
         bld.seg(g, io, 0, s.c, -1); bld.seg(g, ie, 0, s.c, 0); bld.seg(g, io, 0, s.c, 0);
-        g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
-        cur_st = new_stats(s.c); with_stats(g, cur_st, s.c);
+        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias");
+        emits_block_out(g, outp); with_stats(g, outp.st, s.c);
         bld.emit_gemm(g, s.w);
         cur = outp;
-        bld.emit_tap(s.p, cur, o.level, s.c, TL);
+        bld.emit_tap(s.p, cur.p, o.level, s.c, TL);
         break;
       }
       case PlanOp::UP: {
@@ -939,15 +982,16 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           NS_CHECK_CUDA(cudaGetLastError());
         }
         const SplitBuf up = Builder::view(SP_A, TL, s.c);
-        bld.emit_prep(cur, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, up, nullptr, 1, 0, map_d);
-        float* outp = next_out(followed_by_push(pi), rows * s.c);
+        bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, up, nullptr, 1, 0, map_d);
+        Act outp = next_out(followed_by_push(pi), TL, s.c);
+        outp.st = new_stats(s.c);
         GemmOp g = bld.gemm_base(s.w, TL);
         bld.conv3(g, up);
-        g.flags = EPI_BIAS | EPI_OUT_F32; g.bias = h->W(s.p + ".conv.bias"); g.out = outp; g.out_ld = s.c;
-        cur_st = new_stats(s.c); with_stats(g, cur_st, s.c);
+        g.flags = EPI_BIAS; g.bias = h->W(s.p + ".conv.bias");
+        emits_block_out(g, outp); with_stats(g, outp.st, s.c);
         bld.emit_gemm(g, s.w);
         cur = outp;
-        bld.emit_tap(s.p, cur, o.level, s.c, TL);
+        bld.emit_tap(s.p, cur.p, o.level, s.c, TL);
         break;
       }
     }
@@ -955,13 +999,18 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   // output head: GN -> SiLU -> conv_out, stored channel-major [B, out_channels, T]
   {
     const SplitBuf a_h = Builder::view(SP_H, T, c0);
-    bld.emit_prep_gn(cur, c0, cur_st, nullptr, 0, nullptr, T, PREP_AFFINE_SILU, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, a_h);
     GemmOp g = bld.gemm_base(h->conv_out, T);
-    bld.conv3(g, a_h);
+    if (xf_ok(c0, 0)) {
+      const int i0 = bld.add_src(g, cur.sp);
+      bld.xseg(g, i0, 0, c0, 3, 0, nkb_of(c0), 1, 0);
+      g.pre = bld.affine_desc(cur.st, c0, nullptr, 0, T, PREP_AFFINE_SILU, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), 0);
+    } else {
+      bld.emit_prep_gn(cur.p, c0, cur.st, nullptr, 0, nullptr, T, PREP_AFFINE_SILU, c.norm_eps, h->W("conv_norm_out.weight"), h->W("conv_norm_out.bias"), nullptr, 0, a_h);
+      bld.conv3(g, a_h);
+    }
     g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
     bld.emit_gemm(g, h->conv_out, 3);
   }
-  bld.flush_pending();
   if (bld.err) return bld.err;
   if (bytes_out) *bytes_out = ar.off + 256;
   if (!dry) {
@@ -996,7 +1045,7 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
           if (l.patch == 3) g.out = out;
           if (film_ext && l.reads_film) {
             g.rowbias = rebase(g.rowbias);
-            for (int i = 0; i < g.npre; ++i) g.pre_film[i] = rebase(g.pre_film[i]);
+            g.pre_film = rebase(g.pre_film);
           }
           if (h->span && count < h->span_cap) g.span = h->span + 2 * count;
           if (h->trace && gemm_idx < h->trace_cap) g.trace = h->trace + 32 * gemm_idx;
@@ -1160,7 +1209,7 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   const char* be = getenv("NS2VC_GEMM_BACKEND");
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
-  { const char* e = getenv("NS2VC_PIP"); h->pip = (e && e[0] == '1'); }   // measured r02: 3.67 vs 3.44 ms per forward (the prep phase runs at 10 warps per SM) - off
+  { const char* e = getenv("NS2VC_XF"); h->xf = !(e && e[0] == '0'); }
   { const char* e = getenv("NS2VC_MERGE_FF"); h->merge_ff = !(e && e[0] == '0'); }
   build_plan(h);
   register_weights(h);

@@ -4,7 +4,8 @@
 
 namespace ns2vc {
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x); fast division (2 ulp): for very negative v the quotient flushes to 0, which is the limit
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // erf-GELU, as F.gelu default (reference attention.py:295)
 // erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far inside the fp32 parity budget); the libm

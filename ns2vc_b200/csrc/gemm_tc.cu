@@ -51,6 +51,19 @@ constexpr int kStagePerWarp = 8192;
 constexpr int kStageOff = 8192;                         // the staging area starts with two GroupNorm partial-sum buffers (tile parity), <= 4 KB each
 constexpr int kStagingBytes = kStageOff + kEpiWarps * kStagePerWarp;   // 68 KB
 
+// Panel mode (GemmOp::xmode): per 64-channel block the hi and lo panels of 136 rows (130 used: t0-1 .. t0+128) go through a
+// three-stage ring (TMA -> normalise -> MMA), the weight tiles (hi | lo) of up to three taps through a two-stage ring of
+// their own; the affine table sits behind them.
+constexpr int kPanelRows = BM + 2;
+constexpr int kPanelBytes = 136 * 128;                   // 17 KB: 1024-byte aligned so that hi and lo panels share the swizzle phase
+constexpr int kXAStageBytes = 2 * kPanelBytes;           // hi | lo panel of one 64-channel block
+constexpr int kXBStageBytes = 3 * 2 * (64 * BK * 2);     // weight tiles (hi | lo) of up to three taps
+constexpr int kXAStages = 3;                             // TMA -> normalise -> MMA: three panels in flight
+constexpr int kXBStages = 2;
+constexpr int kXOffB = kXAStages * kXAStageBytes;        // 104 448
+constexpr int kXOffAff = kXOffB + kXBStages * kXBStageBytes;   // [Cs] scale | [Cs] shift | [2 G] group statistics (floats), Cs = kXfMaxC
+constexpr int kXAffBytes = (2 * kXfMaxC + 2 * 64) * 4;
+
 template <int BN_> struct TileCfg {
   static constexpr int BN = BN_;
   static constexpr int kBTileBytes = BN_ * BK * 2;      // one bf16 [BN x 64] B tile (hi or lo)
@@ -68,6 +81,7 @@ template <int BN_> struct TileCfg {
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(BM, 2 * BN_);
 };
 static_assert(TileCfg<64>::kSmemBytes <= 227 * 1024 && TileCfg<128>::kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kXOffAff + kXAffBytes <= TileCfg<64>::kPipeBytes && kPrepSlots * kEpiWarps * 32 >= kXfMaxC, "panel mode: stages + affine table inside the pipeline area");
 
 
 // Store 32 consecutive output columns of one row in the layout(s) the op asks for.
@@ -165,19 +179,19 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
 }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// fused-prep stamps of thread 0 of CTA 0: slots 16.. of the 32-slot trace record
-#define PTRACE(i) do { if (op_param.trace && blockIdx.x == 0 && tid == 0) op_param.trace[16 + (i)] = gtime(); } while (0)
+// panel-mode stamps of the first transform thread of CTA 0: slots 16.. of the 32-slot trace record
+#define XTRACE(i) do { if (op_param.trace && blockIdx.x == 0 && tid == 64) op_param.trace[16 + (i)] = gtime(); } while (0)
 #define TRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0) op.trace[i] = gtime(); } while (0)
 // epilogue sub-steps of warp 2 / lane 0 of CTA (0,0), SM clock: slots 8..15 of the 16-slot trace record
 __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
 #define ETRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) op.trace[8 + (i)] = gclk(); } while (0)
 
-static_assert(kPrepSlots * kThreads >= kPrepFuseMaxC && prep_affine_floats(kPrepFuseMaxC) * 4 <= 2 * kATileBytes, "fused prep: affine table");
-static_assert(sizeof(GemmOp) <= 2432 && sizeof(PrepOp) <= 320, "GemmOp must fit the shared-memory descriptor copy");
+static_assert(sizeof(GemmOp) <= 2688 && sizeof(PrepOp) <= 320, "GemmOp must fit the shared-memory descriptor copy");
 
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
-template <int BN_, bool LNF>
+// XF: instantiation with the panel-mode paths (GroupNorm of the A operand applied in shared memory; BN = 64, one tile per CTA)
+template <int BN_, bool LNF, bool XF>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -193,6 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   auto acc_full = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kOffBar + 8 * (2 * kMaxStages + 4));
+  // panel mode: A ring = full_bar / empty_bar (0..2) + a_ready (normalised by the 8 epilogue warps); weight ring of its own
+  auto a_ready = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (19 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (21 + s); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // The 1.7 KB operator descriptor lives in the kernel-parameter constant bank, which is cold at every
@@ -204,11 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint4* src = reinterpret_cast<const uint4*>(&op_param);
     uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc);
     for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
-    // fused-prep descriptors (device memory, static): parked behind the operator copy
-    if (op_param.npre > 0) {
+    // GroupNorm parameters of a panel-mode launch (device memory, static): parked behind the operator copy
+    if (XF && op_param.xmode && op_param.pre) {
       const uint4* ps = reinterpret_cast<const uint4*>(op_param.pre);
-      uint4* pd = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc + 2432);
-      for (int i = tid; i < op_param.npre * (int)(sizeof(PrepOp) / 16); i += kThreads) pd[i] = __ldg(ps + i);
+      uint4* pd = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc + 2688);
+      for (int i = tid; i < (int)(sizeof(PrepOp) / 16); i += kThreads) pd[i] = __ldg(ps + i);
     }
   }
   const GemmOp& op = *reinterpret_cast<const GemmOp*>(smem + Cfg::kOffDesc);
@@ -232,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), kEpiWarps); }
+    if (XF) { for (int a = 0; a < kXAStages; ++a) mbar_init(a_ready(a), kEpiWarps); for (int a = 0; a < kXBStages; ++a) { mbar_init(b_full(a), 1); mbar_init(b_empty(a), 1); } }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
@@ -249,10 +268,169 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && tr0) TRACE(1);
 
+  // ============================================================================================================
+  // Panel mode: one tile per CTA (grid == tile count).  warp 0: panels + weight tiles by TMA; warps 2-9: normalise
+  // each panel in place, then (below) the ordinary epilogue; warp 1: three row-shifted views of the panel per tap.
+  // ============================================================================================================
+  bool xpanel = false;
+  if constexpr (XF) xpanel = op_param.xmode != 0;
+  if constexpr (XF) if (xpanel) {
+    const int tile = (int)blockIdx.x, mtile = tile / n_tiles;
+    const int xb = mtile / tiles_per_batch, xt0 = (mtile % tiles_per_batch) * BM, xn0 = (tile % n_tiles) * BN;
+    int ncblk = 0;
+    for (int si = 0; si < op.nxs; ++si) ncblk += op.xs[si].ncb;
+    if (warp == 0) {
+      if (lane == 0) {
+        // weights of the first two channel blocks before the dependency wait, activations after it
+        auto issue_w = [&](const XSeg& xs, int cb, int sb) {
+          const uint32_t b0 = base + kXOffB + sb * kXBStageBytes;
+          mbar_arrive_expect_tx(b_full(sb), (uint32_t)xs.ntap * 2u * Cfg::kBTileBytes);
+          for (int j = 0; j < xs.ntap; ++j) {
+            const size_t eoff = ((size_t)(xs.kb_tap[j] + cb) * op.N + xn0) * 64;
+            bulk_g2s(b0 + j * 2 * Cfg::kBTileBytes, op.w_hi + eoff, Cfg::kBTileBytes, b_full(sb));
+            bulk_g2s(b0 + j * 2 * Cfg::kBTileBytes + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, b_full(sb));
+          }
+        };
+        { int it = 0;
+          for (int si = 0; si < op.nxs && it < kXBStages; ++si)
+            for (int cb = 0; cb < op.xs[si].ncb && it < kXBStages; ++cb, ++it) issue_w(op.xs[si], cb, it); }
+        pdl_wait();
+        if (tr0) TRACE(2);
+        int it = 0;
+        for (int si = 0; si < op.nxs; ++si) {
+          const XSeg& xs = op.xs[si];
+          for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+            const int sa = it % kXAStages, sb = it % kXBStages;
+            if (it >= kXAStages) mbar_wait(empty_bar(sa), (uint32_t)(((it / kXAStages) & 1) ^ 1));
+            const uint32_t a_hi = base + sa * kXAStageBytes;
+            const uint32_t rows = xs.ntap == 3 ? (uint32_t)kPanelRows : (uint32_t)BM;
+            const int c = xs.c0 + cb * 64, trow = xt0 + (xs.ntap == 3 ? -1 : 0);
+            mbar_arrive_expect_tx(full_bar(sa), 2u * rows * 128u);
+            tma_load_3d(a_hi, &tmaps[2 * xs.src], c, trow, xb, full_bar(sa));
+            tma_load_3d(a_hi + kPanelBytes, &tmaps[2 * xs.src + 1], c, trow, xb, full_bar(sa));
+            if (it >= kXBStages) { mbar_wait(b_empty(sb), (uint32_t)(((it / kXBStages) & 1) ^ 1)); issue_w(xs, cb, sb); }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int it = 0;
+        for (int si = 0; si < op.nxs; ++si) {
+          const XSeg& xs = op.xs[si];
+          for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+            const int sa = it % kXAStages, sb = it % kXBStages;
+            mbar_wait(b_full(sb), (uint32_t)((it / kXBStages) & 1));
+            mbar_wait(a_ready(sa), (uint32_t)((it / kXAStages) & 1));
+            if (it == 0 && tr0) TRACE(3);
+            tc_fence_after();
+            const uint32_t a_hi = base + sa * kXAStageBytes, a_lo = a_hi + kPanelBytes, b0 = base + kXOffB + sb * kXBStageBytes;
+            for (int j = 0; j < xs.ntap; ++j) {            // tap j = panel rows [j, j + 128): start address + 128 B per row
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t dah = umma_desc(a_hi + j * 128 + k * 32), dal = umma_desc(a_lo + j * 128 + k * 32);
+                const uint64_t dbh = umma_desc(b0 + j * 2 * Cfg::kBTileBytes + k * 32);
+                umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc2, (it | j | k) != 0 ? 1u : 0u);
+                umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
+              }
+            }
+            umma_commit(empty_bar(sa));
+            umma_commit(b_empty(sb));
+          }
+        }
+        umma_commit(acc_full(0));
+        if (tr0) TRACE(4);
+      }
+    } else {
+      // ---- transform warps (the epilogue warps; 256 threads) ----
+      const int xt = tid - 64;
+      float* aff = reinterpret_cast<float*>(smem + kXOffAff);
+      const PrepOp& pr = *reinterpret_cast<const PrepOp*>(smem + Cfg::kOffDesc + 2688);
+      const bool have_aff = op.pre != nullptr;
+      const int C = have_aff ? pr.C1 + pr.C2 : 0;
+      auto sync256 = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+      float pg[kPrepSlots], pbv[kPrepSlots], fs[kPrepSlots], fbv[kPrepSlots];
+      if (have_aff) prep_fetch_norm_weights(pr, C, pg, pbv, xt, 256);
+      pdl_wait();
+      XTRACE(0);
+      if (have_aff) {
+        prep_fetch_film(pr, op.pre_film, xb, C, fs, fbv, xt, 256);
+        for (int c = C + xt; c < ((C + 63) & ~63); c += 256) { aff[c] = 0.f; aff[kXfMaxC + c] = 0.f; }   // padding channels of the last block
+        prep_affine(pr, xb, C, kXfMaxC, aff, pg, pbv, fs, fbv, xt, 256, sync256);
+      }
+      XTRACE(1);
+      const bool silu = have_aff && pr.mode == PREP_AFFINE_SILU;
+      int it = 0;
+      for (int si = 0; si < op.nxs; ++si) {
+        const XSeg& xs = op.xs[si];
+        const int rows = xs.ntap == 3 ? kPanelRows : BM, tfirst = xt0 + (xs.ntap == 3 ? -1 : 0);
+        const int Tsrc = op.src[xs.src].T;
+        for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+          const int sa = it % kXAStages;
+          // this thread's 16-byte chunk column q = xt % 8 is the same for every row it touches: its 8 scale / shift values
+          // are fetched once per panel, before the panel itself has landed
+          const int q = xt & 7;
+          float scv[8], shv[8];
+          if (xs.xf) {
+            const float* sc = aff + xs.aff_c0 + cb * 64 + q * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sc + kXfMaxC), b1 = *reinterpret_cast<const float4*>(sc + kXfMaxC + 4);
+            scv[0] = s0.x; scv[1] = s0.y; scv[2] = s0.z; scv[3] = s0.w; scv[4] = s1.x; scv[5] = s1.y; scv[6] = s1.z; scv[7] = s1.w;
+            shv[0] = b0.x; shv[1] = b0.y; shv[2] = b0.z; shv[3] = b0.w; shv[4] = b1.x; shv[5] = b1.y; shv[6] = b1.z; shv[7] = b1.w;
+          }
+          mbar_wait(full_bar(sa), (uint32_t)((it / kXAStages) & 1));
+          if (it == 0) XTRACE(2);
+          if (xs.xf) {
+            uint8_t* p_hi = smem + sa * kXAStageBytes;
+            uint8_t* p_lo = p_hi + kPanelBytes;
+            auto xform = [&](int r, uint4& h4, uint4& l4) {     // one 16-byte chunk (8 channels) of row r, in place
+              const int t = tfirst + r;
+              float v[8];
+              if (t >= 0 && t < Tsrc) {
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float x0, x1;
+                  upk2(fadd2(pk2(__uint_as_float(hw[j] << 16), __uint_as_float(hw[j] & 0xffff0000u)),
+                             pk2(__uint_as_float(lw[j] << 16), __uint_as_float(lw[j] & 0xffff0000u))), x0, x1);
+                  float y0, y1;
+                  upk2(ffma2(pk2(x0, x1), pk2(scv[2 * j], scv[2 * j + 1]), pk2(shv[2 * j], shv[2 * j + 1])), y0, y1);
+                  if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                  v[2 * j] = y0; v[2 * j + 1] = y1;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = 0.f;     // rows outside the sequence: the conv's zero padding (of the NORMALISED activation)
+              }
+              split8(v, h4, l4);
+            };
+            const int nrow = rows;                          // 130 or 128; this thread: rows (xt >> 3) + 32 k
+            for (int r0 = xt >> 3; r0 < nrow; r0 += 64) {    // two rows per iteration: independent chains
+              const int r1 = r0 + 32;
+              const int off0 = r0 * 128 + ((q ^ (r0 & 7)) << 4), off1 = r1 * 128 + ((q ^ (r1 & 7)) << 4);
+              const bool two = r1 < nrow;
+              uint4 h0 = *reinterpret_cast<const uint4*>(p_hi + off0), l0 = *reinterpret_cast<const uint4*>(p_lo + off0);
+              uint4 h1 = make_uint4(0, 0, 0, 0), l1 = make_uint4(0, 0, 0, 0);
+              if (two) { h1 = *reinterpret_cast<const uint4*>(p_hi + off1); l1 = *reinterpret_cast<const uint4*>(p_lo + off1); }
+              xform(r0, h0, l0);
+              if (two) xform(r1, h1, l1);
+              *reinterpret_cast<uint4*>(p_hi + off0) = h0; *reinterpret_cast<uint4*>(p_lo + off0) = l0;
+              if (two) { *reinterpret_cast<uint4*>(p_hi + off1) = h1; *reinterpret_cast<uint4*>(p_lo + off1) = l1; }
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready(sa));
+          if (it == 0) XTRACE(3);
+        }
+      }
+      XTRACE(4);
+    }
+  }
+
   // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
-  // griddepcontrol.wait; the activations (written by the previous kernel, or by the fused prep below) only after it.
+  // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
   const int npf = nkb < nst ? nkb : nst;
-  if (warp == 0 && lane == 0) {
+  if (!xpanel && warp == 0 && lane == 0) {
     const int n0 = ((int)blockIdx.x % n_tiles) * BN;
     for (int kb = 0; kb < npf; ++kb) {
       const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
@@ -264,63 +442,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
   __syncwarp();
 
-  if constexpr (BN == 64) if (op_param.npre > 0) {
-    // ===================== fused prep (whole CTA; grid == tile count, cluster = the N tiles of one row block) =====================
-    // GroupNorm(+FiLM)(+SiLU) / decimation / nearest-upsample of the producer's fp32 activations into the split A operand
-    // (reference resnet.py:597-612, transformer_1d.py:256-262, resnet.py:160,214-223): this CTA converts its share of the
-    // channels for the rows its tile's taps touch; halo rows are also written (with identical values) by the neighbouring
-    // cluster.  Generic-proxy global stores -> cluster barrier (release / acquire) -> proxy fence -> TMA loads.
-    const int tile = (int)blockIdx.x, mtile = tile / n_tiles, part = tile % n_tiles;
-    const int pb_ = mtile / tiles_per_batch, pt0 = (mtile % tiles_per_batch) * BM;
-    float* aff = reinterpret_cast<float*>(smem);             // stage 0's A tiles are idle until the first activation load
-    for (int p = 0; p < op_param.npre; ++p) {
-      const PrepOp& pr = reinterpret_cast<const PrepOp*>(smem + Cfg::kOffDesc + 2432)[p];
-      const int C = pr.C1 + pr.C2;
-      float pg[kPrepSlots], pbv[kPrepSlots], fs[kPrepSlots], fbv[kPrepSlots];
-      prep_fetch_norm_weights(pr, C, pg, pbv);
-      if (p == 0) { pdl_wait(); PTRACE(0); }
-      prep_fetch_film(pr, op.pre_film[p], pb_, C, fs, fbv);
-      const int chunks = pr.out.ld >> 3, per = (chunks + n_tiles - 1) / n_tiles;
-      const int ck_lo = part * per, ck_hi = (ck_lo + per < chunks) ? ck_lo + per : chunks, nck = ck_hi - ck_lo;
-      const int r_lo = (pt0 + op.pre_tap_lo[p] > 0) ? pt0 + op.pre_tap_lo[p] : 0;
-      const int r_hi = (pt0 + BM + op.pre_tap_hi[p] < pr.T_dst) ? pt0 + BM + op.pre_tap_hi[p] : pr.T_dst;
-      const int total = (nck > 0 && r_hi > r_lo) ? (r_hi - r_lo) * nck : 0;
-      constexpr int kWave = 4;                              // independent work items per thread: their loads are in flight together
-      PrepChunk kc[kWave];
-#pragma unroll
-      for (int u = 0; u < kWave; ++u) {                     // the first wave's loads fly while the affine is derived
-        const int i = tid + u * kThreads;
-        if (i < total) prep_load_at(pr, pb_, C, r_lo + i / nck, ck_lo + i % nck, kc[u]);
-      }
-      if (p == 0) PTRACE(1);
-      prep_affine(pr, pb_, C, aff, pg, pbv, fs, fbv);
-      if (p == 0) PTRACE(2);
-#pragma unroll
-      for (int u = 0; u < kWave; ++u)
-        if (tid + u * kThreads < total) prep_finish(pr, pb_, C, aff, kc[u]);
-      for (int i0 = tid + kWave * kThreads; i0 < total; i0 += kWave * kThreads) {
-#pragma unroll
-        for (int u = 0; u < kWave; ++u) {
-          const int i = i0 + u * kThreads;
-          if (i < total) prep_load_at(pr, pb_, C, r_lo + i / nck, ck_lo + i % nck, kc[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kWave; ++u)
-          if (i0 + u * kThreads < total) prep_finish(pr, pb_, C, aff, kc[u]);
-      }
-      if (p == 0) PTRACE(3);
-      __syncthreads();                                      // aff is rewritten by the next prep / handed to the pipeline
-    }
-    PTRACE(4);
-    asm volatile("fence.proxy.async;" ::: "memory");
-    if (op_param.cn > 1) cluster_sync_all(); else __syncthreads();
-    asm volatile("fence.proxy.async;" ::: "memory");
-    PTRACE(5);
-  }
-
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !xpanel) {
       const int npre = npf;
       pdl_wait();
       if (tr0) TRACE(2);
@@ -352,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && !xpanel) {
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * kAccCols);
@@ -671,7 +795,9 @@ int encode_tmaps(GemmOp& op) {
     }
   }
   for (int i = 0; i < op.nsrc; ++i) {
-    const int box_rows = BM;
+    int box_rows = BM;
+    if (op.xmode)                                           // panel mode: a k=3 source is fetched as one 130-row panel per channel block
+      for (int k = 0; k < op.nxs; ++k) if (op.xs[k].src == i && op.xs[k].ntap == 3) box_rows = kPanelRows;
     int rc = encode_one(&op.tmap[2 * i], op.src[i].hi, op.src[i], op.B, box_rows);
     if (rc) return rc;
     rc = encode_one(&op.tmap[2 * i + 1], op.src[i].lo, op.src[i], op.B, box_rows);
@@ -690,25 +816,19 @@ static int sm_count() {
   return n;
 }
 
-template <int BN_, bool LNF>
+template <int BN_, bool LNF, bool XF>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
   const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
-  int grid = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles
-  dim3 cluster(1, 1, 1);
-  if (op.npre > 0) {
-    // fused prep: one tile per CTA, the N tiles of a row block are one cluster (any number of waves is fine: clusters are independent)
-    if (op.cn != op.N / BN_ || op.cn > kMaxPipCluster) { set_error("gemm_tc: fused prep needs the %d N tiles of a row block in one cluster", op.N / BN_); return -1; }
-    grid = tiles;
-    cluster.x = (unsigned)op.cn;
-  }
-  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, LNF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, cluster, op);
+  // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles; panel mode: one tile per CTA
+  const int grid = (XF && op.xmode) ? tiles : (tiles < sm_count() ? tiles : sm_count());
+  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF, XF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -719,19 +839,20 @@ void plan_gemm(GemmOp& op) {
   // N tile: 64 wide (more, smaller tiles balance better over the persistent CTAs); the GEGLU epilogue pairs
   // value|gate inside a 128-column block and needs BN = 128.
   op.bn = (op.flags & EPI_GEGLU) ? 128 : 64;
-  op.cn = op.npre > 0 ? op.N / op.bn : 1;
 }
 
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
-  if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
   const bool lnf = (op.flags & EPI_LNFOLD) != 0;
-  if (op.bn == 128) {
-    if (op.npre) { set_error("gemm_tc: fused prep is not available for GEGLU tiles"); return -1; }
-    return lnf ? launch_bn<128, true>(op, st) : launch_bn<128, false>(op, st);
+  if (op.xmode) {
+    if (lnf || op.bn != 64 || op.nxs < 1 || op.nxs > kMaxXSeg) { set_error("gemm_tc: panel mode needs a plain 64-wide tile and 1..%d segments", kMaxXSeg); return -1; }
+    if (op.pre == nullptr) { set_error("gemm_tc: panel mode without GroupNorm parameters"); return -1; }
+    return launch_bn<64, false, true>(op, st);
   }
+  if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
+  if (op.bn == 128) return lnf ? launch_bn<128, true, false>(op, st) : launch_bn<128, false, false>(op, st);
   if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
-  return lnf ? launch_bn<64, true>(op, st) : launch_bn<64, false>(op, st);
+  return lnf ? launch_bn<64, true, false>(op, st) : launch_bn<64, false, false>(op, st);
 }
 
 }  // namespace ns2vc

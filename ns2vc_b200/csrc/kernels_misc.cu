@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   extern __shared__ float aff[];                         // [2][C] scale | shift of this block's batch entry
   const int C = op.C1 + op.C2;
   float pg[kPrepSlots], pb[kPrepSlots];
-  prep_fetch_norm_weights(op, C, pg, pb);                // weights: before griddepcontrol.wait
+  prep_fetch_norm_weights(op, C, pg, pb, threadIdx.x, blockDim.x);   // weights: before griddepcontrol.wait
   pdl_wait();
   const int b = blockIdx.y;
   const int chunks = op.out.ld >> 3;                     // 8-channel chunks per output row (incl. zero padding)
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(256) prep_split_kernel(PrepOp op) {
   const bool have = i < total;
   if (have) prep_load_at(op, b, C, i / chunks, i % chunks, k0);
   float fs[kPrepSlots], fb[kPrepSlots];
-  prep_fetch_film(op, op.gn.film, b, C, fs, fb);
-  prep_affine(op, b, C, aff, pg, pb, fs, fb);
+  prep_fetch_film(op, op.gn.film, b, C, fs, fb, threadIdx.x, blockDim.x);
+  prep_affine(op, b, C, C, aff, pg, pb, fs, fb, threadIdx.x, blockDim.x, BlockSync());
   if (have) prep_finish(op, b, C, aff, k0);
   for (i += stride; i < total; i += stride) {
     PrepChunk k;

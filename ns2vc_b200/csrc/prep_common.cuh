@@ -65,52 +65,57 @@ __device__ __forceinline__ void prep_finish(const PrepOp& op, int b, int C, cons
   *reinterpret_cast<uint4*>(op.out.lo + orow * op.out.ld + k.c0) = lo;
 }
 
+// The affine is derived by a group of `nthr` threads (the whole block of the prep kernel, or the 8 transform warps of the
+// GEMM) identified by tid in [0, nthr); `sync` is that group's barrier.
+struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+
 // GroupNorm gamma / beta are weights: they can be fetched before the producer of the activations has finished.
-__device__ __forceinline__ void prep_fetch_norm_weights(const PrepOp& op, int C, float* pg, float* pb) {
+__device__ __forceinline__ void prep_fetch_norm_weights(const PrepOp& op, int C, float* pg, float* pb, int tid, int nthr) {
 #pragma unroll
   for (int k = 0; k < kPrepSlots; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = tid + k * nthr;
     const bool ok = op.mode != PREP_RAW && !op.scale && c < C;
     pg[k] = ok ? __ldg(op.gn.gamma + c) : 0.f;
     pb[k] = ok ? __ldg(op.gn.beta + c) : 0.f;
   }
 }
 
-// Per-(b, channel) scale / shift of the whole block's batch entry into aff[0..2C) (uses aff[2C .. 2C + 2G) as scratch).
-// GroupNorm finalise from the per-channel sums the producer epilogues accumulated (reference nn.GroupNorm: biased
-// variance over T x C/G elements; resnet.py:536,557, transformer_1d.py:134), then (1 + scale) / shift of the FiLM row
-// (resnet.py:627-629).  Called by every thread of the block; ends with a __syncthreads().
 // FiLM rows are produced by the timestep path (an earlier kernel): fetched right after the dependency wait, in flight together
 // with the statistics and the first activation loads instead of behind the group reduction.
-__device__ __forceinline__ void prep_fetch_film(const PrepOp& op, const float* film, int b, int C, float* fs, float* fb) {
+__device__ __forceinline__ void prep_fetch_film(const PrepOp& op, const float* film, int b, int C, float* fs, float* fb, int tid, int nthr) {
 #pragma unroll
   for (int k = 0; k < kPrepSlots; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = tid + k * nthr;
     const bool ok = film && op.mode != PREP_RAW && !op.scale && c < C;
     fs[k] = ok ? 1.f + film[(long long)b * op.gn.film_ld + c] : 1.f;
     fb[k] = ok ? film[(long long)b * op.gn.film_ld + C + c] : 0.f;
   }
 }
 
-__device__ __forceinline__ void prep_affine(const PrepOp& op, int b, int C, float* aff, const float* pg, const float* pb,
-                                            const float* fs, const float* fb) {
+// Per-(b, channel) scale / shift of batch entry b into aff[0..C) | aff[Cs..Cs+C) (Cs = stride of the shift row; uses
+// aff[2*Cs .. 2*Cs + 2G) as scratch).  GroupNorm finalise from the per-channel sums the producer epilogues accumulated
+// (reference nn.GroupNorm: biased variance over T x C/G elements; resnet.py:536,557, transformer_1d.py:134), then
+// (1 + scale) / shift of the FiLM row (resnet.py:627-629).  Called by every thread of the group; ends with sync().
+template <class Sync>
+__device__ __forceinline__ void prep_affine(const PrepOp& op, int b, int C, int Cs, float* aff, const float* pg, const float* pb,
+                                            const float* fs, const float* fb, int tid, int nthr, Sync sync) {
   if (op.mode == PREP_RAW) return;
   if (op.scale) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { aff[c] = op.scale[(long long)b * C + c]; aff[C + c] = op.shift[(long long)b * C + c]; }
+    for (int c = tid; c < C; c += nthr) { aff[c] = op.scale[(long long)b * C + c]; aff[Cs + c] = op.shift[(long long)b * C + c]; }
   } else {
     const GnStats& g = op.gn;
     const int cpg = C / g.G;
-    float* gmean = aff + 2 * C;                          // [G] mean | [G] rstd
-    for (int grp = threadIdx.x >> 5; grp < g.G; grp += blockDim.x >> 5) {
+    float* gmean = aff + 2 * Cs;                         // [G] mean | [G] rstd
+    for (int grp = tid >> 5; grp < g.G; grp += nthr >> 5) {
       double s = 0, q = 0;
-      for (int ii = threadIdx.x & 31; ii < cpg; ii += 32) {
+      for (int ii = tid & 31; ii < cpg; ii += 32) {
         const int c = grp * cpg + ii;
         s += (c < op.C1) ? g.sum1[(long long)b * op.C1 + c] : g.sum2[(long long)b * op.C2 + (c - op.C1)];
         q += (c < op.C1) ? g.sq1[(long long)b * op.C1 + c] : g.sq2[(long long)b * op.C2 + (c - op.C1)];
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-      if ((threadIdx.x & 31) == 0) {
+      if ((tid & 31) == 0) {
         const double inv = 1.0 / ((double)op.T_src * cpg);
         const double mean = s * inv;
         double var = q * inv - mean * mean;
@@ -119,10 +124,10 @@ __device__ __forceinline__ void prep_affine(const PrepOp& op, int b, int C, floa
         gmean[g.G + grp] = rsqrtf((float)var + g.eps);
       }
     }
-    __syncthreads();
+    sync();
 #pragma unroll
     for (int k = 0; k < kPrepSlots; ++k) {
-      const int c = threadIdx.x + k * blockDim.x;
+      const int c = tid + k * nthr;
       if (c >= C) break;
       const int grp = c / cpg;
       float ga = pg[k] * gmean[g.G + grp];
@@ -130,10 +135,10 @@ __device__ __forceinline__ void prep_affine(const PrepOp& op, int b, int C, floa
       ga = ga * fs[k];                                       // FiLM: x * (1 + scale) + shift (identity when there is none)
       be = be * fs[k] + fb[k];
       aff[c] = ga;
-      aff[C + c] = be;
+      aff[Cs + c] = be;
     }
   }
-  __syncthreads();
+  sync();
 }
 
 // Shared-memory floats prep_affine() needs for C channels

@@ -27,7 +27,7 @@ _lib.check(L.ns2vc_unet_set_trace(h, None, 0))
 full = buf.view(n, 32).cpu()
 tr = full[:, :8]
 keep = tr[:, 0] > 0
-tr = tr[keep]; ep = full[keep][:, 8:16]; pp = full[keep][:, 16:22]
+tr = tr[keep]; ep = full[keep][:, 8:16]; pp = full[keep][:, 16:21]
 t00 = int(tr[0, 0])
 names = ["entry", "prologue_done", "pdl_wait_done", "first_full", "mma_issued", "acc_ready", "epi_done", "exit"]
 print("idx start_us " + " ".join(f"d_{n}" for n in names[1:]) + " gap_from_prev_exit")
@@ -56,8 +56,8 @@ for i in range(ep.shape[0]):
         if e[j]: acc[j] += d[j]; cnt[j] += 1
 print("mean " + " ".join(f"{(acc[j] / cnt[j] if cnt[j] else 0):12.0f}" for j in range(1, 8)))
 
-pn = ["wait_done", "loads_issued", "affine_ready", "rows_stored", "preps_done", "published"]
-print("fused prep (us since kernel entry; thread 0 of CTA 0), then first_full / acc_ready / exit of the same launch:")
+pn = ["wait_done", "affine_ready", "panel0_full", "panel0_done", "panels_done"]
+print("panel mode (us since kernel entry; first transform thread of CTA 0), then first MMA / acc_ready / exit of the same launch:")
 print("idx " + " ".join(f"{n:>13s}" for n in pn) + "    first_full    acc_ready         exit")
 k = 0
 for i in range(tr.shape[0]):
