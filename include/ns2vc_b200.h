@@ -121,6 +121,10 @@ int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet
 int ns2vc_nearest_index(int t_in, int t_out, int* idx /* [t_out] */);
 int ns2vc_down_length(int t);
 
+/* encoder_attention_mask -> additive attention bias, (1 - m) * -10000 (reference unet_1d_condition.py:816-818): the kernel
+ * prepare_cond runs, exposed for the bit-exact test.  mask [n] uint8 device, bias [n] fp32 device. */
+int ns2vc_mask_bias(const uint8_t* mask, int n, float* bias, ns2vc_stream stream);
+
 /* Diagnostics used by the parity tests. */
 int ns2vc_unet_num_taps(const ns2vc_unet* h);
 int ns2vc_unet_tap_info(const ns2vc_unet* h, int i, const char** name, int* level, int* channels);

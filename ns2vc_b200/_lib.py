@@ -56,6 +56,7 @@ SIGNATURES = {
     "ns2vc_unet_forward_film": (C.c_int, [_P, _P, C.c_longlong, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "ns2vc_dpm_step": (C.c_int, [_P, _P, _P, C.POINTER(DpmCoef), _P, _P, C.c_size_t, _P, _P]),
     "ns2vc_unipc_step": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(UniPcCoef), _P, _P, _P, C.c_size_t, _P, _P]),
+    "ns2vc_mask_bias": (C.c_int, [_P, C.c_int, _P, _P]),
     "ns2vc_nearest_index": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ns2vc_down_length": (C.c_int, [C.c_int]),
     "ns2vc_unet_num_taps": (C.c_int, [_P]),

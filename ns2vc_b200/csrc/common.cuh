@@ -257,7 +257,9 @@ int launch_ln_apply(const float* x, int ld, int M, int C, float eps, const float
 int launch_nct_to_tokens(const float* x, long long bstride, int B, int C, int T, float* out, int ldo, int Cpad,
                          cudaStream_t st);
 // [B, C, T] fp32 -> split token-major [B, T, out.ld] (channels >= C zero-filled up to out.ld)
-int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st);
+// warm / warm_bytes: optional region prefetched into L2 by the same launch (the step's FiLM rows)
+int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st, const void* warm = nullptr,
+                        long long warm_bytes = 0);
 // token-major [B, T, ld] -> [B, C, T]
 int launch_tokens_to_nct(const float* x, int ld, int B, int C, int T, float* out, cudaStream_t st);
 

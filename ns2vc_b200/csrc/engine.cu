@@ -1080,7 +1080,8 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
       case Launch::NCT2SPLIT: {
         const float* src = (l.patch == 1) ? x : content;
         const long long bs = (l.patch == 1) ? x_bstride : content_bstride;
-        rc = launch_nct_to_split(src, bs, h->pB, l.i0, l.i1, l.split, st);
+        const bool warm = l.patch == 1 && film_ext != nullptr;
+        rc = launch_nct_to_split(src, bs, h->pB, l.i0, l.i1, l.split, st, warm ? film_ext : nullptr, warm ? (long long)h->pB * h->film_total * 4 : 0);
         break;
       }
       case Launch::PREP: {
@@ -1362,6 +1363,11 @@ int ns2vc_unipc_step(const float* x_prev, const float* x_eval, const float* unet
   k.alpha_t = c->alpha_t; k.sigma_t = c->sigma_t; k.c_x = c->c_x; k.c_m = c->c_m; k.ab = c->ab; k.rk = c->rk; k.rho0 = c->rho0; k.rho1 = c->rho1;
   k.corr_order = c->corr_order; k.n_c_x = c->n_c_x; k.n_c_m = c->n_c_m; k.nab = c->nab; k.nrk = c->nrk; k.pred_order = c->pred_order;
   return launch_unipc_step(x_prev, x_eval, unet_out, m0, m1, k, m_t, x_t, x_pred, n, nan_flag, (cudaStream_t)stream);
+}
+
+int ns2vc_mask_bias(const uint8_t* mask, int n, float* bias, ns2vc_stream stream) {
+  NS_REQUIRE(mask && bias && n >= 0, "bad argument");
+  return launch_mask_bias(mask, n, bias, (cudaStream_t)stream);
 }
 
 int ns2vc_unet_num_taps(const ns2vc_unet* h) { return h ? (int)h->tap_names.size() : -1; }

@@ -382,39 +382,47 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if (xs.xf) {
             uint8_t* p_hi = smem + sa * kXAStageBytes;
             uint8_t* p_lo = p_hi + kPanelBytes;
-            auto xform = [&](int r, uint4& h4, uint4& l4) {     // one 16-byte chunk (8 channels) of row r, in place
+            auto xform = [&](int r, uint4& h4, uint4& l4) {     // one 16-byte chunk (8 channels) of row r, in place (branch-free)
               const int t = tfirst + r;
+              const float keep = (t >= 0 && t < Tsrc) ? 1.f : 0.f;   // rows outside the sequence: the conv's zero padding (of the NORMALISED activation)
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
               float v[8];
-              if (t >= 0 && t < Tsrc) {
-                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float x0, x1;
-                  upk2(fadd2(pk2(__uint_as_float(hw[j] << 16), __uint_as_float(hw[j] & 0xffff0000u)),
-                             pk2(__uint_as_float(lw[j] << 16), __uint_as_float(lw[j] & 0xffff0000u))), x0, x1);
-                  float y0, y1;
-                  upk2(ffma2(pk2(x0, x1), pk2(scv[2 * j], scv[2 * j + 1]), pk2(shv[2 * j], shv[2 * j + 1])), y0, y1);
-                  if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-                  v[2 * j] = y0; v[2 * j + 1] = y1;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.f;     // rows outside the sequence: the conv's zero padding (of the NORMALISED activation)
+              for (int j = 0; j < 4; ++j) {
+                float x0, x1;
+                upk2(fadd2(pk2(__uint_as_float(hw[j] << 16), __uint_as_float(hw[j] & 0xffff0000u)),
+                           pk2(__uint_as_float(lw[j] << 16), __uint_as_float(lw[j] & 0xffff0000u))), x0, x1);
+                float y0, y1;
+                upk2(ffma2(pk2(x0, x1), pk2(scv[2 * j], scv[2 * j + 1]), pk2(shv[2 * j], shv[2 * j + 1])), y0, y1);
+                if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+                v[2 * j] = y0 * keep; v[2 * j + 1] = y1 * keep;
               }
               split8(v, h4, l4);
             };
-            const int nrow = rows;                          // 130 or 128; this thread: rows (xt >> 3) + 32 k
-            for (int r0 = xt >> 3; r0 < nrow; r0 += 64) {    // two rows per iteration: independent chains
-              const int r1 = r0 + 32;
-              const int off0 = r0 * 128 + ((q ^ (r0 & 7)) << 4), off1 = r1 * 128 + ((q ^ (r1 & 7)) << 4);
-              const bool two = r1 < nrow;
-              uint4 h0 = *reinterpret_cast<const uint4*>(p_hi + off0), l0 = *reinterpret_cast<const uint4*>(p_lo + off0);
-              uint4 h1 = make_uint4(0, 0, 0, 0), l1 = make_uint4(0, 0, 0, 0);
-              if (two) { h1 = *reinterpret_cast<const uint4*>(p_hi + off1); l1 = *reinterpret_cast<const uint4*>(p_lo + off1); }
-              xform(r0, h0, l0);
-              if (two) xform(r1, h1, l1);
-              *reinterpret_cast<uint4*>(p_hi + off0) = h0; *reinterpret_cast<uint4*>(p_lo + off0) = l0;
-              if (two) { *reinterpret_cast<uint4*>(p_hi + off1) = h1; *reinterpret_cast<uint4*>(p_lo + off1) = l1; }
+            // this thread: chunk column q of rows r, r + 32, r + 64, r + 96 (always inside the panel) - four independent
+            // chains in flight - and of row r + 128 for the two halo rows of a k=3 panel
+            const int rb = xt >> 3;
+            uint4 h4[4], l4[4];
+            int off[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = rb + 32 * u;
+              off[u] = r * 128 + ((q ^ (r & 7)) << 4);
+              h4[u] = *reinterpret_cast<const uint4*>(p_hi + off[u]);
+              l4[u] = *reinterpret_cast<const uint4*>(p_lo + off[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xform(rb + 32 * u, h4[u], l4[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(p_hi + off[u]) = h4[u];
+              *reinterpret_cast<uint4*>(p_lo + off[u]) = l4[u];
+            }
+            if (rb + 128 < rows) {
+              const int r = rb + 128, o = r * 128 + ((q ^ (r & 7)) << 4);
+              uint4 hh = *reinterpret_cast<const uint4*>(p_hi + o), ll = *reinterpret_cast<const uint4*>(p_lo + o);
+              xform(r, hh, ll);
+              *reinterpret_cast<uint4*>(p_hi + o) = hh; *reinterpret_cast<uint4*>(p_lo + o) = ll;
             }
             fence_proxy_async();
           }

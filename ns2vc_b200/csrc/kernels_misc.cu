@@ -265,8 +265,15 @@ int launch_ln_split(const float* x, int ld, int M, int C, float eps, const float
 }
 
 // [B, C, T] fp32 -> split token-major [B, T, out.ld]; 32x32 smem transpose, zero-fills c >= C.
-__global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstride, int C, int T, SplitBuf out) {
+__global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstride, int C, int T, SplitBuf out,
+                                    const char* warm, long long warm_bytes) {
   pdl_trigger();
+  // first kernel of a forward: pull this step's FiLM rows (a slice of the run's timestep table, cold in L2) towards L2 so that
+  // the 22 conv2 launches that read them later do not each wait for HBM
+  if (warm) {
+    const long long line = ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
+    if (line * 128 < warm_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(warm + line * 128));
+  }
   pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -288,9 +295,10 @@ __global__ void nct_to_split_kernel(const float* __restrict__ x, long long bstri
     }
   }
 }
-int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st) {
+int launch_nct_to_split(const float* x, long long bstride, int B, int C, int T, SplitBuf out, cudaStream_t st, const void* warm,
+                        long long warm_bytes) {
   dim3 grid(ceil_div(T, 32), ceil_div(out.ld, 32), B), block(32, 8);
-  launch_k(nct_to_split_kernel, grid, block, 0, st, x, bstride, C, T, out);
+  launch_k(nct_to_split_kernel, grid, block, 0, st, x, bstride, C, T, out, (const char*)warm, warm_bytes);
   NS_LAUNCH_CHECK();
   return 0;
 }

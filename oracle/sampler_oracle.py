@@ -170,3 +170,29 @@ class OracleDDPM:
         mean = self.coef1[bt][:, None, None] * x0 + self.coef2[bt][:, None, None] * x
         nz = noise if t > 0 else 0.0
         return mean + (0.5 * self.log_var[bt][:, None, None]).exp() * nz
+
+
+def ddim_sample(x_start_fn: Callable, alphas_cumprod: torch.Tensor, x: torch.Tensor, total_timesteps: int, sampling_timesteps: int,
+                eta: float = 0.0) -> torch.Tensor:
+    """NaturalSpeech2.ddim_sample after pre_model.infer (reference model.py:570-603), eta = 0 (the reference's default,
+    :446): integer timesteps linspace(-1, T-1, S+1) reversed; x0 = model(x, t); noise = predict_noise_from_start (:498-503);
+    x <- sqrt(a_next) x0 + sqrt(1 - a_next) noise; the last pair (t, -1) returns x0."""
+    assert eta == 0.0
+    times = torch.linspace(-1, total_timesteps - 1, steps=sampling_timesteps + 1)
+    times = list(reversed(times.int().tolist()))
+    sqrt_recip = torch.sqrt(1.0 / alphas_cumprod).to(torch.float32)
+    sqrt_recipm1 = torch.sqrt(1.0 / alphas_cumprod - 1).to(torch.float32)
+    ac32 = alphas_cumprod.to(torch.float32)
+    B = x.shape[0]
+    for time, time_next in zip(times[:-1], times[1:]):
+        bt = torch.full((B,), time, dtype=torch.long)
+        x0 = x_start_fn(x, bt)
+        pred_noise = (sqrt_recip[bt][:, None, None] * x - x0) / sqrt_recipm1[bt][:, None, None]
+        if time_next < 0:
+            x = x0
+            continue
+        alpha, alpha_next = ac32[time], ac32[time_next]
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = (1 - alpha_next - sigma ** 2).sqrt()
+        x = x0 * alpha_next.sqrt() + c * pred_noise
+    return x

@@ -330,3 +330,192 @@ def test_weights_repack_after_update(full_model):
     ok, msg = close(b, ref)
     assert ok, msg
     assert not torch.allclose(a, b)
+
+
+# ------------------------------------------------------------------ BASELINE cfg1 / DDIM through the generic forward
+def test_cfg1_one_layer_unet_ten_p_sample_steps(gold):
+    """BASELINE.json configs[0] exactly: layers_per_block=1, B=1, C=100, T=128, S=64, DDPM p_sample t = 999 .. 990
+    (model.py:535-542) with injected noise; every intermediate latent against the reference's own run."""
+    from oracle.make_golden_cfg1 import cfg1_config
+    g = gold("cfg1_p_sample.pt")
+    m, _ = make_unet(cfg1_config())
+    inp = make_inputs(1, 128, 64, seed=g["seed_inputs"])
+    fn = _closure(m, inp)
+    ddpm = sampler_oracle.OracleDDPM(1000)
+    x = inp["x"].cuda()
+    with torch.no_grad():
+        for i, t in enumerate(range(999, 989, -1)):
+            noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(g["noise_seed0"] + i)).cuda()
+            bt = torch.full((1,), t, dtype=torch.long, device="cuda")
+            x0 = fn(x, bt)
+            mean = ddpm.coef1.cuda()[bt][:, None, None] * x0 + ddpm.coef2.cuda()[bt][:, None, None] * x
+            x = mean + (0.5 * ddpm.log_var.cuda()[bt][:, None, None]).exp() * noise
+            ok, msg = close(x, g["xs"][i])
+            assert ok, f"step {i}: {msg}"
+
+
+def test_ddim_sample_through_generic_forward(gold, full_model):
+    """NaturalSpeech2.ddim_sample (model.py:563-603; 6 steps, eta 0): integer timesteps through UNet.forward, fixture from the
+    reference's own ddim_sample."""
+    g = gold("ddim.pt")
+    m, _ = full_model
+    inp = make_inputs(2, 72, 24, ragged=True, seed=g["seed_inputs"])
+    fn = _closure(m, inp)
+    with torch.no_grad():
+        out = sampler_oracle.ddim_sample(lambda x, t: fn(x.cuda(), t.cuda()).cpu(), g["alphas_cumprod"], inp["x"], 1000, g["steps"])
+    ok, msg = close(out, g["out"])
+    assert ok, msg
+
+
+# ------------------------------------------------------------------ small pieces that used to be checked only through the outputs
+def test_mask_bias_bit_exact():
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(7)
+    mask = (torch.rand(3, 257, generator=g) > 0.4)
+    m8 = mask.to(torch.uint8).cuda()
+    bias = torch.empty(mask.shape, dtype=torch.float32, device="cuda")
+    _lib.check(L.ns2vc_mask_bias(m8.data_ptr(), m8.numel(), bias.data_ptr(), None))
+    torch.cuda.synchronize()
+    want = (1 - mask.to(torch.float32)) * -10000.0          # reference unet_1d_condition.py:817
+    assert torch.equal(bias.cpu(), want)
+
+
+def test_timestep_table_matches_reference_embeddings(gold):
+    """emb = time_embedding(t) + add_embedding(prompt) of the tiny fixture (taps 'emb', 'aug_emb' recorded from the reference's
+    forward hooks) pushed through every resnet's time_emb_proj: the rows ns2vc_unet_time_table() produces."""
+    from ns2vc_b200.arch import build_plan
+    g = gold("tiny_forward.pt")
+    cfg = tiny_config()
+    m, sd = make_unet(cfg)
+    inp = tiny_inputs()
+    sess = _session(m, inp)
+    sess.prepare()
+    L = _lib.lib()
+    B = 2
+    tv = g["t"].to(torch.float32).cuda().contiguous()
+    table = torch.empty(int(L.ns2vc_unet_time_table_floats(sess.h, B)), dtype=torch.float32, device="cuda")
+    sess.time_table(tv.view(1, B), table)
+    torch.cuda.synchronize()
+    fw = int(L.ns2vc_unet_film_width(sess.h))
+    film = table[:B * fw].view(B, fw).cpu()
+    emb = g["taps"]["emb"]
+    want = torch.cat([torch.nn.functional.linear(torch.nn.functional.silu(emb), sd[op.prefix + ".time_emb_proj.weight"], sd[op.prefix + ".time_emb_proj.bias"])
+                      for op in build_plan(cfg) if op.kind == "resnet"], dim=1)
+    assert film.shape == want.shape
+    ok, msg = close(film, want, rtol=1e-4, atol=1e-5)
+    assert ok, msg
+
+
+# ------------------------------------------------------------------ drop-in semantics of the fused path
+def test_fresh_schedule_objects_share_one_graph_and_other_betas_do_not(gold):
+    """model.py:621-622 builds a NEW NoiseScheduleVP in every sample(): the captured loop must be found by schedule CONTENT
+    (replayed, same result), and a different beta table must neither hit that entry nor reuse its coefficients."""
+    g = gold("tiny_samplers.pt")
+    m, _ = make_unet(tiny_config())
+    inp = tiny_inputs()
+    x0 = inp["x"].cuda()
+
+    def run(betas):
+        ns = our_dpm.NoiseScheduleVP("discrete", betas=betas)          # fresh object every call, as the reference does
+        mf = our_dpm.model_wrapper(_closure(m, inp), ns, model_type="x_start", model_kwargs={})
+        return our_dpm.DPM_Solver(mf, ns, algorithm_type="dpmsolver++").sample(x0, steps=12, order=2, skip_type="time_uniform", method="multistep")
+    with torch.no_grad():
+        outs = [run(linear_betas(1000).cuda()) for _ in range(3)]
+    sessions = list(m.__dict__["_sessions"].values())
+    assert len(sessions) == 1
+    ents = list(sessions[0]._graphs.values())
+    assert len(ents) == 1 and ents[0]["graph"] is not None, "three calls with fresh schedule objects must end up replaying one captured loop"
+    for o in outs:
+        ok, msg = close(o, g["dpmpp2m_12"])
+        assert ok, msg
+    assert torch.equal(outs[1], outs[2])
+    # a different schedule: own entry, own coefficients; must agree with the generic Python loop for THAT schedule
+    betas2 = torch.linspace(2e-4, 0.03, 1000, dtype=torch.float64).to(torch.float32).cuda()
+    with torch.no_grad():
+        o2 = run(betas2)
+        os.environ["NS2VC_B200_FUSED"] = "0"
+        try:
+            o2_generic = run(betas2)
+        finally:
+            os.environ.pop("NS2VC_B200_FUSED")
+    assert len(sessions[0]._graphs) == 2
+    assert not torch.allclose(o2, outs[0], atol=1e-3)
+    ok, msg = close(o2, o2_generic)
+    assert ok, "second schedule, fused vs generic: " + msg
+    assert len(sessions[0]._graphs) <= sessions[0].MAX_GRAPHS
+
+
+def test_nan_input_raises_like_the_reference():
+    """model.py:404 asserts on NaN in the denoiser input every call; the fused loop checks a device flag once per run."""
+    m, _ = make_unet(tiny_config())
+    inp = tiny_inputs()
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    x = inp["x"].cuda().clone()
+    ok = sess.sample_dpmpp_2m(x, ns, torch.linspace(1.0, 1e-3, 11))
+    assert torch.isfinite(ok).all()
+    x[1, 3, 5] = float("nan")
+    for _ in range(3):                                   # eager, capture, replay
+        with pytest.raises(AssertionError):
+            sess.sample_dpmpp_2m(x, ns, torch.linspace(1.0, 1e-3, 11))
+    assert torch.isfinite(sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 11))).all()
+
+
+# ------------------------------------------------------------------ the benchmark shapes end to end
+def test_fused_dpm_50_steps_T1024_vs_oracle(full_model):
+    """cfg2's sequence length and prompt length (B=1): 50-step DPM-Solver++(2M) against the CPU oracle loop."""
+    m, sd = full_model
+    cfg = ns2vc_denoiser_config()
+    inp = make_inputs(1, 1024, 256, seed=51)
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 51))
+    sch = sampler_oracle.OracleSchedule(linear_betas(1000))
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    with torch.no_grad():
+        ref = sampler_oracle.dpmpp_2m(fn, sch, inp["x"], 50)
+    ok, msg = close(out, ref)
+    assert ok, msg
+
+
+def test_fused_unipc_30_steps_T2048_vs_oracle(full_model):
+    """cfg3's sequence length (B=1, T=2048, S=256): UniPC bh2, the reference's default 30 steps."""
+    m, sd = full_model
+    cfg = ns2vc_denoiser_config()
+    inp = make_inputs(1, 2048, 256, seed=52)
+    ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
+    sess = _session(m, inp)
+    out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 31))
+    sch = sampler_oracle.OracleSchedule(linear_betas(1000))
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    with torch.no_grad():
+        ref = sampler_oracle.unipc_bh(fn, sch, inp["x"], 30)
+    ok, msg = close(out, ref)
+    assert ok, msg
+
+
+# ------------------------------------------------------------------ numerics under stress
+@pytest.mark.parametrize("gain,offset", [(3.0, 0.0), (1.0, 30.0), (3.0, 30.0)])
+def test_forward_with_large_gain_weights_and_offset_activations(gain, offset):
+    """3xBF16 GEMMs, folded LayerNorms (rstd * (x W' - mean g): cancellation grows with |row mean| / std) and the fp16-P / fp16-V
+    attention under weights of `gain` x the synthetic scale and a per-channel offset on the residual stream (the proj_in bias of
+    every transformer, so LayerNorm rows have |mean| >> std).  Reports err / tol; must stay inside the contract."""
+    cfg = ns2vc_denoiser_config()
+    sd = make_state_dict(cfg, 0)
+    for k in sd:
+        if k.endswith(".weight") and sd[k].dim() >= 2 and ".norm" not in k:
+            sd[k] = sd[k] * gain ** 0.25                       # four-ish contractions deep per block: keeps activations finite
+        if offset and k.endswith("proj_in.bias"):
+            sd[k] = sd[k] + offset
+    m, _ = make_unet(cfg)
+    m.load_state_dict(sd)
+    inp = make_inputs(2, 200, 40, ragged=True, seed=61)
+    x, ehs, mask = unet_inputs(inp)
+    t = torch.tensor([731.0, 12.5], device="cuda")
+    with torch.no_grad():
+        out = m(x, t, ehs, encoder_attention_mask=mask).sample.cpu()
+        ref = unet_oracle.unet_forward(sd, cfg, x.cpu(), t.cpu(), ehs.cpu(), mask.cpu())
+    err = (out - ref).abs()
+    ratio = (err / (ATOL + RTOL * ref.abs())).max().item()
+    print(f"gain {gain} offset {offset}: max|err| {err.max().item():.3e}, ref rms {ref.pow(2).mean().sqrt().item():.3e}, worst err/tol {ratio:.2f}")
+    assert ratio <= 1.0, f"worst err/tol {ratio:.2f}"

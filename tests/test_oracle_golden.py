@@ -96,3 +96,31 @@ def test_p_sample(gold):
         noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i))
         x = ddpm.p_sample(fn, x, t, noise)
         assert torch.allclose(x, g["xs"][i], rtol=0, atol=1e-5)
+
+
+def test_cfg1_p_sample_ten_steps(gold):
+    """BASELINE.json configs[0]: 1-layer UNet, C=100, T=128, B=1, S=64, ten DDPM steps t = 999 .. 990 (fixture produced by the
+    reference's own p_sample, oracle/make_golden_cfg1.py)."""
+    from oracle.make_golden_cfg1 import cfg1_config
+    g = gold("cfg1_p_sample.pt")
+    cfg = cfg1_config()
+    sd = make_state_dict(cfg, 0)
+    assert state_dict_checksum(sd) == g["checksum"]
+    inp = make_inputs(1, 128, 64, seed=g["seed_inputs"])
+    ddpm = sampler_oracle.OracleDDPM(1000)
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    x = inp["x"]
+    for i, t in enumerate(range(999, 989, -1)):
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(g["noise_seed0"] + i))
+        x = ddpm.p_sample(fn, x, t, noise)
+        assert torch.allclose(x, g["xs"][i], rtol=0, atol=1e-5), i
+
+
+def test_ddim_sample(gold):
+    g = gold("ddim.pt")
+    cfg = ns2vc_denoiser_config()
+    sd = make_state_dict(cfg, 0)
+    inp = make_inputs(2, 72, 24, ragged=True, seed=g["seed_inputs"])
+    fn = lambda x, t: unet_oracle.denoiser_forward(sd, cfg, x, inp["content"], inp["prompt"], inp["refer_lengths"], t)
+    out = sampler_oracle.ddim_sample(fn, g["alphas_cumprod"], inp["x"], 1000, g["steps"])
+    assert torch.allclose(out, g["out"], rtol=0, atol=1e-5)
