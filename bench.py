@@ -30,6 +30,11 @@ sys.path.insert(0, REPO)
 B, T, S, NFE = 8, 1024, 256, 50
 METRIC = "denoiser-steps/s"
 UNIT = "denoiser-steps/s"
+# algorithmic work of one sample-step, F(T,S) FLOPs (conv + linear + QK^T/PV + the step-invariant K/V projections,
+# counted because the reference executes them every step), and the ideal-fusion byte count (3.20 GB per cfg2 step, fp32 I/O)
+def survey_flops(Bn, Tn, Sn):
+    return Bn * (31818240 * Tn + 4352 * Tn * Tn + 7296 * Sn * Tn + 4456448 * Sn)
+SURVEY_BYTES_CFG2 = 3.20e9
 
 
 def workload_cfg(n_gpus):
@@ -197,18 +202,26 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = B * per_step * args.steps / dt
+    # one COMPLETE 50-NFE DPM-Solver++(2M) run of the reference path (outside the timed steps): the whole-run rate
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        sampler_oracle.dpmpp_2m(fn, sch, inp["x"], NFE)
+    full_dt = time.perf_counter() - t1
     sample = f"{per_step} of {NFE} denoiser calls (UNet forward + x0 round trip) per step at B={B},T={T},S={S}; reference CPU path via the oracle port (reference is pure PyTorch; /root/reference is absent on the GPU box)"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args.gpus),
-                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                       "full_run": {"value": B * NFE / full_dt, "unit": UNIT, "seconds": full_dt, "what": f"one complete {NFE}-NFE DPM-Solver++(2M) run at B={B},T={T},S={S}"}},
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))
 
 
 def ncu_traffic(kernel):
     """Average DRAM bytes per launch of `kernel` from the committed ncu launch list (profiles/)."""
-    p = os.path.join(REPO, "profiles", "r01_traffic.json")
+    p = os.path.join(REPO, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(REPO, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
     tab = json.load(open(p))
@@ -236,7 +249,6 @@ def main():
     import torch.distributed as dist
     from ns2vc_b200 import _lib, api
     from ns2vc_b200.arch import ns2vc_denoiser_config
-    from ns2vc_b200.debug import profile_forward
     from ns2vc_b200.fused import DenoiserSession
     from ns2vc_b200.synth import make_state_dict
     from ns2vc_b200.unet import UNet1DConditionModel
@@ -327,37 +339,97 @@ def main():
            "ms_per_unet_forward": ms / args.steps / nfe}
 
     if rank == 0:
-        # ---- per-kernel timing of 3 forwards (CUDA events around every launch, on the launch stream)
+        # ---- in-step kernel times: [first CTA entry, last CTA exit] %globaltimer of every launch of ONE forward replayed from a
+        # CUDA graph (PDL overlap intact, no event bracketing).  A launch's EXCLUSIVE time = its exit minus max(its entry, the
+        # latest exit of the launches before it): the shares add up to the forward, so no kernel can be charged more than the step.
         sess = DenoiserSession(unet, content_d, prompt_d, mask_d)
         sess.prepare()
         tv = torch.full((B,), 500.0, device=dev)
         o = torch.empty_like(x_d)
-        nprof = 3
-        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-        prof = profile_forward(unet, lambda: [sess.forward(x_d, tv, o) for _ in range(nprof)], dev,
-                               dump_csv=os.path.join(REPO, "gpurun_out", "launch_times.csv"))
-        total = sum(v[0] for v in prof.values())
-        kernels = {k: {"ms_per_forward": v[0] / nprof, "launches_per_forward": v[1] // nprof, "share": v[0] / total} for k, v in prof.items()}
+        for _ in range(2):
+            sess.forward(x_d, tv, o)
+        torch.cuda.synchronize(dev)
+        nl = L.ns2vc_unet_launch_count(h)
+        span = torch.empty(nl * 2, dtype=torch.int64, device=dev)
+        sv = span.view(nl, 2)
+        _lib.check(L.ns2vc_unet_set_span_trace(h, span.data_ptr(), nl))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            sess.forward(x_d, tv, o)
+        _lib.check(L.ns2vc_unet_set_span_trace(h, None, 0))
+        g.replay(); torch.cuda.synchronize(dev)
+        sv[:, 0] = 0x7fffffffffffffff; sv[:, 1] = 0
+        torch.cuda.synchronize(dev)
+        g.replay(); torch.cuda.synchronize(dev)
+        tr = sv.cpu()
+        names = [L.ns2vc_profile_kind_name(L.ns2vc_unet_launch_kind(h, i)).decode() for i in range(nl)]
+        rows = [(names[i], int(tr[i, 0]), int(tr[i, 1])) for i in range(nl) if int(tr[i, 1]) > 0]
+        excl, dur, cnt = {}, {}, {}
+        prev_end = rows[0][1]
+        for k, a, e in rows:
+            x_us = max(0.0, (e - max(a, prev_end)) / 1e3)
+            excl[k] = excl.get(k, 0.0) + x_us; dur[k] = dur.get(k, 0.0) + (e - a) / 1e3; cnt[k] = cnt.get(k, 0) + 1
+            prev_end = max(prev_end, e)
+        span_us = (max(r[2] for r in rows) - rows[0][1]) / 1e3
+        kernels = {k: {"launches_per_forward": cnt[k], "exclusive_us_per_forward": excl[k], "span_sum_us_per_forward": dur[k],
+                       "share": excl[k] / span_us} for k in excl}
+        del g
         peaks = read_peaks()
         fl_gemm, fl_attn = flops_per_forward(cfg, B, T, S, gemm_only=True)
-        dom = max(prof, key=lambda k: prof[k][0])
+        fl_gemm += B * 4 * S * cfg.cross_attention_dim * sum(op.cout for op in __import__("ns2vc_b200.arch", fromlist=["build_plan"]).build_plan(cfg) if op.kind == "xformer")  # step-invariant K/V projections (SURVEY 8d counts them)
+        dom = max(excl, key=lambda k: excl[k])
+        dom_ms = excl[dom] / 1e3
+        assert dom_ms <= ms / args.steps / nfe * 1.25, "a kernel cannot take longer than the step it is part of"
         if dom == "attention":
-            ach = fl_attn / (prof[dom][0] / nprof * 1e-3) / 1e12
+            ach = fl_attn / (dom_ms * 1e-3) / 1e12
             alg = f"{fl_attn / 1e9:.1f} GFLOP QK^T+PV per forward"
         else:
             dom = "gemm_tc"
-            ach = fl_gemm / (prof[dom][0] / nprof * 1e-3) / 1e12
-            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic; the 3xBF16 split issues 3x this on the tensor pipe)"
+            ach = fl_gemm / (excl[dom] / 1e3 * 1e-3) / 1e12
+            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic, SURVEY 8d; the 3xBF16 split issues 3x this on the tensor pipe)"
         traffic = ncu_traffic(dom)
+        whole = survey_flops(B, T, S)
+        ms_fwd = ms / args.steps / nfe
+        t_hbm = SURVEY_BYTES_CFG2 / (peaks["hbm_gbs"] * 1e9) * 1e3
+        t_tc = whole / (peaks["tflops"] * 1e12) * 1e3
         out["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                           "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, cold-cache capture in profiles/r01_ncu_launches.md)", "algorithmic": alg, "peak_source": peaks["src"],
-                           "issued_tflops": 3 * ach if dom == "gemm_tc" else ach, "frac_issued": (3 * ach if dom == "gemm_tc" else ach) / peaks["tflops"],
-                           "note": "fp32-level parity forces 3 bf16 MMAs per product term set (hi*hi, hi*lo, lo*hi): issued = 3 x algorithmic; at M=128 tiles a tcgen05.mma costs ~80-110 cycles whatever its N (profiles/r01_*_incta_timeline.txt), so launches of <=148 tiles are bound by instruction count and the 335-launch dependency chain, not by the pipe's FLOP rate",
-                           "launch_avg_us": 1e3 * prof[dom][0] / prof[dom][1], "timing": f"CUDA events around each launch, {nprof} forwards, profiling pass outside the timed region"}
+                           "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, cold-cache capture, profiles/r02_ncu_launches.md)",
+                           "algorithmic": alg, "peak_source": peaks["src"], "issued_tflops": 3 * ach if dom == "gemm_tc" else ach,
+                           "frac_issued": (3 * ach if dom == "gemm_tc" else ach) / peaks["tflops"],
+                           "kernel_ms_per_forward": dom_ms, "launch_avg_us": excl[dom] / cnt[dom],
+                           "timing": "exclusive in-step time of the kernel's launches from %globaltimer [entry, exit] spans of one graph-replayed forward (sums to the forward; never above ms_per_unet_forward)",
+                           "step": {"ms_per_unet_forward": ms_fwd, "algorithmic_gflop": whole / 1e9, "algorithmic_gb": SURVEY_BYTES_CFG2 / 1e9,
+                                    "t_hbm_ms": t_hbm, "t_tc_ms": t_tc, "t_tc_ms_3xbf16_issued": 3 * t_tc,
+                                    "binding": "hbm" if t_hbm >= t_tc else "tensor", "frac_vs_binding": max(t_hbm, t_tc) / ms_fwd,
+                                    "achieved_tflops": whole / (ms_fwd * 1e-3) / 1e12, "achieved_gbs": SURVEY_BYTES_CFG2 / (ms_fwd * 1e-3) / 1e9,
+                                    "note": "SURVEY.md 8(d) constants: 40.20 GFLOP per sample-step (321.6 per cfg2 step), 3.20 GB ideal-fusion bytes; graded against the tighter (larger-time) bound"},
+                           "note": "the step is a chain of dependent launches (PDL-linked, one CUDA graph): launches of <= 148 tiles are bound by per-launch latency (TMA round trip, epilogue stores at L2 bandwidth), not by the pipe's FLOP rate"}
         out["kernels"] = kernels
-        whole = flops_per_forward(cfg, B, T, S)[0]
-        out["step_roofline"] = {"achieved_tflops": whole / (ms / args.steps / nfe * 1e-3) / 1e12, "algorithmic_gflop_per_forward": whole / 1e9,
-                                "t_hbm_ms_ideal_fusion": 3.20e9 / (peaks["hbm_gbs"] * 1e9) * 1e3, "t_tc_ms_3xbf16": 3 * whole / (peaks["tflops"] * 1e12) * 1e3}
+        out["forward_span_us"] = span_us
+        # ---- cfg3 (BASELINE.json configs[2]): B=4, T=2048, UniPC bh2 at the reference default of 30 steps and at 50, same process
+        try:
+            from ns2vc_b200.synth import make_inputs
+            c3 = make_inputs(4, 2048, S, seed=3)
+            c3s = DenoiserSession(unet, c3["content"].permute(1, 2, 0).contiguous().to(dev), c3["prompt"].permute(1, 0, 2).contiguous().to(dev),
+                                  api.sequence_mask(c3["refer_lengths"].to(dev), S))
+            x3 = c3["x"].to(dev)
+            cfg3 = {}
+            for n3 in (30, 50):
+                ts3 = torch.linspace(1.0, 1e-3, n3 + 1)
+                for _ in range(3):
+                    c3s.sample_unipc(x3, ns, ts3)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    c3s.sample_unipc(x3, ns, ts3)
+                e1.record(); torch.cuda.synchronize(dev)
+                m3 = e0.elapsed_time(e1) / 2
+                cfg3[f"unipc_{n3}"] = {"value": 4 * n3 / (m3 / 1e3), "unit": UNIT, "ms_per_run": m3, "ms_per_unet_forward": m3 / n3}
+            out["cfg3"] = {"workload": f"cfg3: B=4, C=100, T=2048, S={S}, UniPC bh2 (order 2), 1 GPU, device-resident inputs", **cfg3}
+            del c3s
+        except Exception as e:                                   # the extra key must never cost the headline line
+            out["cfg3"] = {"error": repr(e)}
         if world == 1:
             threads = best_thread_count()
             nf = 3

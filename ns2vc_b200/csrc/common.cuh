@@ -169,6 +169,8 @@ struct GemmOp {
   // the three taps of a k=3 conv are three row-shifted views of the same panel (descriptor start address + 128 B per row:
   // the 128B swizzle is a function of the shared-memory address bits), so a conv reads and normalises each activation once.
   int xmode;
+  int ksplit;                  // 1, or 2: the channel blocks are divided between the two CTAs of a cluster (few-tile, deep-K launches);
+                               // the second CTA ships its fp32 partial tile into the first one's shared memory, which runs the epilogue
   int nxs;
   XSeg xs[kMaxXSeg];
   const PrepOp* pre;           // GroupNorm parameters of the normalised segments (device memory; only the affine part is used)

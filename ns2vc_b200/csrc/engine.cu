@@ -137,6 +137,7 @@ struct ns2vc_unet {
   std::vector<Stash> stash;
   int last_launches = 0;
   bool profiling = false;
+  bool ksplit = true;        // split-K pairs for few-tile panel-mode launches (NS2VC_KSPLIT=0: one CTA per tile)
   bool xf = true;            // GroupNorm(+FiLM)(+SiLU) of the conv / proj_in inputs applied inside the GEMM (panel mode; NS2VC_XF=0: prep launches)
   bool merge_ff = true;      // ff.net.2 + proj_out as one GEMM (NS2VC_MERGE_FF=0: two launches)
   float* film_base = nullptr;        // FiLM rows of the active program (workspace), and the caller-supplied replacement for one forward
@@ -534,6 +535,7 @@ struct Builder {
     g.B = B; g.T_out = T_out;
     g.w_hi = w.hi; g.w_lo = w.lo; g.w_f32 = w.f32; g.N = w.Npad; g.n_valid = w.n_logical;
     g.f16_col0 = 0x7fffffff;
+    g.ksplit = 1;
     return g;
   }
   int add_src(GemmOp& g, const SplitBuf& s) { g.src[g.nsrc] = s; return g.nsrc++; }
@@ -548,6 +550,14 @@ struct Builder {
   }
   void emit_gemm(GemmOp& g, const PackedB& w, int patch = 0) {
     Launch l; l.kind = Launch::GEMM; l.patch = patch;
+    if (g.xmode && h->ksplit) {
+      // few-tile, deep-K launches (the two coarsest levels at B = 8: 64 tiles of 24-64 k-blocks each): two CTAs per tile, each
+      // half of the channel blocks; worth it when both halves still have a few panels and all pairs are resident at once
+      const int tiles = B * ceil_div(g.T_out, 128) * (w.Npad / 64);
+      int panels = 0;
+      for (int i = 0; i < g.nxs; ++i) panels += g.xs[i].ncb;
+      if (2 * tiles <= gemm_sm_count() && panels >= 8) g.ksplit = 2;
+    }
     if (!dry) {
       if (g.nkb_total != w.nkb) { fprintf(stderr, "ns2vc: internal K mismatch %d vs %d\n", g.nkb_total, w.nkb); abort(); }
       plan_gemm(g);
@@ -1211,6 +1221,7 @@ int ns2vc_unet_create(const ns2vc_unet_cfg* cfg, ns2vc_unet** out) {
   h->simt = be && strcmp(be, "simt") == 0;
   { const char* e = getenv("NS2VC_LNFOLD"); h->lnfold = !(e && e[0] == '0'); }
   { const char* e = getenv("NS2VC_XF"); h->xf = !(e && e[0] == '0'); }
+  { const char* e = getenv("NS2VC_KSPLIT"); h->ksplit = !(e && e[0] == '0'); }
   { const char* e = getenv("NS2VC_MERGE_FF"); h->merge_ff = !(e && e[0] == '0'); }
   build_plan(h);
   register_weights(h);

@@ -238,19 +238,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int tiles_per_batch = (op_param.T_out + BM - 1) / BM;
   const int n_tiles = op_param.N / BN;
   const int total_tiles = op_param.B * tiles_per_batch * n_tiles;
-  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // split-K (panel mode only): the `ks` CTAs of a cluster share one tile; kr = this CTA's share of the channel blocks
+  const int ks = (XF && op_param.xmode && op_param.ksplit > 1) ? op_param.ksplit : 1;
+  const int kr = (int)blockIdx.x % ks, bid = (int)blockIdx.x / ks, nblk = (int)gridDim.x / ks;
+  const int my_tiles = (total_tiles - bid + nblk - 1) / nblk;
   const bool multi = my_tiles > 1;
   const int nst = multi ? Cfg::kStagesMulti : Cfg::kStagesSingle;   // pipeline depth actually used
   uint8_t* stage_area = smem + (multi ? Cfg::kOffStagingMulti : 0);
   const int nkb = op_param.nkb_total;
   const bool tr0 = blockIdx.x == 0;
+  auto xr_ready = [&]() { return bar_base + 8u * 23; };     // split-K: the first CTA's rings are idle, the partner may write
+  auto xr_full = [&]() { return bar_base + 8u * 24; };      // split-K: the partner's partial tile has landed (8 warps)
   if (tid == 0 && op_param.trace && tr0) op_param.trace[0] = gtime();
   span_begin(op_param.span);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), kEpiWarps); }
-    if (XF) { for (int a = 0; a < kXAStages; ++a) mbar_init(a_ready(a), kEpiWarps); for (int a = 0; a < kXBStages; ++a) { mbar_init(b_full(a), 1); mbar_init(b_empty(a), 1); } }
+    if (XF) { mbar_init(xr_ready(), 1); mbar_init(xr_full(), kEpiWarps); for (int a = 0; a < kXAStages; ++a) mbar_init(a_ready(a), kEpiWarps); for (int a = 0; a < kXBStages; ++a) { mbar_init(b_full(a), 1); mbar_init(b_empty(a), 1); } }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && tr0) TRACE(1);
+  if constexpr (XF) if (ks > 1) cluster_sync_all();          // split-K: the partner's mbarriers exist before anyone arrives on them remotely
 
   // ============================================================================================================
   // Panel mode: one tile per CTA (grid == tile count).  warp 0: panels + weight tiles by TMA; warps 2-9: normalise
@@ -275,10 +281,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   bool xpanel = false;
   if constexpr (XF) xpanel = op_param.xmode != 0;
   if constexpr (XF) if (xpanel) {
-    const int tile = (int)blockIdx.x, mtile = tile / n_tiles;
+    const int tile = bid, mtile = tile / n_tiles;
     const int xb = mtile / tiles_per_batch, xt0 = (mtile % tiles_per_batch) * BM, xn0 = (tile % n_tiles) * BN;
     int ncblk = 0;
     for (int si = 0; si < op.nxs; ++si) ncblk += op.xs[si].ncb;
+    const int p_lo = ncblk * kr / ks, p_hi = ncblk * (kr + 1) / ks;   // this CTA's channel blocks (global panel indices)
     if (warp == 0) {
       if (lane == 0) {
         // weights of the first two channel blocks before the dependency wait, activations after it
@@ -291,15 +298,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             bulk_g2s(b0 + j * 2 * Cfg::kBTileBytes + Cfg::kBTileBytes, op.w_lo + eoff, Cfg::kBTileBytes, b_full(sb));
           }
         };
-        { int it = 0;
+        { int it = 0, gp = 0;
           for (int si = 0; si < op.nxs && it < kXBStages; ++si)
-            for (int cb = 0; cb < op.xs[si].ncb && it < kXBStages; ++cb, ++it) issue_w(op.xs[si], cb, it); }
+            for (int cb = 0; cb < op.xs[si].ncb && it < kXBStages; ++cb, ++gp) {
+              if (gp < p_lo || gp >= p_hi) continue;
+              issue_w(op.xs[si], cb, it); ++it;
+            } }
         pdl_wait();
         if (tr0) TRACE(2);
-        int it = 0;
+        int it = 0, gp = 0;
         for (int si = 0; si < op.nxs; ++si) {
           const XSeg& xs = op.xs[si];
-          for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+          for (int cb = 0; cb < xs.ncb; ++cb, ++gp) {
+            if (gp < p_lo || gp >= p_hi) continue;
             const int sa = it % kXAStages, sb = it % kXBStages;
             if (it >= kXAStages) mbar_wait(empty_bar(sa), (uint32_t)(((it / kXAStages) & 1) ^ 1));
             const uint32_t a_hi = base + sa * kXAStageBytes;
@@ -309,15 +320,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tma_load_3d(a_hi, &tmaps[2 * xs.src], c, trow, xb, full_bar(sa));
             tma_load_3d(a_hi + kPanelBytes, &tmaps[2 * xs.src + 1], c, trow, xb, full_bar(sa));
             if (it >= kXBStages) { mbar_wait(b_empty(sb), (uint32_t)(((it / kXBStages) & 1) ^ 1)); issue_w(xs, cb, sb); }
+            ++it;
           }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        int it = 0;
+        int it = 0, gp = 0;
         for (int si = 0; si < op.nxs; ++si) {
           const XSeg& xs = op.xs[si];
-          for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+          for (int cb = 0; cb < xs.ncb; ++cb, ++gp) {
+            if (gp < p_lo || gp >= p_hi) continue;
             const int sa = it % kXAStages, sb = it % kXBStages;
             mbar_wait(b_full(sb), (uint32_t)((it / kXBStages) & 1));
             mbar_wait(a_ready(sa), (uint32_t)((it / kXAStages) & 1));
@@ -335,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             umma_commit(empty_bar(sa));
             umma_commit(b_empty(sb));
+            ++it;
           }
         }
         umma_commit(acc_full(0));
@@ -359,12 +373,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       XTRACE(1);
       const bool silu = have_aff && pr.mode == PREP_AFFINE_SILU;
-      int it = 0;
+      int it = 0, gp = 0;
       for (int si = 0; si < op.nxs; ++si) {
         const XSeg& xs = op.xs[si];
         const int rows = xs.ntap == 3 ? kPanelRows : BM, tfirst = xt0 + (xs.ntap == 3 ? -1 : 0);
         const int Tsrc = op.src[xs.src].T;
-        for (int cb = 0; cb < xs.ncb; ++cb, ++it) {
+        for (int cb = 0; cb < xs.ncb; ++cb, ++gp) {
+          if (gp < p_lo || gp >= p_hi) continue;
           const int sa = it % kXAStages;
           // this thread's 16-byte chunk column q = xt % 8 is the same for every row it touches: its 8 scale / shift values
           // are fetched once per panel, before the panel itself has landed
@@ -429,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(a_ready(sa));
           if (it == 0) XTRACE(3);
+          ++it;
         }
       }
       XTRACE(4);
@@ -439,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
   const int npf = nkb < nst ? nkb : nst;
   if (!xpanel && warp == 0 && lane == 0) {
-    const int n0 = ((int)blockIdx.x % n_tiles) * BN;
+    const int n0 = (bid % n_tiles) * BN;
     for (int kb = 0; kb < npf; ++kb) {
       const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
       mbar_arrive_expect_tx(full_bar(kb), 2u * kATileBytes + 2u * Cfg::kBTileBytes);
@@ -458,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (tr0) TRACE(2);
       int g = 0;                                            // k-block counter across this CTA's tiles
       for (int it = 0; it < my_tiles; ++it) {
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int tile = bid + it * nblk;
         const int mt = tile / n_tiles, n0 = (tile % n_tiles) * BN;
         const int b = mt / tiles_per_batch, t0 = (mt % tiles_per_batch) * BM;
         int si = 0, kbl = 0;
@@ -520,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const TMap* tmo = op_param.tmap_out;
     bool staged_once = false;
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = bid + it * nblk;
       const int mt = tile / n_tiles, nt = tile % n_tiles, n0 = nt * BN;
       const int b = mt / tiles_per_batch, t0 = (mt % tiles_per_batch) * BM;
       const int t = t0 + r;
@@ -652,6 +668,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tmem_ld32_sum(trow + (uint32_t)(cc * 32), trow + (uint32_t)(BN + cc * 32), acc);
           if (cc + 2 >= BN / 32) release_acc();
           if (it == 0 && tr0) ETRACE(1);
+          if constexpr (XF) if (ks > 1) {
+            // split-K: the partner CTA's fp32 partial of this thread's 32 values travels through THIS tile owner's shared
+            // memory (its weight ring is idle once its own accumulator is complete): [8 x float4][256 threads]
+            const int te = tid - 64;
+            if (kr != 0) {
+              mbar_wait_cluster(xr_ready(), 0);              // the owner has finished its main loop
+              const uint32_t rbase = mapa_u32(base + kXOffB, 0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) st_remote_f32x4(rbase + (uint32_t)((j * 256 + te) * 16), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+              asm volatile("fence.acq_rel.cluster;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(mapa_u32(xr_full(), 0));
+              continue;                                      // no epilogue of its own: the owner stores the tile
+            }
+            if (warp == 2 && lane == 0) mbar_arrive_remote(mapa_u32(xr_ready(), 1));   // (acc_full has been waited for: our rings are idle)
+            mbar_wait_cluster(xr_full(), 0);
+            const float4* xr = reinterpret_cast<const float4*>(smem + kXOffB);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = xr[j * 256 + te];
+              acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w;
+            }
+          }
           const int nbase = n0 + cc * 32;
           const bool cvalid = nbase < op.n_valid;           // (uniform across the warp)
           if (cvalid) {
@@ -712,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             sm_part[(q * BN + cc * 32 + lane) * 2 + 1] = 0.f;
           }
         }
-        if (op.flags & EPI_STATS) {
+        if ((op.flags & EPI_STATS) && kr == 0) {            // (a split-K partner has no output of its own)
           asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 epilogue warps
           if (it == 0 && tr0) ETRACE(5);
           const int col = tid - 64;                         // 0..127
@@ -835,8 +874,10 @@ static int launch_bn(const GemmOp& op, cudaStream_t st) {
   }
   const int tiles = op.B * ceil_div(op.T_out, BM) * (op.N / BN_);
   // persistent: one CTA per SM at most, each looping over its share of the (m, n) tiles; panel mode: one tile per CTA
-  const int grid = (XF && op.xmode) ? tiles : (tiles < sm_count() ? tiles : sm_count());
-  cudaError_t e = launch_k(gemm_tc_kernel<BN_, LNF, XF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, op);
+  int grid = (XF && op.xmode) ? tiles : (tiles < sm_count() ? tiles : sm_count());
+  dim3 cluster(1, 1, 1);
+  if (XF && op.xmode && op.ksplit > 1) { grid = tiles * op.ksplit; cluster.x = (unsigned)op.ksplit; }   // split-K: the CTAs of a cluster share a tile
+  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, LNF, XF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, cluster, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -855,6 +896,7 @@ int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.xmode) {
     if (lnf || op.bn != 64 || op.nxs < 1 || op.nxs > kMaxXSeg) { set_error("gemm_tc: panel mode needs a plain 64-wide tile and 1..%d segments", kMaxXSeg); return -1; }
     if (op.pre == nullptr) { set_error("gemm_tc: panel mode without GroupNorm parameters"); return -1; }
+    if (op.ksplit != 1 && op.ksplit != 2) { set_error("gemm_tc: ksplit must be 1 or 2"); return -1; }
     return launch_bn<64, false, true>(op, st);
   }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }

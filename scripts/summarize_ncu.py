@@ -16,7 +16,7 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__share
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
-for name, rep, cmd in (("gemm_tc", "gpurun_out/prof_gemm.ncu-rep", "-k regex:gemm_tc -s 60 -c 6"), ("attn_v2", "gpurun_out/prof_attn.ncu-rep", "-k regex:attn_v2 -s 0 -c 6")):
+for name, rep, cmd in (("gemm_tc", "gpurun_out/prof_gemm.ncu-rep", "-k regex:gemm_tc -s 60 -c 6"), ("gemm_tc_panel", "gpurun_out/prof_xf.ncu-rep", "--kernel-name-base demangled -k regex:\"gemm_tc_kernel<64, false, true>\" -s 4 -c 4"), ("attn_v2", "gpurun_out/prof_attn.ncu-rep", "-k regex:attn_v2 -s 0 -c 6")):
     if not os.path.exists(rep):
         continue
     hdr, units, data = raw(rep)
