@@ -49,6 +49,8 @@ struct SplitBuf {
   int T;              // rows per batch entry
   int C;              // valid channels
   int ld;             // row pitch in elements (multiple of 8)
+  long long bpitch;   // elements between batch entries; 0 = T * ld (dense).  Views over row PAIRS of a tensor with an odd
+                      // number of rows (the stride-2 conv's even / odd rows) need their own value
 };
 
 struct alignas(128) TMap { unsigned long long v[16]; };   // CUtensorMap storage (driver-encoded)
@@ -65,7 +67,7 @@ struct GnStats {
   const float* film; int film_ld;          // nullptr or [B, film_ld]: scale at film[b,c], shift at film[b,C+c]
   int G; float eps;
 };
-struct PrepOp {
+struct alignas(16) PrepOp {      // (16-byte multiples: arrays of descriptors are copied with 128-bit loads)
   const float* src1; int ld1; int C1;
   const float* src2; int ld2; int C2;     // nullptr / 0 when there is no concat
   int B, T_src, T_dst;
@@ -246,7 +248,8 @@ int encode_attn_tmaps(AttnOp& op);
 // Generic 3-D tiled bf16 tensor map over a token-major [B, T, ld] buffer with C valid channels.
 int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes);
 // Same for fp32 data (elem_bytes = 4) / bf16 (elem_bytes = 2)
-int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes);
+int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes,
+                    long long bpitch = 0);
 
 // ---------------------------------------------------------------------------------------------
 // Norm statistics and small kernels (kernels_misc.cu)

@@ -124,6 +124,10 @@ struct ns2vc_unet {
   // cached program
   int pB = 0, pT = 0, pS = 0; void* pws = nullptr; bool has_mask = false; bool cond_ready = false;
   float* aug = nullptr;                                   // add_embedding output [B, ted] of the active program (workspace)
+  // Per-program STATIC device data (GroupNorm descriptors, nearest-upsample index tables) lives outside the caller's workspace:
+  // several shapes may share one workspace, and captured graphs keep reading these tables, so they are only released when the
+  // weights are re-packed or the handle is destroyed (~20 KB per shape ever seen)
+  std::vector<void*> static_bufs;
   std::vector<Launch> prog_cond, prog_fwd;
   std::vector<std::string> tap_names; std::vector<int> tap_level, tap_ch;
   std::vector<float*> tap_dst;
@@ -521,7 +525,7 @@ struct Builder {
   int err = 0;
 
   SplitBuf split(int Tn, int C) {
-    SplitBuf s; s.T = Tn; s.C = C; s.ld = pad_to(C, 8);
+    SplitBuf s{}; s.T = Tn; s.C = C; s.ld = pad_to(C, 8);
     s.hi = ar.get<__nv_bfloat16>((size_t)B * Tn * s.ld);
     s.lo = ar.get<__nv_bfloat16>((size_t)B * Tn * s.ld);
     return s;
@@ -583,9 +587,18 @@ struct Builder {
     p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
     p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
     p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
-    PrepOp* d = ar.get<PrepOp>(1);
-    if (!dry && cudaMemcpy(d, &p, sizeof(p), cudaMemcpyHostToDevice) != cudaSuccess) err = -2;
-    return d;
+    // all descriptors of a program sit in one workspace array and go to the device in ONE copy when the program is complete
+    if ((int)aff_host.size() >= aff_cap) { err = -1; set_error("internal: affine descriptor table full"); return nullptr; }
+    aff_host.push_back(p);
+    return aff_dev ? aff_dev + (aff_host.size() - 1) : reinterpret_cast<const PrepOp*>(uintptr_t(16));   // (dry run: any non-null value)
+  }
+  std::vector<PrepOp> aff_host; PrepOp* aff_dev = nullptr; int aff_cap = 0;
+  Arena sar;                                               // the program's static buffer (see ns2vc_unet::static_bufs)
+  void reserve_affine(int n) { aff_cap = n; aff_dev = sar.get<PrepOp>((size_t)n); aff_host.reserve(n); }
+  int upload_affine(cudaStream_t st) {
+    if (dry || aff_host.empty()) return 0;
+    // pageable source: the runtime stages it before returning, so the vector may die with the builder
+    return cudaMemcpyAsync(aff_dev, aff_host.data(), aff_host.size() * sizeof(PrepOp), cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -2;
   }
   void push(const Launch& l) { out->push_back(l); }
   void emit_prep(const float* s1, int C1, const float* s2, int C2, int T_src, int T_dst, int mode, const float* scale,
@@ -638,6 +651,18 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
   }
   Builder bld{h, Arena{(uint8_t*)ws, 0}, B, T, S, &cond, dry};
   Arena& ar = bld.ar;
+  {
+    const int n_aff = 2 * (int)h->resnets.size() + (int)h->xformers.size() + 2;
+    size_t sbytes = 1024 + (size_t)n_aff * sizeof(PrepOp);
+    for (auto& o : h->plan) if (o.kind == PlanOp::UP) sbytes += 256 + (size_t)Tl[o.level] * sizeof(int);
+    if (!dry) {
+      void* sb = nullptr;
+      NS_CHECK_CUDA(cudaMalloc(&sb, sbytes));
+      h->static_bufs.push_back(sb);
+      bld.sar = Arena{(uint8_t*)sb, 0};
+    }
+    bld.reserve_affine(n_aff);
+  }
 
   // ---- persistent conditioning buffers
   float* P = (Cc > 0) ? ar.get<float>((size_t)B * T * c0) : nullptr;      // conv_in(content) + bias
@@ -966,9 +991,16 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const ConvSite& s = h->resamplers[si++];
         const int Tin = Tl[o.level - 1];
         const int To = Tin / 2;                                  // odd-row count
-        const SplitBuf ev = Builder::view(SP_A, TL, s.c), od = Builder::view(SP_R, std::max(To, 1), s.c);
-        bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, ev, nullptr, 2, 0);
-        bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, std::max(To, 1), PREP_RAW, nullptr, nullptr, od, nullptr, 2, 1);
+        SplitBuf ev = Builder::view(SP_A, TL, s.c), od = Builder::view(SP_R, std::max(To, 1), s.c);
+        if (xf_on && To >= 1) {
+          // no copy at all: the raw split of the block input seen as row PAIRS [B, ceil(Tin/2), 2*ld] - even rows are the first
+          // half of a pair, odd rows the second (one row fewer when Tin is odd: rows past it are the TMA unit's zero fill)
+          ev = cur.sp; ev.T = TL; ev.ld = 2 * cur.sp.ld; ev.bpitch = (long long)Tin * cur.sp.ld;
+          od = ev; od.hi += cur.sp.ld; od.lo += cur.sp.ld; od.T = To;
+        } else {
+          bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, TL, PREP_RAW, nullptr, nullptr, ev, nullptr, 2, 0);
+          bld.emit_prep(cur.p, s.c, nullptr, 0, Tin, std::max(To, 1), PREP_RAW, nullptr, nullptr, od, nullptr, 2, 1);
+        }
         Act outp = next_out(followed_by_push(pi), TL, s.c);
         outp.st = new_stats(s.c);
         GemmOp g = bld.gemm_base(s.w, TL);
@@ -986,7 +1018,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
         const int Tin = Tl[o.level + 1];
         // nearest-neighbour source rows of F.interpolate(size=TL) (reference resnet.py:160): a table in the workspace, filled on
         // the device with the same fp32 rule as ns2vc_nearest_index() (stream-ordered: no allocation, no host sync)
-        int* map_d = ar.get<int>((size_t)TL);
+        int* map_d = bld.sar.get<int>((size_t)TL);
         if (!dry) {
           nearest_index_kernel<<<ceil_div(TL, 256), 256, 0, st>>>(Tin, TL, map_d);
           NS_CHECK_CUDA(cudaGetLastError());
@@ -1021,6 +1053,7 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
     g.flags = EPI_BIAS | EPI_OUT_NCT; g.bias = h->W("conv_out.bias"); g.out = nullptr;
     bld.emit_gemm(g, h->conv_out, 3);
   }
+  if (!bld.err && bld.upload_affine(st)) { set_error("affine descriptor upload failed"); return -2; }
   if (bld.err) return bld.err;
   if (bytes_out) *bytes_out = ar.off + 256;
   if (!dry) {
@@ -1138,7 +1171,9 @@ int run_program(ns2vc_unet* h, std::vector<Launch>& prog, const float* x, long l
 void stash_active(ns2vc_unet* h) {
   if (!h->pws) return;
   ns2vc_unet::Stash s;
-  s.pB = h->pB; s.pT = h->pT; s.pS = h->pS; s.pws = h->pws; s.has_mask = h->has_mask; s.cond_ready = h->cond_ready;
+  // programs of different shapes may share one workspace (the caller's grow-only scratch buffer): the conditioning a stashed
+  // program prepared is gone once another program has run there, so it must be prepared again when it comes back
+  s.pB = h->pB; s.pT = h->pT; s.pS = h->pS; s.pws = h->pws; s.has_mask = h->has_mask; s.cond_ready = false;
   s.prog_cond = std::move(h->prog_cond); s.prog_fwd = std::move(h->prog_fwd); s.film_base = h->film_base; s.aug = h->aug;
   s.tap_names = std::move(h->tap_names); s.tap_level = std::move(h->tap_level); s.tap_ch = std::move(h->tap_ch); s.tap_dst = std::move(h->tap_dst);
   h->prog_cond.clear(); h->prog_fwd.clear(); h->tap_names.clear(); h->tap_level.clear(); h->tap_ch.clear(); h->tap_dst.clear();
@@ -1149,6 +1184,8 @@ void stash_active(ns2vc_unet* h) {
 
 void drop_all_programs(ns2vc_unet* h) {
   h->stash.clear();
+  for (void* p : h->static_bufs) cudaFree(p);
+  h->static_bufs.clear();
   h->prog_cond.clear(); h->prog_fwd.clear();
   h->pB = h->pT = h->pS = 0; h->pws = nullptr; h->cond_ready = false;
 }

@@ -99,7 +99,7 @@ __device__ __forceinline__ float a_fetch_split(const GemmOp& op, const GSeg& s, 
   const SplitBuf& src = op.src[s.src];
   const int r = t + s.tap, ch = s.c0 + c;
   if (r < 0 || r >= src.T || ch >= src.C) return 0.f;
-  const long long off = ((long long)b * src.T + r) * src.ld + ch;
+  const long long off = (src.bpitch ? (long long)b * src.bpitch + (long long)r * src.ld : ((long long)b * src.T + r) * src.ld) + ch;
   return __bfloat162float(src.hi[off]) + __bfloat162float(src.lo[off]);
 }
 

@@ -797,7 +797,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes) {
+int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, int B, int ld, int box_c, int box_rows, int swizzle_bytes,
+                    long long bpitch) {
   static_assert(sizeof(CUtensorMap) == sizeof(TMap), "CUtensorMap size");
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
@@ -805,7 +806,7 @@ int encode_tmap_any(TMap* out, const void* base, int elem_bytes, int C, int T, i
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  const cuuint64_t gstr[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)T * ld * elem_bytes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)(bpitch ? bpitch : (long long)T * ld) * elem_bytes};
   const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
@@ -819,7 +820,7 @@ int encode_tmap_rows(TMap* out, const __nv_bfloat16* base, int C, int T, int B, 
 }
 
 static int encode_one(TMap* out, const __nv_bfloat16* base, const SplitBuf& s, int B, int box_rows) {
-  return encode_tmap_rows(out, base, s.C, s.T, B, s.ld, 64, box_rows, 128);
+  return encode_tmap_any(out, base, 2, s.C, s.T, B, s.ld, 64, box_rows, 128, s.bpitch);
 }
 
 int encode_tmaps(GemmOp& op) {

@@ -50,6 +50,7 @@ class DenoiserSession:
     it ONCE after the run, raising the same ``AssertionError``."""
 
     MAX_GRAPHS = 4                                           # LRU bound of captured loops per session
+    CAPTURE_AFTER = 3                                        # the loop is captured on its third run, replayed from the fourth
 
     def __init__(self, unet: UNet1DConditionModel, content_BCT: Optional[torch.Tensor], prompt_BSC: torch.Tensor,
                  prompt_mask: Optional[torch.Tensor], T: Optional[int] = None):
@@ -77,9 +78,7 @@ class DenoiserSession:
         self.x_in = torch.empty((self.B, self.Cl, self.T), **f32)
         self.first_out = torch.empty((self.B, self.Co, self.T), **f32)   # step-0 model output handed in by the drop-in samplers
         self.nan_flag = torch.zeros((1,), dtype=torch.int32, device=self.dev)
-        n = C.c_size_t()
-        _lib.check(self.L.ns2vc_unet_workspace_bytes(self.h, self.B, self.T, self.S, C.byref(n)))
-        self.ws = torch.empty(int(n.value), dtype=torch.uint8, device=self.dev)
+        self.ws = unet.workspace(self.B, self.T, self.S, self.dev)     # the module's shared grow-only scratch buffer
         self._graphs = collections.OrderedDict()
         self._wsig = unet._wsig
         self.set_cond(content_BCT, prompt_BSC, prompt_mask)
@@ -105,10 +104,11 @@ class DenoiserSession:
                 (self.Cc * self.T) if self.content is not None else 0, self.prompt.data_ptr(),
                 self.mask.data_ptr() if self.mask is not None else None, self.B, self.T, self.S, self.ws.data_ptr(), self._stream()))
         self._prepared = True
+        self.unet.__dict__["_cond_owner"] = self                 # the shared workspace holds THIS session's conditioning now
 
     def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor, film_rows: Optional[torch.Tensor] = None):
         """x [B,Cl,T] fp32 contiguous, t [B] fp32 (or B precomputed FiLM rows), out [B,Co,T] fp32 — all on the session device."""
-        if not self._prepared:
+        if not self._prepared or self.unet.__dict__.get("_cond_owner") is not self:
             self.prepare()
         with torch.cuda.device(self.dev):
             if film_rows is not None:
@@ -209,18 +209,19 @@ class DenoiserSession:
             nrows = tvals.numel()
             table = torch.empty(int(self.L.ns2vc_unet_time_table_floats(self.h, nrows)), dtype=torch.float32, device=self.dev)
             ent = {"steps": steps, "tvals": tvals, "table": table, "film_width": int(self.L.ns2vc_unet_film_width(self.h)),
-                   "graph": None, "out": None, "warm": False}
+                   "graph": None, "out": None, "runs": 0}
             self._graphs[key] = ent
             while len(self._graphs) > self.MAX_GRAPHS:     # LRU: the oldest captured loop (graph + tables) is dropped
                 self._graphs.popitem(last=False)
         else:
             self._graphs.move_to_end(key)
+        ent["runs"] += 1
         if not use_graph:
             res = self._loop(kind, ent, use_first)
-        elif ent["graph"] is None and not ent["warm"]:
-            # first run eagerly: builds the launch program, sets kernel attributes, warms the allocator
+        elif ent["graph"] is None and ent["runs"] < self.CAPTURE_AFTER:
+            # eager: the first run builds the launch program and sets kernel attributes; a shape / schedule seen only once or
+            # twice (the CLI: every slice a new length) never pays for a capture (~0.1-1 s for 6 000+ kernel nodes)
             res = self._loop(kind, ent, use_first)
-            ent["warm"] = True
         else:
             if ent["graph"] is None:
                 torch.cuda.synchronize(self.dev)
@@ -230,6 +231,7 @@ class DenoiserSession:
                 ent["graph"] = g
             ent["graph"].replay()
             self._prepared = True
+            self.unet.__dict__["_cond_owner"] = self
             res = ent["out"].clone()
         self._check_nan()
         return res
@@ -257,9 +259,10 @@ def get_session(unet: UNet1DConditionModel, content_BCT, prompt_BSC, prompt_mask
     cache = unet.__dict__.setdefault("_sessions", {})
     sess = cache.get(key)
     if sess is None or sess.h != unet.engine(prompt_BSC.device):
-        if len(cache) > 4:
-            cache.clear()
+        while len(cache) >= 8:                               # bounded: oldest shape first (dicts keep insertion order)
+            cache.pop(next(iter(cache)))
         sess = DenoiserSession(unet, content_BCT, prompt_BSC, prompt_mask, T=T)
+        cache = unet.__dict__.setdefault("_sessions", {})     # (the workspace may have grown and dropped the old sessions)
         cache[key] = sess
     else:
         sess.set_cond(content_BCT, prompt_BSC, prompt_mask)

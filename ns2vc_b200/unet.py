@@ -258,7 +258,8 @@ class UNet1DConditionModel(nn.Module):
 
         self._handle: Optional[int] = None
         self._wsig = None
-        self._ws: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._ws_need: Dict[Tuple[int, int, int], int] = {}
         self._handle_device = None
 
     # ------------------------------------------------------------------ engine management
@@ -321,20 +322,30 @@ class UNet1DConditionModel(nn.Module):
                 _lib.check(L.ns2vc_unet_load_weight(self._handle, key.encode(), t.data_ptr(), shape, t.dim(), stream))
             _lib.check(L.ns2vc_unet_finalize(self._handle, stream))
         self._wsig = sig
-        self._ws = {}
+        self._ws_need = {}
         return self._handle
 
     def workspace(self, B: int, T: int, S: int, device: torch.device) -> torch.Tensor:
+        """ONE grow-only scratch buffer per module, shared by every shape (the CLI feeds a different T per slice: a fresh
+        multi-hundred-MB allocation per shape was most of a cold call).  Calls are stream-ordered and never concurrent, and
+        every program re-runs prepare_cond after a shape switch, so shapes can alias the same memory.  Growing it invalidates
+        the captured loops that baked the old pointer (the sessions are dropped)."""
         key = (B, T, S)
-        ws = self._ws.get(key)
-        if ws is None or ws.device != device:
+        need = self._ws_need.get(key)
+        if need is None:
             n = C.c_size_t()
             _lib.check(_lib.lib().ns2vc_unet_workspace_bytes(self.engine(device), B, T, S, C.byref(n)))
-            if len(self._ws) > 4:
-                self._ws.clear()
-            ws = torch.empty(int(n.value), dtype=torch.uint8, device=device)
-            self._ws[key] = ws
-        return ws
+            need = int(n.value)
+            if len(self._ws_need) > 256:
+                self._ws_need.clear()
+            self._ws_need[key] = need
+        pool = self._ws.get("pool")
+        if pool is None or pool.device != device or pool.numel() < need:
+            self.__dict__.get("_sessions", {}).clear()
+            self._ws.pop("pool", None)
+            pool = None
+            self._ws["pool"] = pool = torch.empty(int(need * 1.25) if need < (8 << 30) else need, dtype=torch.uint8, device=device)
+        return pool
 
     def plan_string(self) -> str:
         return "".join(f"{o.kind}|{o.prefix}|{o.cin}|{o.cout}|{o.level}\n" for o in build_plan(self.cfg))
@@ -404,6 +415,7 @@ class UNet1DConditionModel(nn.Module):
         Cl, Cin = self.latent_channels, self.cfg.in_channels
         content_ptr = x.data_ptr() + 4 * Cl * T if Cin > Cl else None
         with torch.cuda.device(dev):
+            self.__dict__["_cond_owner"] = None
             _lib.check(L.ns2vc_unet_prepare_cond(h, content_ptr, Cin * T, ehs.data_ptr(),
                                                  mask_u8.data_ptr() if mask_u8 is not None else None, B, T, S, ws.data_ptr(), stream))
             _lib.check(L.ns2vc_unet_forward(h, x.data_ptr(), Cin * T, t32.data_ptr(), out.data_ptr(), B, T, S, ws.data_ptr(), stream))

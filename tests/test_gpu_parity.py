@@ -205,17 +205,17 @@ def test_fused_samplers_tiny_vs_reference_fixture(gold):
     ns = NoiseScheduleVP("discrete", betas=linear_betas(1000))
     sess = _session(m, inp)
     outs = []
-    for i in range(3):          # 1st call eager, 2nd captures the CUDA graph, 3rd replays it
+    for i in range(4):          # calls 1-2 eager, the 3rd captures the CUDA graph, the 4th replays it
         out = sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 13))
         ok, msg = close(out, g["dpmpp2m_12"])
         assert ok, f"call {i}: {msg}"
         outs.append(out)
-    assert torch.equal(outs[1], outs[2]), "graph replay must reproduce the captured run"
+    assert torch.equal(outs[2], outs[3]), "graph replay must reproduce the captured run"
     # new inputs through the same captured graph
     x2 = torch.randn_like(outs[0])
     a = sess.sample_dpmpp_2m(x2, ns, torch.linspace(1.0, 1e-3, 13))
     assert not torch.allclose(a, outs[2])
-    for i in range(3):
+    for i in range(4):
         out = sess.sample_unipc(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 9))
         ok, msg = close(out, g["unipc_bh2_8"])
         assert ok, f"unipc call {i}: {msg}"
@@ -420,15 +420,15 @@ def test_fresh_schedule_objects_share_one_graph_and_other_betas_do_not(gold):
         mf = our_dpm.model_wrapper(_closure(m, inp), ns, model_type="x_start", model_kwargs={})
         return our_dpm.DPM_Solver(mf, ns, algorithm_type="dpmsolver++").sample(x0, steps=12, order=2, skip_type="time_uniform", method="multistep")
     with torch.no_grad():
-        outs = [run(linear_betas(1000).cuda()) for _ in range(3)]
+        outs = [run(linear_betas(1000).cuda()) for _ in range(4)]
     sessions = list(m.__dict__["_sessions"].values())
     assert len(sessions) == 1
     ents = list(sessions[0]._graphs.values())
-    assert len(ents) == 1 and ents[0]["graph"] is not None, "three calls with fresh schedule objects must end up replaying one captured loop"
+    assert len(ents) == 1 and ents[0]["graph"] is not None and ents[0]["runs"] == 4, "calls with fresh schedule objects must find (and end up replaying) ONE captured loop"
     for o in outs:
         ok, msg = close(o, g["dpmpp2m_12"])
         assert ok, msg
-    assert torch.equal(outs[1], outs[2])
+    assert torch.equal(outs[2], outs[3])
     # a different schedule: own entry, own coefficients; must agree with the generic Python loop for THAT schedule
     betas2 = torch.linspace(2e-4, 0.03, 1000, dtype=torch.float64).to(torch.float32).cuda()
     with torch.no_grad():
@@ -455,7 +455,7 @@ def test_nan_input_raises_like_the_reference():
     ok = sess.sample_dpmpp_2m(x, ns, torch.linspace(1.0, 1e-3, 11))
     assert torch.isfinite(ok).all()
     x[1, 3, 5] = float("nan")
-    for _ in range(3):                                   # eager, capture, replay
+    for _ in range(4):                                   # eager, eager, capture, replay
         with pytest.raises(AssertionError):
             sess.sample_dpmpp_2m(x, ns, torch.linspace(1.0, 1e-3, 11))
     assert torch.isfinite(sess.sample_dpmpp_2m(inp["x"].cuda(), ns, torch.linspace(1.0, 1e-3, 11))).all()
