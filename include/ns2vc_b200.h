@@ -5,9 +5,13 @@
  * drop-in modules (ns2vc_b200/unet.py, fused.py) bind with ctypes; each entry point names the
  * reference interface it stands in for.  Plain C types, raw device pointers + cudaStream_t,
  * int return (0 = ok, <0 = error; ns2vc_last_error() returns the message).  No exceptions or C++
- * types cross the ABI; the caller owns every buffer, the handle owns only its packed weights.
- * All calls are stream-ordered, allocation-free after ns2vc_unet_finalize() and capturable in a
- * CUDA graph.  One handle per device; not thread-safe per handle.
+ * types cross the ABI; the caller owns every buffer, the handle owns only its packed weights and, per
+ * (B, T, S, workspace) it has seen, a launch program with ~20 KB of static device tables.
+ * All calls are stream-ordered.  The FIRST prepare_cond / forward / time_table for a new (B, T, S, workspace)
+ * builds that program (host work, one cudaMalloc, one host-to-device copy): it must not run under stream
+ * capture - run a shape once eagerly, after which its calls allocate nothing, never synchronise and are
+ * capturable in a CUDA graph.  One workspace may serve several shapes one after another (prepare_cond again
+ * after a switch).  One handle per device, one run at a time; not thread-safe per handle.
  */
 #ifndef NS2VC_B200_H
 #define NS2VC_B200_H

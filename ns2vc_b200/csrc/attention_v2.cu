@@ -424,16 +424,12 @@ bool attention_v2_p_fp16() {
 }
 
 bool attention_v2_supported(int dh, int Tk, bool biased) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("NS2VC_ATTN"); off = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
-  if (off || !(dh == 16 || dh == 32 || dh == 48 || dh == 64)) return false;
+  if (!(dh == 16 || dh == 32 || dh == 48 || dh == 64)) return false;
   return !biased || ceil_div(Tk, kKeys) * kKeys <= (dh == 16 ? 768 : 1024);   // the additive bias of a row of keys is staged in shared memory
 }
 
 int encode_attn_tmaps(AttnOp& op) {
-  static int wide = -1;                                     // NS2VC_ATTN_PB=128: padded 128-byte rows for every head dim
-  if (wide < 0) { const char* e = getenv("NS2VC_ATTN_PB"); wide = (e && atoi(e) == 128) ? 1 : 0; }
-  op.pb = wide ? 128 : natural_pb(op.dh);
+  op.pb = natural_pb(op.dh);                                // (padded 128-byte rows for every head dim were measured slower in r01)
   const int bc = op.pb / 2;                                 // box width in channels
   int rc = 0;
   if ((rc = encode_tmap_rows(&op.tm[0], op.qs.hi, op.qs.C, op.qs.T, op.B, op.qs.ld, bc, kQ, op.pb))) return rc;
@@ -450,8 +446,6 @@ int launch_attention_v2(const AttnOp& op, cudaStream_t st) {
   if (op.qs.T != op.Tq || op.ks.T != op.Tk || op.vs.T != op.Tk) { set_error("attention v2: split buffer / sequence length mismatch"); return -1; }
   const int dh = op.dh;
   if (op.pb == 128) {
-    if (dh == 16) return launch_v2<16, 128>(op, st);
-    if (dh == 32) return launch_v2<32, 128>(op, st);
     if (dh == 48) return launch_v2<48, 128>(op, st);
     if (dh == 64) return launch_v2<64, 128>(op, st);
   } else if (op.pb == 64 && dh == 32) {

@@ -833,6 +833,7 @@ int encode_tmaps(GemmOp& op) {
       if (rc) return rc;
       op.tma_out |= 1;
     }
+    // (per-thread 16-byte stores of the split instead of two TMA stores were measured in r02: 3.46 vs 3.16 ms per forward)
     if ((op.flags & EPI_OUT_SPLIT) && (op.out_split_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(op.out_hi) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(op.out_lo) & 15) == 0) {
       int rc = encode_tmap_any(&op.tmap_out[1], op.out_hi, 2, op.n_valid, op.T_out, op.B, op.out_split_ld, 32, 32, 64);

@@ -23,9 +23,6 @@ from . import _lib, coefs
 from .unet import UNet1DConditionModel, trace_calls
 
 
-_HOIST = os.environ.get("NS2VC_HOIST", "1") != "0"     # diagnostic: 0 = timestep path recomputed inside every forward
-
-
 def schedule_signature(ns) -> tuple:
     """Content key of a noise schedule.  The reference builds a NEW NoiseScheduleVP inside every ``sample()``
     (model.py:621-622, 655-656), so object identity is useless as a cache key (and a recycled ``id()`` could
@@ -34,6 +31,21 @@ def schedule_signature(ns) -> tuple:
         la = ns.log_alpha_array.detach().to("cpu", torch.float32).contiguous()
         return ("discrete", int(ns.total_N), hashlib.sha1(la.numpy().tobytes()).hexdigest())
     return (str(getattr(ns, "schedule", "?")), float(getattr(ns, "beta_0", 0.0)), float(getattr(ns, "beta_1", 0.0)), int(getattr(ns, "total_N", 0)))
+
+
+_TABLES = collections.OrderedDict()     # per-step scalars do not depend on the shape: shared by every session (the CLI: a new shape per slice)
+
+
+def _step_table(kind, ns, ts, extra, key):
+    tab = _TABLES.get(key)
+    if tab is None:
+        tab = coefs.dpmpp_2m_table(ns, ts, extra) if kind == "dpm" else coefs.unipc_bh2_table(ns, ts, extra)
+        _TABLES[key] = tab
+        while len(_TABLES) > 16:
+            _TABLES.popitem(last=False)
+    else:
+        _TABLES.move_to_end(key)
+    return tab
 
 
 class DenoiserSession:
@@ -139,7 +151,7 @@ class DenoiserSession:
             if k == 0 and use_first:
                 out.copy_(self.first_out)
             else:
-                self.forward(x, ent["tvals"][k], out, film_rows=self._film(ent, k) if _HOIST else None)
+                self.forward(x, ent["tvals"][k], out, film_rows=self._film(ent, k))
             c = _lib.DpmCoef(st.alpha_s, st.sigma_s, st.c_x, st.c_m, st.c_d, st.inv_r0, st.order)
             with torch.cuda.device(self.dev):
                 _lib.check(self.L.ns2vc_dpm_step(x.data_ptr(), out.data_ptr(), m_b.data_ptr(), C.byref(c), m_a.data_ptr(),
@@ -159,7 +171,7 @@ class DenoiserSession:
             if k == 0 and use_first:
                 out.copy_(self.first_out)
             else:
-                self.forward(x_eval, ent["tvals"][k], out, film_rows=self._film(ent, k) if _HOIST else None)
+                self.forward(x_eval, ent["tvals"][k], out, film_rows=self._film(ent, k))
             m_t = torch.empty_like(x_prev)
             x_t = torch.empty_like(x_prev) if st.corr_order > 0 else None
             x_pred = torch.empty_like(x_prev)
@@ -204,7 +216,7 @@ class DenoiserSession:
         use_graph = os.environ.get("NS2VC_GRAPH", "1") != "0"
         ent = self._graphs.get(key)
         if ent is None:
-            steps = coefs.dpmpp_2m_table(ns, ts, extra) if kind == "dpm" else coefs.unipc_bh2_table(ns, ts, extra)
+            steps = _step_table(kind, ns, ts, extra, key[:4])
             tvals = torch.tensor([[st.t_input] * self.B for st in steps], dtype=torch.float32).to(self.dev)
             nrows = tvals.numel()
             table = torch.empty(int(self.L.ns2vc_unet_time_table_floats(self.h, nrows)), dtype=torch.float32, device=self.dev)

@@ -519,3 +519,19 @@ def test_forward_with_large_gain_weights_and_offset_activations(gain, offset):
     ratio = (err / (ATOL + RTOL * ref.abs())).max().item()
     print(f"gain {gain} offset {offset}: max|err| {err.max().item():.3e}, ref rms {ref.pow(2).mean().sqrt().item():.3e}, worst err/tol {ratio:.2f}")
     assert ratio <= 1.0, f"worst err/tol {ratio:.2f}"
+
+
+# ------------------------------------------------------------------ every documented switch keeps parity
+@pytest.mark.parametrize("env", ["NS2VC_XF=0", "NS2VC_KSPLIT=0", "NS2VC_MERGE_FF=0", "NS2VC_LNFOLD=0", "NS2VC_ATTN_P=split",
+                                 "NS2VC_PDL=0", "NS2VC_GRAPH=0"])
+def test_diagnostic_switches_keep_parity(env):
+    """The environment switches of README.md (A/B paths and numerical fallbacks) are read once per process / engine, so each one is
+    exercised in a child process on the per-op tap test, the reference full-config fixture and the tiny sampler fixtures."""
+    import subprocess
+    import sys
+    k, v = env.split("=")
+    child_env = dict(os.environ, **{k: v})
+    sel = "tiny_forward_every_op and tc or full_forward_matches_reference_fixture or fused_samplers_tiny_vs_reference_fixture"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k", sel],
+                       env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " passed" in r.stdout, f"{env}:\n{r.stdout[-1500:]}\n{r.stderr[-500:]}"
