@@ -250,6 +250,7 @@ def main():
     from ns2vc_b200 import _lib, api
     from ns2vc_b200.arch import ns2vc_denoiser_config
     from ns2vc_b200.fused import DenoiserSession
+    from ns2vc_b200.shard import gather_latents
     from ns2vc_b200.synth import make_state_dict
     from ns2vc_b200.unet import UNet1DConditionModel
 
@@ -281,13 +282,13 @@ def main():
         sess = get_session(unet, content_d, prompt_d, mask_d)
         out = sess.sample_dpmpp_2m(x_d, ns, ts)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            gather_latents(out, out=gathered)
         return out
 
     def run_e2e():
         out = api.sample_latents(unet, hin["x"], hin["content"], hin["prompt"], hin["refer_lengths"], steps=nfe, device=dev)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            gather_latents(out, out=gathered)
             return gathered.to("cpu", non_blocking=False) if rank == 0 else out[:1, :1, :1].cpu()
         return out.cpu()
 

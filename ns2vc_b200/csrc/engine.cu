@@ -851,14 +851,15 @@ int build_programs(ns2vc_unet* h, int B, int T, int S, void* ws, size_t* bytes_o
           }
           {
             GemmOp g = bld.gemm_base(s.conv2, TL);
-            const int j0 = bld.add_src(g, a_h);
-            bld.xseg(g, j0, 0, s.cout, 3, 0, no, 1, 0);
             g.flags = EPI_BIAS; g.bias = s.bias2;
+            // the raw 1x1 shortcut panels go first: their MMAs run while the transform warps still derive the GroupNorm affine
             if (s.shortcut) {
               const int a0 = bld.add_src(g, cur.sp);
               bld.xseg(g, a0, 0, s.c1, 1, 3 * no, 0, 0, 0);
               if (s.c2) { const int a1 = bld.add_src(g, cat2.sp); bld.xseg(g, a1, 0, s.c2, 1, 3 * no + n1, 0, 0, 0); }
             } else { g.flags |= EPI_RESIDUAL; g.res = s1; g.res_ld = s.c1; }
+            const int j0 = bld.add_src(g, a_h);
+            bld.xseg(g, j0, 0, s.cout, 3, 0, no, 1, 0);
             g.pre = bld.affine_desc(h1_st, s.cout, nullptr, 0, TL, PREP_AFFINE_SILU, c.norm_eps, h->W(s.p + ".norm2.weight"),
                                     h->W(s.p + ".norm2.bias"), h->film_total);
             g.pre_film = c.time_scale_shift ? film + s.film_off : nullptr;

@@ -366,18 +366,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (have_aff) prep_fetch_norm_weights(pr, C, pg, pbv, xt, 256);
       pdl_wait();
       XTRACE(0);
-      if (have_aff) {
-        prep_fetch_film(pr, op.pre_film, xb, C, fs, fbv, xt, 256);
-        for (int c = C + xt; c < ((C + 63) & ~63); c += 256) { aff[c] = 0.f; aff[kXfMaxC + c] = 0.f; }   // padding channels of the last block
-        prep_affine(pr, xb, C, kXfMaxC, aff, pg, pbv, fs, fbv, xt, 256, sync256);
-      }
-      XTRACE(1);
+      if (have_aff) prep_fetch_film(pr, op.pre_film, xb, C, fs, fbv, xt, 256);
+      bool aff_done = !have_aff;                              // derived when the first normalised segment comes up: raw (shortcut)
+                                                              // panels queued before it are released to the MMA warp at once
       const bool silu = have_aff && pr.mode == PREP_AFFINE_SILU;
       int it = 0, gp = 0;
       for (int si = 0; si < op.nxs; ++si) {
         const XSeg& xs = op.xs[si];
         const int rows = xs.ntap == 3 ? kPanelRows : BM, tfirst = xt0 + (xs.ntap == 3 ? -1 : 0);
         const int Tsrc = op.src[xs.src].T;
+        if (xs.xf && !aff_done && gp < p_hi && gp + xs.ncb > p_lo) {   // (only if some of this segment's panels are this CTA's)
+          for (int c = C + xt; c < ((C + 63) & ~63); c += 256) { aff[c] = 0.f; aff[kXfMaxC + c] = 0.f; }   // padding channels of the last block
+          prep_affine(pr, xb, C, kXfMaxC, aff, pg, pbv, fs, fbv, xt, 256, sync256);
+          aff_done = true;
+          XTRACE(1);
+        }
         for (int cb = 0; cb < xs.ncb; ++cb, ++gp) {
           if (gp < p_lo || gp >= p_hi) continue;
           const int sa = it % kXAStages;
