@@ -378,16 +378,18 @@ def main():
         peaks = read_peaks()
         fl_gemm, fl_attn = flops_per_forward(cfg, B, T, S, gemm_only=True)
         fl_gemm += B * 4 * S * cfg.cross_attention_dim * sum(op.cout for op in __import__("ns2vc_b200.arch", fromlist=["build_plan"]).build_plan(cfg) if op.kind == "xformer")  # step-invariant K/V projections (SURVEY 8d counts them)
-        dom = max(excl, key=lambda k: excl[k])
-        dom_ms = excl[dom] / 1e3
+        gemm_kinds = [k for k in excl if k.startswith("gemm")]                  # gemm_tc (one launch per GEMM) + gemm_chain (chained launches)
+        gemm_us, gemm_n = sum(excl[k] for k in gemm_kinds), sum(cnt[k] for k in gemm_kinds)
+        dom = "attention" if excl.get("attention", 0.0) > gemm_us else "gemm_tc"
+        dom_ms = (excl["attention"] if dom == "attention" else gemm_us) / 1e3
+        dom_n = cnt["attention"] if dom == "attention" else gemm_n
         assert dom_ms <= ms / args.steps / nfe * 1.25, "a kernel cannot take longer than the step it is part of"
         if dom == "attention":
             ach = fl_attn / (dom_ms * 1e-3) / 1e12
             alg = f"{fl_attn / 1e9:.1f} GFLOP QK^T+PV per forward"
         else:
-            dom = "gemm_tc"
-            ach = fl_gemm / (excl[dom] / 1e3 * 1e-3) / 1e12
-            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic, SURVEY 8d; the 3xBF16 split issues 3x this on the tensor pipe)"
+            ach = fl_gemm / (dom_ms * 1e-3) / 1e12
+            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic, SURVEY 8d; the 3xBF16 split issues 3x this on the tensor pipe); gemm_tc + gemm_chain launches"
         traffic = ncu_traffic(dom)
         whole = survey_flops(B, T, S)
         ms_fwd = ms / args.steps / nfe
@@ -397,7 +399,7 @@ def main():
                            "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, cold-cache capture, profiles/r02_ncu_launches.md)",
                            "algorithmic": alg, "peak_source": peaks["src"], "issued_tflops": 3 * ach if dom == "gemm_tc" else ach,
                            "frac_issued": (3 * ach if dom == "gemm_tc" else ach) / peaks["tflops"],
-                           "kernel_ms_per_forward": dom_ms, "launch_avg_us": excl[dom] / cnt[dom],
+                           "kernel_ms_per_forward": dom_ms, "launch_avg_us": 1e3 * dom_ms / dom_n,
                            "timing": "exclusive in-step time of the kernel's launches from %globaltimer [entry, exit] spans of one graph-replayed forward (sums to the forward; never above ms_per_unet_forward)",
                            "step": {"ms_per_unet_forward": ms_fwd, "algorithmic_gflop": whole / 1e9, "algorithmic_gb": SURVEY_BYTES_CFG2 / 1e9,
                                     "t_hbm_ms": t_hbm, "t_tc_ms": t_tc, "t_tc_ms_3xbf16_issued": 3 * t_tc,

@@ -302,9 +302,17 @@ class UNet1DConditionModel(nn.Module):
         """Opaque engine handle with the current parameter values packed for the tensor cores
         (re-packed when any parameter changed: optimizer step, load_state_dict, .to())."""
         L = _lib.lib()
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # 701 (storage, version) pairs over a cached list of the Parameter objects: the module tree is fixed after construction,
+        # `.to()` / `load_state_dict` / optimizers change storage or bump versions of the SAME objects (the recursive
+        # `self.parameters()` walk on every forward of the generic path was ~1 ms of host time per call)
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        sig = tuple((p.data_ptr(), p._version) for p in plist)
         if self._handle is not None and self._wsig == sig and self._handle_device == device:
             return self._handle
+        plist = self.__dict__["_plist"] = list(self.parameters())     # something changed: re-walk the tree before re-packing
+        sig = tuple((p.data_ptr(), p._version) for p in plist)
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
             if self._handle is None or self._handle_device != device:
