@@ -126,7 +126,6 @@ struct XSeg {
 };
 
 struct GemmOp {
-  TMap tmap[2 * kMaxSrc];      // [2*i] = hi, [2*i+1] = lo of src[i]; box = {64 ch, 128 rows, 1}
   SplitBuf src[kMaxSrc];
   int nsrc;
   GSeg seg[kMaxSeg];
@@ -160,7 +159,6 @@ struct GemmOp {
   double* stat_sq;
   unsigned long long* trace;   // diagnostics: 8 globaltimer stamps of CTA (0,0), or nullptr
   unsigned long long* span;    // diagnostics: [min entry, max exit] of the grid, or nullptr
-  TMap tmap_out[3];            // TMA store maps: fp32 out (box 32 cols x 32 rows, SWIZZLE_128B), out_hi, out_lo (SWIZZLE_64B)
   int tma_out;                 // bit 0: fp32 output goes through tmap_out[0]; bit 1: split output through tmap_out[1..2]
   int bn;                      // N tile (64 / 128), chosen by plan_gemm()
   // Panel mode (xmode = 1): the GroupNorm(+FiLM)(+SiLU) of the A operand is applied INSIDE this kernel (reference
@@ -177,6 +175,10 @@ struct GemmOp {
   XSeg xs[kMaxXSeg];
   const PrepOp* pre;           // GroupNorm parameters of the normalised segments (device memory; only the affine part is used)
   const float* pre_film;       // FiLM rows read by that affine (nullptr: none) - kept here because they change per forward
+  // ---- tensor maps last: the TMA unit reads them by address (kernel-parameter space); the kernel copies only the fields
+  // ---- before them into shared memory (kGemmOpHotBytes)
+  TMap tmap[2 * kMaxSrc];      // [2*i] = hi, [2*i+1] = lo of src[i]; box = {64 ch, 128 rows, 1} (130 rows for a panel-mode k=3 source)
+  TMap tmap_out[3];            // TMA store maps: fp32 out (box 32 cols x 32 rows, SWIZZLE_128B), out_hi, out_lo (SWIZZLE_64B)
 };
 // Choose the N tile for op (fills op.bn); must precede encode_tmaps().
 void plan_gemm(GemmOp& op);

@@ -186,7 +186,9 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 __device__ __forceinline__ long long gclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
 #define ETRACE(i) do { if (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) op.trace[8 + (i)] = gclk(); } while (0)
 
-static_assert(sizeof(GemmOp) <= 2688 && sizeof(PrepOp) <= 320, "GemmOp must fit the shared-memory descriptor copy");
+// only the fields in front of the tensor maps are copied to shared memory (the maps are used by address)
+constexpr int kGemmOpHotBytes = (int)offsetof(GemmOp, tmap);
+static_assert(kGemmOpHotBytes % 16 == 0 && kGemmOpHotBytes <= 2688 && sizeof(PrepOp) <= 320, "GemmOp's hot part must fit the shared-memory descriptor copy");
 
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   {
     const uint4* src = reinterpret_cast<const uint4*>(&op_param);
     uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::kOffDesc);
-    for (int i = tid; i < (int)(sizeof(GemmOp) / 16); i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < kGemmOpHotBytes / 16; i += kThreads) dst[i] = src[i];
     // GroupNorm parameters of a panel-mode launch (device memory, static): parked behind the operator copy
     if (XF && op_param.xmode && op_param.pre) {
       const uint4* ps = reinterpret_cast<const uint4*>(op_param.pre);
@@ -258,7 +260,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (XF) { mbar_init(xr_ready(), 1); mbar_init(xr_full(), kEpiWarps); for (int a = 0; a < kXAStages; ++a) mbar_init(a_ready(a), kEpiWarps); for (int a = 0; a < kXBStages; ++a) { mbar_init(b_full(a), 1); mbar_init(b_empty(a), 1); } }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * op_param.nsrc; ++i) prefetch_tmap(&tmaps[i]);
     // the store maps too: the first bulk store through a cold descriptor costs a ~0.5 us fetch on the epilogue's critical path
@@ -267,10 +268,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (op_param.tma_out & 2) { prefetch_tmap(&pm[1]); prefetch_tmap(&pm[2]); }
   }
   pdl_trigger();
+#ifdef NS2VC_TMEM_LATE
+  __syncthreads();                                          // descriptor copy + armed barriers: the TMA producer may go
+  // The tensor-memory allocation (~0.4 us) is needed by the MMA issuer and the epilogue only: it runs AFTER the CTA-wide barrier
+  // and is joined by warps 1-9 alone, so the producer's weight / activation loads are in flight while it completes.
+  uint32_t tmem_base = 0;
+  if (warp >= 1) {
+    if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
+    tc_fence_before();
+    asm volatile("bar.sync 2, 288;" ::: "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
+#else
+  if (warp == 2) tmem_alloc(smem_u32((const void*)tmem_slot), 2 * kAccCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#endif
   if (tid == 0 && tr0) TRACE(1);
   if constexpr (XF) if (ks > 1) cluster_sync_all();          // split-K: the partner's mbarriers exist before anyone arrives on them remotely
 

@@ -3,9 +3,11 @@
 API mirror of the reference's ``sampler/dpm_solver.py`` (``NoiseScheduleVP`` :6-167,
 ``model_wrapper`` :170-334, ``interpolate_fn`` :1253-1292, ``expand_dims`` :1295) and of the
 near-identical copies in ``sampler/uni_pc.py`` (:6-234; no ``numerical_clip_alpha`` there).
-Written from the published DPM-Solver / UniPC definitions; arithmetic is kept in the
-reference's op order so that every schedule scalar is bit-equal to the reference's fp32 value
-(checked in tests/test_schedule.py against fixtures generated from the reference).
+The schedule methods are a handful of one-line formulas whose op ORDER is part of the contract: every scalar
+must be bit-equal to the reference's fp32 value (the fused samplers precompute all per-step coefficients from
+them), so they follow the reference statement for statement; `interpolate_fn` (searchsorted instead of the
+reference's sort/gather) and `WrappedModel` are restructured.  Checked against fixtures generated from the
+reference in tests/test_samplers_cpu.py::test_schedule_bit_exact and tests/test_oracle_golden.py.
 """
 from __future__ import annotations
 
