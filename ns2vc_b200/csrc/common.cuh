@@ -66,6 +66,7 @@ struct GnStats {
   const float* gamma; const float* beta;   // [C1+C2]
   const float* film; int film_ld;          // nullptr or [B, film_ld]: scale at film[b,c], shift at film[b,C+c]
   int G; float eps;
+  double inv_n;                            // 1 / (T * C/G): elements per group, reciprocal taken on the host (0: derive it on the device)
 };
 struct alignas(16) PrepOp {      // (16-byte multiples: arrays of descriptors are copied with 128-bit loads)
   const float* src1; int ld1; int C1;

@@ -587,6 +587,7 @@ struct Builder {
     p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
     p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
     p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
+    p.gn.inv_n = 1.0 / ((double)Tn * ((C1 + C2) / p.gn.G));
     // all descriptors of a program sit in one workspace array and go to the device in ONE copy when the program is complete
     if ((int)aff_host.size() >= aff_cap) { err = -1; set_error("internal: affine descriptor table full"); return nullptr; }
     aff_host.push_back(p);
@@ -621,6 +622,7 @@ struct Builder {
     p.gn.sum1 = st1; p.gn.sq1 = st1 ? st1 + (size_t)B * C1 : nullptr;
     p.gn.sum2 = st2; p.gn.sq2 = st2 ? st2 + (size_t)B * C2 : nullptr;
     p.gn.gamma = gamma; p.gn.beta = beta; p.gn.film = film; p.gn.film_ld = film_ld; p.gn.G = h->cfg.norm_num_groups; p.gn.eps = eps;
+    p.gn.inv_n = 1.0 / ((double)Tn * ((C1 + C2) / p.gn.G));
   }
   void emit_ln_split(const float* x, int ld, int M, int C, const float* gamma, const float* beta, const SplitBuf& o) {
     Launch l; l.kind = Launch::LN_SPLIT; l.a = x; l.i0 = ld; l.i1 = M; l.i2 = C; l.f0 = 1e-5f; l.b = gamma; l.c = beta; l.split = o;

@@ -5,9 +5,10 @@
 //
 // issued as TWO MMAs per 16-wide k-step: A_hi x [B_hi ; B_lo] (one N = 2*BN instruction: the hi and lo
 // weight tiles are adjacent in shared memory, its result lands in two TMEM column groups) and
-// A_lo x B_hi (N = BN, accumulating into the first group); the epilogue adds the two groups.  A
-// tcgen05.mma of these shapes costs ~80 SM cycles whatever its N (measured, profiles/r01_attn_incta_timeline.txt),
-// so instruction count, not FLOPs, sets the main-loop time.
+// A_lo x B_hi (N = BN, accumulating into the first group); the epilogue adds the two groups.  In a
+// long chain a tcgen05.mma (M = 128, K = 16, SS) costs max(~50, N/2) SM cycles - 114 per k-step at BN = 64 -
+// whether or not consecutive MMAs hit the same accumulator columns (scripts/micro/mma_rate.cu,
+// profiles/r02_mma_rate.txt): folding B_hi | B_lo into one N = 2*BN instruction is what keeps the count down.
 //
 // fp32-level parity with the reference (rtol 1e-3 / atol 1e-4) cannot be met by single-pass
 // bf16/tf32 MMAs, so both operands are split x = hi + lo (bf16 each) and
@@ -426,10 +427,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 float x0, x1;
                 upk2(fadd2(pk2(__uint_as_float(hw[j] << 16), __uint_as_float(hw[j] & 0xffff0000u)),
                            pk2(__uint_as_float(lw[j] << 16), __uint_as_float(lw[j] & 0xffff0000u))), x0, x1);
-                float y0, y1;
-                upk2(ffma2(pk2(x0, x1), pk2(scv[2 * j], scv[2 * j + 1]), pk2(shv[2 * j], shv[2 * j + 1])), y0, y1);
-                if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-                v[2 * j] = y0 * keep; v[2 * j + 1] = y1 * keep;
+                unsigned long long y2 = ffma2(pk2(x0, x1), pk2(scv[2 * j], scv[2 * j + 1]), pk2(shv[2 * j], shv[2 * j + 1]));
+                if (silu) y2 = silu2(y2);
+                upk2(fmul2(y2, pk2(keep, keep)), v[2 * j], v[2 * j + 1]);
               }
               split8(v, h4, l4);
             };
