@@ -378,7 +378,7 @@ def main():
         peaks = read_peaks()
         fl_gemm, fl_attn = flops_per_forward(cfg, B, T, S, gemm_only=True)
         fl_gemm += B * 4 * S * cfg.cross_attention_dim * sum(op.cout for op in __import__("ns2vc_b200.arch", fromlist=["build_plan"]).build_plan(cfg) if op.kind == "xformer")  # step-invariant K/V projections (SURVEY 8d counts them)
-        gemm_kinds = [k for k in excl if k.startswith("gemm")]                  # gemm_tc (one launch per GEMM) + gemm_chain (chained launches)
+        gemm_kinds = [k for k in excl if k.startswith("gemm")]                  # every GEMM instantiation (plain / folded-LayerNorm / panel mode) is one kind
         gemm_us, gemm_n = sum(excl[k] for k in gemm_kinds), sum(cnt[k] for k in gemm_kinds)
         dom = "attention" if excl.get("attention", 0.0) > gemm_us else "gemm_tc"
         dom_ms = (excl["attention"] if dom == "attention" else gemm_us) / 1e3
@@ -389,7 +389,7 @@ def main():
             alg = f"{fl_attn / 1e9:.1f} GFLOP QK^T+PV per forward"
         else:
             ach = fl_gemm / (dom_ms * 1e-3) / 1e12
-            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic, SURVEY 8d; the 3xBF16 split issues 3x this on the tensor pipe); gemm_tc + gemm_chain launches"
+            alg = f"{fl_gemm / 1e9:.1f} GFLOP conv+linear per forward (algorithmic, SURVEY 8d; the 3xBF16 split issues 3x this on the tensor pipe); all gemm_tc instantiations"
         traffic = ncu_traffic(dom)
         whole = survey_flops(B, T, S)
         ms_fwd = ms / args.steps / nfe
