@@ -76,7 +76,13 @@ __device__ __forceinline__ void tmem_ld_nw<8>(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+// Per-tile role timeline of CTA (0,0,0) (scripts/trace_attn.py): compiled in only with -DNS2VC_ATTN_TRACE (NVCC_EXTRA of build.sh) -
+// eight predicated stamps per key tile are ~7 % of the softmax loop's issue slots and a live pointer in a 56-register kernel.
+#ifdef NS2VC_ATTN_TRACE
 #define ATRACE(j, slot) do { if (tr && (j) < 16) tr[(j) * 16 + (slot)] = clk(); } while (0)
+#else
+#define ATRACE(j, slot) do { } while (0)
+#endif
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int DHP, int PB, bool BIAS, bool PF16>
@@ -106,7 +112,9 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
     op.trace[256 + 3 * cta_lin] = gtime_ns();
     op.trace[256 + 3 * cta_lin + 2] = smid;
   }
+#ifdef NS2VC_ATTN_TRACE
   unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ((warp == 0 && lane <= 1) || (warp == 1 && lane == 0))) ? op.trace : nullptr;
+#endif
   if (tid == 0) {
     mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1);
     for (int s = 0; s < NST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
       ATRACE(j, 0);
-      mbar_wait(s_full, par);
+      mbar_wait_quiet(s_full, par);
       tc_fence_after();
       ATRACE(j, 1);
       float sv[32];
@@ -284,37 +292,35 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
       const float corr = ex2f(m_run - m_new);
       const unsigned long long nm2 = pk2(-m_new, -m_new);
       unsigned long long lt2 = pk2(0.f, 0.f);
-      uint32_t ph2[PF16 ? 16 : 1];
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        float a, bq;
-        if (BIAS) upk2(fadd2(pk2(sv[c], sv[c + 1]), nm2), a, bq);
-        else upk2(ffma2(pk2(sv[c], sv[c + 1]), qs2, nm2), a, bq);
-        sv[c] = ex2f(a); sv[c + 1] = ex2f(bq);
-        if (PF16) {                                         // the weights ARE the fp16-rounded values: numerator and row sum agree
-          const uint32_t h2 = pack_f16x2(sv[c], sv[c + 1]);
-          ph2[c >> 1] = h2;
-          sv[c] = f16lo_to_f32(h2); sv[c + 1] = f16hi_to_f32(h2);
-        }
-        lt2 = fadd2(lt2, pk2(sv[c], sv[c + 1]));
-      }
-      float lt, lt_hi;
-      upk2(lt2, lt, lt_hi);
-      lt += lt_hi;
-      l_run = l_run * corr + lt;
-      m_run = m_new;
-      ATRACE(j, 4);
-      if (j > 0) {                                          // PV(j-1) has retired: the P buffer is free, O_tile(j-1) is complete
-        mbar_wait(o_full, par ^ 1u);
+      // PV(j-1) was issued as soon as P(j-1) was complete, i.e. before these warps even picked up S(j): by now it has
+      // retired (the P buffer is free, O_tile(j-1) complete).  Waiting for it HERE lets every 8-column group of P go to
+      // shared memory as soon as it is computed instead of staying live in registers across the wait (the kernel runs
+      // at 56 registers per thread for four CTAs per SM).
+      if (j > 0) {
+        mbar_wait_quiet(o_full, par ^ 1u);
         tc_fence_after();
       }
       ATRACE(j, 5);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t ph2[4];
+#pragma unroll
+        for (int c = 8 * c8; c < 8 * c8 + 8; c += 2) {
+          float a, bq;
+          if (BIAS) upk2(fadd2(pk2(sv[c], sv[c + 1]), nm2), a, bq);
+          else upk2(ffma2(pk2(sv[c], sv[c + 1]), qs2, nm2), a, bq);
+          sv[c] = ex2f(a); sv[c + 1] = ex2f(bq);
+          if (PF16) {                                       // the weights ARE the fp16-rounded values: numerator and row sum agree
+            const uint32_t h2 = pack_f16x2(sv[c], sv[c + 1]);
+            ph2[(c >> 1) & 3] = h2;
+            sv[c] = f16lo_to_f32(h2); sv[c + 1] = f16hi_to_f32(h2);
+          }
+          lt2 = fadd2(lt2, pk2(sv[c], sv[c + 1]));
+        }
         const int ck = hf * 4 + c8;
         const int off = r * 128 + ((ck ^ (r & 7)) << 4);
         if (PF16) {
-          *reinterpret_cast<uint4*>(smem + C::kOffP + off) = make_uint4(ph2[4 * c8], ph2[4 * c8 + 1], ph2[4 * c8 + 2], ph2[4 * c8 + 3]);
+          *reinterpret_cast<uint4*>(smem + C::kOffP + off) = make_uint4(ph2[0], ph2[1], ph2[2], ph2[3]);
         } else {
           uint4 hi, lo;
           split8(sv + 8 * c8, hi, lo);
@@ -322,6 +328,12 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
           *reinterpret_cast<uint4*>(smem + C::kOffP + C::kPBytes + off) = lo;
         }
       }
+      float lt, lt_hi;
+      upk2(lt2, lt, lt_hi);
+      lt += lt_hi;
+      l_run = l_run * corr + lt;
+      m_run = m_new;
+      ATRACE(j, 4);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
       if (j > 0) add_o_tile(par ^ 1u, corr);
       ATRACE(j, 7);
     }
-    mbar_wait(o_full, (uint32_t)((ntiles - 1) & 1));
+    mbar_wait_quiet(o_full, (uint32_t)((ntiles - 1) & 1));
     tc_fence_after();
     add_o_tile((uint32_t)((ntiles - 1) & 1), 1.0f);
 
