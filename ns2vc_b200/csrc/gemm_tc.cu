@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (int si = 0; si < op.nxs; ++si) ncblk += op.xs[si].ncb;
     const int p_lo = ncblk * kr / ks, p_hi = ncblk * (kr + 1) / ks;   // this CTA's channel blocks (global panel indices)
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         // weights of the first two channel blocks before the dependency wait, activations after it
         auto issue_w = [&](const XSeg& xs, int cb, int sb) {
           const uint32_t b0 = base + kXOffB + sb * kXBStageBytes;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         int it = 0, gp = 0;
         for (int si = 0; si < op.nxs; ++si) {
           const XSeg& xs = op.xs[si];
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
   // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
   const int npf = nkb < nst ? nkb : nst;
-  if (!xpanel && warp == 0 && lane == 0) {
+  if (!xpanel && warp == 0 && elect_one()) {
     const int n0 = (bid % n_tiles) * BN;
     for (int kb = 0; kb < npf; ++kb) {
       const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && !xpanel) {
+    if (!xpanel && elect_one()) {
       const int npre = npf;
       pdl_wait();
       if (tr0) TRACE(2);
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && !xpanel) {
+    if (!xpanel && elect_one()) {
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * kAccCols);

@@ -45,6 +45,14 @@ __device__ __forceinline__ void mbar_wait_quiet(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
 }
+// One lane of a CONVERGED warp: ptxas knows that the region guarded by elect.sync runs on a single thread and issues the
+// uniform-datapath instructions (UTCHMMA, UTMALDG, UBLKCP...) directly; behind a `lane == 0` test it wraps every one of them
+// in an ELECT / BRA.U.ANY serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
