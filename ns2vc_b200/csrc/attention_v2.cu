@@ -1,17 +1,18 @@
 // tcgen05 flash attention, v2 (product path): TMA-fed and warp-specialised.
 //   out = softmax(q k^T * dh^-0.5 + bias) v      (reference attention_processor.py:1025-1036)
 //
-// CTA = 128 queries of one (batch, head); key tiles of 64; 320 threads:
-//   warp 0      TMA producer: Q once, then a ring of {K_hi, K_lo, V_hi, V_lo} tiles.  q / k / v are the
-//               bf16 hi/lo "split" tensors the projection GEMMs' epilogues wrote (token-major), so a
-//               tile is a plain 3-D box {head channels, 64 keys, 1 batch} - no conversion, no transpose.
-//   warp 1      MMA issuer: S[128x64] = Q K^T (A, B K-major) and O_tile[128xdh] = P V with V as an
-//               MN-major B operand (dh contiguous, keys = MMA K dimension), each as 3 bf16 MMAs over the
-//               hi/lo splits, fp32 accumulators in TMEM.  x_hi*[y_hi ; y_lo] is one instruction of twice the N
-//               (two TMEM column groups), x_lo*y_hi a second one: 2 MMAs per k-step instead of 3.
-//   warps 2-9   online softmax, two threads per query row (32 score columns and dh/2 output columns
+// CTA = 128 queries of one (batch, head); key tiles of 64; 288 threads:
+//   warp 0      one elected thread (elect.sync) is TMA producer and MMA issuer at once.  Producer: Q once, then a ring of
+//               {K_hi, K_lo, V_hi, V_lo} tiles.  q / k / v are the bf16 hi/lo "split" tensors the projection GEMMs'
+//               epilogues wrote (token-major), so a tile is a plain 3-D box {head channels, 64 keys, 1 batch} - no
+//               conversion, no transpose.  MMA issuer: S[128x64] = Q K^T (A, B K-major) and O_tile[128xdh] = P V with V
+//               as an MN-major B operand (dh contiguous, keys = MMA K dimension), each as 3 bf16 MMAs over the hi/lo
+//               splits, fp32 accumulators in TMEM.  x_hi*[y_hi ; y_lo] is one instruction of twice the N (two TMEM column
+//               groups), x_lo*y_hi a second one: 2 MMAs per k-step instead of 3.  The ring stage of tile j-1 is refilled
+//               right before PV(j) is issued (PV(j-1) has retired by then: the softmax warps waited for it).
+//   warps 1-8   online softmax, two threads per query row (32 score columns and dh/2 output columns
 //               each): exp2 with scale*log2(e) folded into one FFMA, P written as a SWIZZLE_128B A operand.
-// The three roles only meet through mbarriers: S(j+1) is issued as soon as the softmax warps have
+// The roles only meet through mbarriers: S(j+1) is issued as soon as the softmax warps have
 // pulled S(j) out of TMEM, and P(j) V(j) runs under softmax(j+1), so neither MMA latency nor a
 // CTA-wide barrier sits on the per-tile critical path.
 // Shared-memory rows of the Q/K/V tiles are `PB` bytes wide (32/64/128 = the TMA box width and the
@@ -27,7 +28,7 @@ namespace ns2vc {
 namespace {
 
 constexpr int kQ = 128, kKeys = 64;
-constexpr int kThreadsV2 = 288;                          // warp 0: TMA producer (lane 0) + MMA issuer (lane 1); warps 1-8: softmax
+constexpr int kThreadsV2 = 288;                          // warp 0: TMA producer + MMA issuer (one elected thread); warps 1-8: softmax
 
 template <int DHP, int PB, bool PF16, bool BIAS> struct ACfg {
   static constexpr int NST = (PB == 128) ? 2 : 3;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
     op.trace[256 + 3 * cta_lin + 2] = smid;
   }
 #ifdef NS2VC_ATTN_TRACE
-  unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ((warp == 0 && lane <= 1) || (warp == 1 && lane == 0))) ? op.trace : nullptr;
+  unsigned long long* tr = (op.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 0 || (warp == 1 && lane == 0))) ? op.trace : nullptr;
 #endif
   if (tid == 0) {
     mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1);
@@ -133,32 +134,28 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
   const uint32_t tS = tmem_base, tO = tmem_base + C::kSCols;   // O: two buffers of kOCols columns (tile parity)
   const uint32_t sQ = base + C::kOffQ, sP = base + C::kOffP, sKV = base + C::kOffKV;
 
-  // Warp 0 hosts two independent single-thread roles as divergent lanes (independent thread scheduling): lane 0 streams
-  // the tiles, lane 1 issues the MMAs.  Eight softmax warps + this one = 288 threads, so that four CTAs fit an SM.
+  // Warp 0: ONE elected thread streams the tiles AND issues the MMAs (eight softmax warps + this one = 288 threads, so that
+  // four CTAs fit an SM).  Under elect.sync ptxas issues the uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) back to
+  // back; as two divergent lanes of one warp each of them sat in an ELECT / BRA.U.ANY serialisation loop.
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      pdl_wait();                                           // q / k / v are the previous kernels' outputs
-      mbar_arrive_expect_tx(q_full, 2u * C::kQBytes);
-      tma_load_3d(sQ, &op.tm[0], op.q_c0 + h * dh, q0, b, q_full);
-      tma_load_3d(sQ + C::kQBytes, &op.tm[1], op.q_c0 + h * dh, q0, b, q_full);
-      for (int j = 0; j < ntiles; ++j) {
+    if (elect_one()) {
+      auto load_kv = [&](int j) {
         const int stage = j % NST;
-        if (j >= NST) mbar_wait(kv_empty(stage), (uint32_t)(((j / NST) & 1) ^ 1));
-        ATRACE(j, 12);
         const uint32_t dst = sKV + stage * C::kStageBytes;
         mbar_arrive_expect_tx(kv_full(stage), (uint32_t)C::kStageBytes);
         tma_load_3d(dst, &op.tm[2], op.k_c0 + h * dh, j * kKeys, b, kv_full(stage));
         tma_load_3d(dst + C::kTBytes, &op.tm[3], op.k_c0 + h * dh, j * kKeys, b, kv_full(stage));
         tma_load_3d(dst + 2 * C::kTBytes, &op.tm[4], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
         tma_load_3d(dst + 3 * C::kTBytes, &op.tm[5], op.v_c0 + h * dh, j * kKeys, b, kv_full(stage));
-      }
-    } else if (lane == 1) {
-      // ===================== MMA issuer =====================
+      };
+      pdl_wait();                                           // q / k / v are the previous kernels' outputs
+      mbar_arrive_expect_tx(q_full, 2u * C::kQBytes);
+      tma_load_3d(sQ, &op.tm[0], op.q_c0 + h * dh, q0, b, q_full);
+      tma_load_3d(sQ + C::kQBytes, &op.tm[1], op.q_c0 + h * dh, q0, b, q_full);
+      for (int j = 0; j < NST && j < ntiles; ++j) { ATRACE(j, 12); load_kv(j); }
       // Every product is hi*hi + hi*lo + lo*hi.  The hi and lo tiles of K (and of V) are adjacent in shared memory,
       // so X_hi x [Y_hi ; Y_lo] is ONE instruction of twice the N whose result lands in two TMEM column groups;
-      // X_lo x Y_hi accumulates into the first group and the softmax warps add the groups.  (A tcgen05.mma of
-      // these shapes costs ~80 SM cycles whatever its N: instruction count is what the tensor pipe charges for.)
+      // X_lo x Y_hi accumulates into the first group and the softmax warps add the groups.
       constexpr uint32_t idS2 = umma_idesc_bf16(kQ, 2 * kKeys), idS1 = umma_idesc_bf16(kQ, kKeys);                    // A, B K-major
       constexpr uint32_t idO2 = umma_idesc_bf16(kQ, 2 * C::NO) | (1u << 16), idO1 = umma_idesc_bf16(kQ, C::NO) | (1u << 16);   // B (= V) MN-major
       auto issue_S = [&](int j) {
@@ -183,8 +180,19 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
       mbar_wait(kv_full(0), 0);
       tc_fence_after();
       issue_S(0);
+      // Refill of the ring stage tile j-1 occupied (with tile j-1+NST), once PV(j-1) has retired.  Three stages: after the
+      // wait for P(j) - the softmax warps waited for PV(j-1) before they stored P(j), so the stage is free without waiting.
+      // Two stages (128-byte head rows): tile j+1 itself goes there, so it is refilled first thing in iteration j.
+      auto refill = [&](int j) {
+        if (j >= 1 && j - 1 + NST < ntiles) {
+          mbar_wait(kv_empty((j - 1) % NST), (uint32_t)(((j - 1) / NST) & 1));
+          ATRACE(j - 1 + NST, 12);
+          load_kv(j - 1 + NST);
+        }
+      };
       for (int j = 0; j < ntiles; ++j) {
         const uint32_t par = (uint32_t)(j & 1);
+        if (NST < 3) refill(j);
         if (j + 1 < ntiles) {
           mbar_wait(kv_full((j + 1) % NST), (uint32_t)(((j + 1) / NST) & 1));
           mbar_wait(s_empty, par);                          // every softmax thread holds S(j) in registers
@@ -196,6 +204,7 @@ __global__ void __launch_bounds__(kThreadsV2, ACfg<DHP, PB, PF16, BIAS>::kMinCta
         mbar_wait(p_full, par);                             // P(j) is in shared memory, O_tile(j-1) has been read
         tc_fence_after();
         ATRACE(j, 10);
+        if (NST >= 3) refill(j);
         const uint32_t vst = sKV + (j % NST) * C::kStageBytes + 2 * C::kTBytes;
 #pragma unroll
         for (int k = 0; k < kKeys / 16; ++k) {
