@@ -140,7 +140,7 @@ __device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) { 
   return reinterpret_cast<float*>(st + row * 128 + ((c4 ^ (row & 7)) << 4));
 }
 // Store one 32-column chunk of this warp's 32 rows.  val: this thread's row (already zero for rows past T_out).
-__device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool stage_f32, int b, int t,
+__device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool leader, bool stage_f32, int b, int t,
                                            int t_warp0, long long m, bool mv, int nbase, const float* val, bool with_split = true,
                                            unsigned long long* stamp = nullptr) {
   if (stage_f32) {
@@ -164,12 +164,12 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
     fence_proxy_async();
     __syncwarp();
     if (stamp) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); stamp[13] = t; }   // fence + syncwarp done
-    // lanes 0 / 1 / 2 issue the fp32 / hi / lo store in ONE warp instruction (a bulk tensor store costs the issuing thread
-    // ~0.4 us; three back-to-back from one lane were the longest step of the epilogue) and own one bulk group each
-    const bool mine = (lane == 0 && (tma & 1)) || ((lane == 1 || lane == 2) && (tma & 2));
-    if (mine) {
-      const uint32_t sa = smem_u32(st) + (lane == 0 ? 0u : lane == 1 ? 4096u : 6144u);
-      tma_store_3d(&tmo[lane], sa, nbase, t_warp0, b);
+    // the warp's elected thread (elect.sync once per warp: `leader`) issues the fp32 / hi / lo stores back to back as ONE bulk
+    // group; behind lane tests every UTMASTG sat in a serialisation loop (~0.4 us per store)
+    if (leader) {
+      const uint32_t sa = smem_u32(st);
+      if (tma & 1) tma_store_3d(&tmo[0], sa, nbase, t_warp0, b);
+      if (tma & 2) { tma_store_3d(&tmo[1], sa + 4096u, nbase, t_warp0, b); tma_store_3d(&tmo[2], sa + 6144u, nbase, t_warp0, b); }
       bulk_commit();
     }
   }
@@ -548,6 +548,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ===================== epilogue (warps 2..9) =====================
     pdl_wait();                                             // residual reads / output writes follow the previous kernel
+    __syncwarp();
+    const bool leader = elect_one();                        // this warp's bulk-store thread (issues, commits and waits for its groups)
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const int cc0 = (warp - 2) >> 2;
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       };
       auto wait_staging = [&]() {                           // the TMA unit must have read the previous chunk out of the staging area
         if (staged_once && op.tma_out) {
-          if (lane < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
         }
       };
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
             }
             wait_staging();
-            emit_chunk(op, tmo, st, lane, false, b, t, t_warp0, m, mv, nbase, val);
+            emit_chunk(op, tmo, st, lane, leader, false, b, t, t_warp0, m, mv, nbase, val);
             staged_once = true;
           }
         } else {
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               atomicAdd(op.row_stats + m * 2 + 1, (double)rq);
             }
             wait_staging();
-            emit_chunk(op, tmo, st, lane, stage_f32, b, t, t_warp0, m, mv, nbase, acc, true,
+            emit_chunk(op, tmo, st, lane, leader, stage_f32, b, t, t_warp0, m, mv, nbase, acc, true,
                        (it == 0 && tr0 && warp == 2 && lane == 0) ? op.trace : nullptr);
             staged_once = true;
             if (it == 0 && tr0) ETRACE(3);
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     // Shared memory must outlive the TMA unit's reads of the staged chunks; the writes themselves are made visible to the
     // dependent grid by grid completion (griddepcontrol.wait on the other side), as in CUTLASS' tma_store_wait.
-    if (op.tma_out && lane < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (op.tma_out && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   if (warp == 2 && lane == 0 && tr0) TRACE(6);
