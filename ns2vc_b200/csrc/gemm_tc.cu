@@ -85,60 +85,59 @@ static_assert(TileCfg<64>::kSmemBytes <= 227 * 1024 && TileCfg<128>::kSmemBytes 
 static_assert(kXOffAff + kXAffBytes <= TileCfg<64>::kPipeBytes && kPrepSlots * kEpiWarps * 32 >= kXfMaxC, "panel mode: stages + affine table inside the pipeline area");
 
 
-// Store 32 consecutive output columns of one row in the layout(s) the op asks for.
-__device__ __forceinline__ void store_chunk(const GemmOp& op, int flags, int b, int t, long long m, int nbase, const float* val) {
-  if (flags & EPI_OUT_NCT) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int n = nbase + j;
-      if (n < op.n_valid) op.out[((long long)b * op.n_valid + n) * op.T_out + t] = val[j];
-    }
-    return;
-  }
-  const bool fullc = nbase + 32 <= op.n_valid;
-  if (flags & EPI_OUT_F32) {
-    float* po = op.out + m * op.out_ld + nbase;
-    if (fullc && ((op.out_ld & 3) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(po + 4 * j) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (nbase + j < op.n_valid) po[j] = val[j];
-    }
-  }
-  if (flags & EPI_OUT_SPLIT) {
-    __nv_bfloat16* ph = op.out_hi + m * op.out_split_ld + nbase;
-    __nv_bfloat16* pl = op.out_lo + m * op.out_split_ld + nbase;
-    if (fullc && ((op.out_split_ld & 7) == 0)) {
-      const bool f16 = nbase >= op.f16_col0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 hi, lo;
-        if (f16) split8_f16(val + 8 * j, hi, lo); else split8(val + 8 * j, hi, lo);
-        *reinterpret_cast<uint4*>(ph + 8 * j) = hi;
-        *reinterpret_cast<uint4*>(pl + 8 * j) = lo;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (nbase + j < op.n_valid) {
-          if (nbase >= op.f16_col0) {
-            const __half h = __float2half_rn(val[j]);
-            reinterpret_cast<__half*>(ph)[j] = h;
-            reinterpret_cast<__half*>(pl)[j] = __float2half_rn(val[j] - __half2float(h));
-          } else {
-            const __nv_bfloat16 h = __float2bfloat16_rn(val[j]);
-            ph[j] = h;
-            pl[j] = __float2bfloat16_rn(val[j] - __bfloat162float(h));
-          }
-        }
-    }
-  }
-}
-
 __device__ __forceinline__ float* stage_f32_ptr(uint8_t* st, int row, int c4) {      // 16-byte group c4 (0..7) of row
   return reinterpret_cast<float*>(st + row * 128 + ((c4 ^ (row & 7)) << 4));
 }
+
+// ---- Cold paths, OUT OF LINE.  Partial chunks (n_valid not a multiple of 32), unaligned leading dimensions and the channel-major
+// output of the head are rare; inlined into the epilogue (32-fold unrolled element code) they were half of the kernel's
+// instructions and raised its register pressure: 2.90 -> 2.74 ms per forward with them compiled out.  The thread parks its 32
+// values in its row of the warp's fp32 staging chunk and these element loops work on that row.
+
+// Element-wise epilogue (bias / GEGLU / row bias / residual / folded LayerNorm) of this thread's parked row; gate values of a
+// GEGLU chunk are parked as plain [32 rows][32] floats behind the fp32 chunk (the 16-bit staging area).
+template <bool LNF>
+__device__ __noinline__ void epi_cold(const GemmOp& op, int b, long long m, int nbase, uint8_t* st, int lane, bool with_gate) {
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    float* pv = stage_f32_ptr(st, lane, j >> 2) + (j & 3);
+    const float g = with_gate ? reinterpret_cast<const float*>(st + 4096)[lane * 32 + j] : 0.f;
+    *pv = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, *pv, g) : 0.f;
+  }
+}
+// Element-wise stores of this thread's parked row in the layout(s) `flags` asks for (channel-major, fp32 or split rows).
+__device__ __noinline__ void store_cold(const GemmOp& op, int flags, int b, int t, long long m, int nbase, uint8_t* st, int lane) {
+  const bool f16 = nbase >= op.f16_col0;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int n = nbase + j;
+    if (n >= op.n_valid) break;
+    const float v = stage_f32_ptr(st, lane, j >> 2)[j & 3];
+    if (flags & EPI_OUT_NCT) { op.out[((long long)b * op.n_valid + n) * op.T_out + t] = v; continue; }
+    if (flags & EPI_OUT_F32) op.out[m * op.out_ld + n] = v;
+    if (flags & EPI_OUT_SPLIT) {
+      const long long o = m * op.out_split_ld + n;
+      if (f16) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half*>(op.out_hi)[o] = h;
+        reinterpret_cast<__half*>(op.out_lo)[o] = __float2half_rn(v - __half2float(h));
+      } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        op.out_hi[o] = h;
+        op.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+}
+__device__ __forceinline__ void park_row(uint8_t* st, int lane, const float* val) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage_f32_ptr(st, lane, j)) = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
+}
+__device__ __forceinline__ void fetch_row(uint8_t* st, int lane, float* val) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float4 v = *reinterpret_cast<const float4*>(stage_f32_ptr(st, lane, j)); val[4 * j] = v.x; val[4 * j + 1] = v.y; val[4 * j + 2] = v.z; val[4 * j + 3] = v.w; }
+}
+
 // Store one 32-column chunk of this warp's 32 rows.  val: this thread's row (already zero for rows past T_out).
 __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, uint8_t* st, int lane, bool leader, bool stage_f32, int b, int t,
                                            int t_warp0, long long m, bool mv, int nbase, const float* val, bool with_split = true,
@@ -176,7 +175,10 @@ __device__ __forceinline__ void emit_chunk(const GemmOp& op, const TMap* tmo, ui
   // whatever does not go through TMA (channel-major output, unaligned leading dimensions)
   const int direct = ((op.flags & EPI_OUT_NCT) ? EPI_OUT_NCT : 0) | (((op.flags & EPI_OUT_F32) && !(op.tma_out & 1)) ? EPI_OUT_F32 : 0) |
                      (((op.flags & EPI_OUT_SPLIT) && with_split && !(op.tma_out & 2)) ? EPI_OUT_SPLIT : 0);
-  if (direct && mv) store_chunk(op, direct, b, t, m, nbase, val);
+  if (direct) {                                             // (warp-uniform; cold)
+    if (!stage_f32) park_row(st, lane, val);
+    if (mv) store_cold(op, direct, b, t, m, nbase, st, lane);
+  }
 }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -669,9 +671,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                   upk2(fmul2(fadd2(pk2(val[j], val[j + 1]), pk2(pre[j], pre[j + 1])), gelu_erf2(fadd2(pk2(gate[j], gate[j + 1]), pk2(preg[j], preg[j + 1])))),
                        val[j], val[j + 1]);
               }
-            } else {
+            } else {                                        // cold: partial chunk - out of line, through the staging row
+              wait_staging();
+              park_row(st, lane, val);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, val[j], gate[j]) : 0.f;
+              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(st + 4096)[lane * 8 + j] = make_float4(gate[4 * j], gate[4 * j + 1], gate[4 * j + 2], gate[4 * j + 3]);
+              epi_cold<LNF>(op, b, m, nbase, st, lane, true);
+              fetch_row(st, lane, val);
             }
             wait_staging();
             emit_chunk(op, tmo, st, lane, leader, false, b, t, t_warp0, m, mv, nbase, val);
@@ -738,9 +744,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { const float4 v = __ldg(pr + j); acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w; }
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] = (nbase + j < op.n_valid) ? epi_value<LNF>(op, b, m, nbase + j, acc[j], 0.f) : 0.f;
+            } else {                                        // cold: partial chunk / row bias / unaligned residual - out of line
+              wait_staging();
+              park_row(st, lane, acc);
+              epi_cold<LNF>(op, b, m, nbase, st, lane, false);
+              fetch_row(st, lane, acc);
             }
             if (it == 0 && tr0) ETRACE(2);
             if ((op.flags & EPI_ROWSTATS) && mv) {          // LayerNorm statistics of this row for the consumer GEMM
