@@ -29,13 +29,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.  The message (a printf call site per wait:
+// code size and registers in every role loop) is compiled in with -DNS2VC_WAIT_MESSAGES only.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) {
+#ifdef NS2VC_WAIT_MESSAGES
       printf("ns2vc: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
@@ -102,7 +105,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > (1u << 24)) { printf("ns2vc: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (!ok && ++spins > (1u << 24)) {
+#ifdef NS2VC_WAIT_MESSAGES
+      printf("ns2vc: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+#endif
+      __trap();
+    }
   } while (!ok);
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
