@@ -297,9 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // Panel mode: one tile per CTA (grid == tile count).  warp 0: panels + weight tiles by TMA; warps 2-9: normalise
   // each panel in place, then (below) the ordinary epilogue; warp 1: three row-shifted views of the panel per tap.
   // ============================================================================================================
-  bool xpanel = false;
-  if constexpr (XF) xpanel = op_param.xmode != 0;
-  if constexpr (XF) if (xpanel) {
+  constexpr bool xpanel = XF;                               // the XF instantiation IS the panel mode (launch_gemm_tc): no plain main loop in it
+  if constexpr (XF) {
     const int tile = bid, mtile = tile / n_tiles;
     const int xb = mtile / tiles_per_batch, xt0 = (mtile % tiles_per_batch) * BM, xn0 = (tile % n_tiles) * BN;
     int ncblk = 0;
@@ -475,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // The weights do not depend on the previous kernel: the first tile's first stages are in flight before
   // griddepcontrol.wait; the activations (written by the previous kernel) only after it.
   const int npf = nkb < nst ? nkb : nst;
-  if (!xpanel && warp == 0 && elect_one()) {
+  if constexpr (!xpanel) if (warp == 0 && elect_one()) {
     const int n0 = (bid % n_tiles) * BN;
     for (int kb = 0; kb < npf; ++kb) {
       const uint32_t b_hi = base + kb * kStageBytes + 2 * kATileBytes;
@@ -489,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (!xpanel && elect_one()) {
+    if constexpr (!xpanel) if (elect_one()) {
       const int npre = npf;
       pdl_wait();
       if (tr0) TRACE(2);
@@ -521,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (!xpanel && elect_one()) {
+    if constexpr (!xpanel) if (elect_one()) {
       int g = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * kAccCols);
@@ -580,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // LNF instantiation: every per-column vector lives in shared memory (no register copies: the epilogue is register-bound)
         if (mv) ln_row_stats(op, m, ln_mu, ln_rstd);
         __syncwarp();
-        if (op.flags & EPI_GEGLU) {
+        if constexpr (BN == 128) {                          // (BN = 128 <=> GEGLU: plan_gemm, checked at launch)
           const int nb = nt * 64 + cc0 * 32 + lane;
           const bool ok = nb < op.n_valid;
           sg[lane] = ok ? __ldg(op.ln_g + nb) : 0.f;
@@ -598,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         __syncwarp();
       }
       if constexpr (!LNF) {
-      if (op.flags & EPI_GEGLU) {
+      if constexpr (BN == 128) {
         const int nb = nt * 64 + cc0 * 32;
         if (BN == 128 && nb + 32 <= op.n_valid) {
           pre_ok = true;
@@ -645,8 +644,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();
         }
       };
-      if (op.flags & EPI_GEGLU) {
-        if (BN == 128) {
+      if constexpr (BN == 128) {
+        {
           const int hh = cc0;                               // the two warps of a lane quarter take one half each
           float val[32], gate[32];
           tmem_ld32_sum(trow + (uint32_t)(hh * 32), trow + (uint32_t)(BN + hh * 32), val);
@@ -683,8 +682,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             emit_chunk(op, tmo, st, lane, leader, false, b, t, t_warp0, m, mv, nbase, val);
             staged_once = true;
           }
-        } else {
-          release_acc();
         }
       } else {
         float* sm_part = reinterpret_cast<float*>(stage_area) + (it & 1) * (4 * BN * 2);   // [4 quarters][BN][2] GroupNorm partial sums (per tile parity)
@@ -931,6 +928,7 @@ int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
     return launch_bn<64, false, true>(op, st);
   }
   if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
+  if ((op.bn == 128) != ((op.flags & EPI_GEGLU) != 0)) { set_error("gemm_tc: the 128-wide tile is the GEGLU instantiation (plan_gemm)"); return -1; }
   if (op.bn == 128) return lnf ? launch_bn<128, true, false>(op, st) : launch_bn<128, false, false>(op, st);
   if (op.bn != 64) { set_error("gemm_tc: plan_gemm() was not called"); return -1; }
   return lnf ? launch_bn<64, true, false>(op, st) : launch_bn<64, false, false>(op, st);
