@@ -158,6 +158,41 @@ int ns2vc_unet_profile_read(ns2vc_unet* h, int kind, double* ms_total, long long
 int ns2vc_unet_profile_dump(ns2vc_unet* h, const char* csv_path);   /* one row per launch */
 int ns2vc_unet_profile_reset(ns2vc_unet* h);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Condition encoders: `Pre_model.infer` (reference model.py:360-377) - the step immediately BEFORE the denoiser
+ * (SURVEY.md 8(f) rank 1): ref_enc (TextTimeEmbedding, unet1d/embeddings.py:421-434), PromptEncoder and PhoneEncoder
+ * (model.py:98-190: ConvLayer -> n x EncSALayer (operations.py:784-821: LayerNorm, 8-head self-attention with key padding,
+ * LayerNorm, k=9 conv-FFN) -> ConvLayer -> LayerNorm), all frames past an utterance's length exactly zero.
+ * Same conventions as the denoiser handle above: raw device pointers, caller-owned workspace, stream-ordered, int errors.
+ * The first call for a new (B, T, S, workspace) builds the launch program on the host (no device allocation). */
+typedef struct ns2vc_pre ns2vc_pre;
+typedef struct ns2vc_pre_cfg {       /* reference config.json "phoneme_encoder" / "prompt_encoder" (model.py:332-340)        */
+  int phone_in, phone_hidden, phone_out, phone_layers;       /* PhoneEncoder(in_channels, hidden_channels, out_channels, n_layers) */
+  int prompt_in, prompt_hidden, prompt_out, prompt_layers;   /* PromptEncoder(...)                                          */
+  int ref_dim;                       /* TextTimeEmbedding(100, 100, 1): width of the mel prompt (= prompt_in)                 */
+  int ref_heads;                     /* 1                                                                                     */
+  int n_heads;                       /* EncSALayer(c, 8, ...) (operations.py:961)                                             */
+  int ffn_kernel;                    /* 9 (operations.py:963)                                                                 */
+} ns2vc_pre_cfg;
+int ns2vc_pre_create(const ns2vc_pre_cfg* cfg, ns2vc_pre** out);
+void ns2vc_pre_destroy(ns2vc_pre* h);
+int ns2vc_pre_num_weights(const ns2vc_pre* h);                                  /* state_dict contract: reference key names / shapes */
+int ns2vc_pre_weight_info(const ns2vc_pre* h, int i, const char** name, int64_t shape[4], int* ndim);
+int ns2vc_pre_load_weight(ns2vc_pre* h, const char* key, const float* dptr, const int64_t* shape, int ndim, ns2vc_stream stream);
+int ns2vc_pre_finalize(ns2vc_pre* h, ns2vc_stream stream);                      /* strict: fails on a missing key                   */
+int ns2vc_pre_workspace_bytes(const ns2vc_pre* h, int B, int T, int S, size_t* bytes);
+/* Pre_model.infer:
+ *   c [B, phone_in, T] fp32, refer [B, prompt_in, S] fp32 (contiguous), lengths / refer_lengths [B] int64 (device, each >= 1)
+ *   -> content [B, T, phone_out], prompt [B, S, prompt_out] fp32 token-major (the reference returns the [T, B, C] / [S, B, C]
+ *      views of the same values: model.py:147, 189).                                                                        */
+int ns2vc_pre_infer(ns2vc_pre* h, const float* c, const float* refer, const int64_t* lengths, const int64_t* refer_lengths,
+                    float* content, float* prompt, int B, int T, int S, void* ws, ns2vc_stream stream);
+/* Diagnostics for the parity tests: per-layer activations (token-major [B, rows, channels]; rows = 1 for the speaker vector). */
+int ns2vc_pre_num_taps(const ns2vc_pre* h);
+int ns2vc_pre_tap_info(const ns2vc_pre* h, int i, const char** name, int* rows, int* channels);
+int ns2vc_pre_set_tap(ns2vc_pre* h, int i, float* dst);
+int ns2vc_pre_launch_count(const ns2vc_pre* h);   /* kernels launched by the last infer */
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,12 @@ class UNetCfg(C.Structure):
     ]
 
 
+class PreCfg(C.Structure):
+    _fields_ = [("phone_in", C.c_int), ("phone_hidden", C.c_int), ("phone_out", C.c_int), ("phone_layers", C.c_int),
+                ("prompt_in", C.c_int), ("prompt_hidden", C.c_int), ("prompt_out", C.c_int), ("prompt_layers", C.c_int),
+                ("ref_dim", C.c_int), ("ref_heads", C.c_int), ("n_heads", C.c_int), ("ffn_kernel", C.c_int)]
+
+
 class DpmCoef(C.Structure):
     _fields_ = [("alpha_s", C.c_float), ("sigma_s", C.c_float), ("c_x", C.c_float), ("c_m", C.c_float),
                 ("c_d", C.c_float), ("inv_r0", C.c_float), ("order", C.c_int)]
@@ -74,6 +80,19 @@ SIGNATURES = {
     "ns2vc_unet_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ns2vc_unet_profile_dump": (C.c_int, [_P, C.c_char_p]),
     "ns2vc_unet_profile_reset": (C.c_int, [_P]),
+    # condition encoders (Pre_model)
+    "ns2vc_pre_create": (C.c_int, [C.POINTER(PreCfg), C.POINTER(_P)]),
+    "ns2vc_pre_destroy": (None, [_P]),
+    "ns2vc_pre_num_weights": (C.c_int, [_P]),
+    "ns2vc_pre_weight_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "ns2vc_pre_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
+    "ns2vc_pre_finalize": (C.c_int, [_P, _P]),
+    "ns2vc_pre_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "ns2vc_pre_infer": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "ns2vc_pre_num_taps": (C.c_int, [_P]),
+    "ns2vc_pre_tap_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ns2vc_pre_set_tap": (C.c_int, [_P, C.c_int, _P]),
+    "ns2vc_pre_launch_count": (C.c_int, [_P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -112,6 +112,9 @@ enum EpiFlags : int {
   EPI_LNFOLD = 256,   // the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights:
                       //   acc <- rstd_row * (acc - mean_row * ln_g[n]);  bias then carries beta.W + bias   (see engine.cu)
   EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
+  // condition encoders (pre_engine.cu; the ENC instantiation of the tcgen05 kernel):
+  EPI_RELU = 1024,    // max(v, 0) after bias / residual              (conv-FFN, reference operations.py:686)
+  EPI_ROWMASK = 2048, // v *= rowmask[m] after everything else         (x * (1 - padding_mask), reference operations.py:812, 820)
 };
 
 // One panel segment of a panel-mode GEMM: `ncb` 64-channel blocks of one raw split source
@@ -176,6 +179,7 @@ struct GemmOp {
   XSeg xs[kMaxXSeg];
   const PrepOp* pre;           // GroupNorm parameters of the normalised segments (device memory; only the affine part is used)
   const float* pre_film;       // FiLM rows read by that affine (nullptr: none) - kept here because they change per forward
+  const float* rowmask;        // EPI_ROWMASK: [B*T_out] keep factor (1 = frame inside the utterance, 0 = padding)
   // ---- tensor maps last: the TMA unit reads them by address (kernel-parameter space); the kernel copies only the fields
   // ---- before them into shared memory (kGemmOpHotBytes)
   TMap tmap[2 * kMaxSrc];      // [2*i] = hi, [2*i+1] = lo of src[i]; box = {64 ch, 128 rows, 1} (130 rows for a panel-mode k=3 source)
@@ -320,6 +324,20 @@ struct UniPcStepCoef {  // UniPC-bh2, data prediction: corrector at t (+ predict
 int launch_unipc_step(const float* x_prev, const float* x_eval, const float* unet_out, const float* m0,
                       const float* m1, const UniPcStepCoef& c, float* m_t, float* x_t, float* x_pred, size_t n,
                       int* nan_flag, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// Condition encoders (pre_kernels.cu; program in pre_engine.cu)
+// ---------------------------------------------------------------------------------------------
+int launch_seq_mask(const long long* len, int B, int T, float* keep, float* kbias, cudaStream_t st);
+int launch_enc_input(const float* x, long long bstride, const float* rowbias, const float* keep, int B, int C, int T, float* out, int ld,
+                     cudaStream_t st);
+int launch_ln_mask(const float* x, int ld, int M, int C, float eps, const float* gamma, const float* beta, const float* keep, float* y, int y_ld,
+                   cudaStream_t st);
+int launch_pool_attend_wide(const float* q, const float* kv, int B, int S1, int C, int heads, float* out, cudaStream_t st);
+int launch_tbc_weight(const float* w, int k, int cin, int cout, float* o, cudaStream_t st);
+int launch_ffn_taps(const float* const* w, int k, int F, int H, int centre, float scale, float* o, cudaStream_t st);
+int launch_scale_vec(const float* a, float s, float* o, int n, cudaStream_t st);
+int launch_ln_fold_vec(const float* W, const float* gamma, const float* beta, const float* bias, float* g, float* bf, int N, int C, cudaStream_t st);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

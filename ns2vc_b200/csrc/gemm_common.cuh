@@ -151,6 +151,8 @@ __device__ __forceinline__ float epi_value(const GemmOp& op, int b, long long m,
   }
   if (op.flags & EPI_ROWBIAS) v += __ldg(op.rowbias + (long long)b * op.rowbias_ld + n);
   if (op.flags & EPI_RESIDUAL) v += __ldg(op.res + m * op.res_ld + n);
+  if (op.flags & EPI_RELU) v = fmaxf(v, 0.f);
+  if (op.flags & EPI_ROWMASK) v *= __ldg(op.rowmask + m);
   return v;
 }
 

@@ -196,7 +196,9 @@ static_assert(kGemmOpHotBytes % 16 == 0 && kGemmOpHotBytes <= 2688 && sizeof(Pre
 // LNF: instantiation for the consumers of a folded LayerNorm (EPI_LNFOLD); the other GEMMs run the LNF = false code, which
 // keeps the epilogue free of the extra live values (the epilogue is register-bound: 168 per thread at 320 threads).
 // XF: instantiation with the panel-mode paths (GroupNorm of the A operand applied in shared memory; BN = 64, one tile per CTA)
-template <int BN_, bool LNF, bool XF>
+// ENC: instantiation for the condition encoders (pre_engine.cu): ReLU and the per-row keep mask in the epilogue (EPI_RELU /
+// EPI_ROWMASK); the denoiser's instantiations do not carry that code
+template <int BN_, bool LNF, bool XF, bool ENC = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmOp op_param) {
   using Cfg = TileCfg<BN_>;
   constexpr int BN = Cfg::BN;
@@ -629,6 +631,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
       }   // !LNF
+      float enc_keep = 1.f;
+      if constexpr (ENC) if ((op.flags & EPI_ROWMASK) && mv) enc_keep = __ldg(op.rowmask + m);
       mbar_wait(acc_full(it & 1), (uint32_t)((it >> 1) & 1));
       if (it == 0 && tr0 && warp == 2 && lane == 0) TRACE(5);
       if (it == 0 && tr0) ETRACE(0);
@@ -719,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const bool cvalid = nbase < op.n_valid;           // (uniform across the warp)
           if (cvalid) {
             const bool fullc = nbase + 32 <= op.n_valid;
+            bool enc_hot = ENC && mv;                       // (the out-of-line path applies ReLU / mask itself: epi_value)
             if (!mv) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] = 0.f;
@@ -746,6 +751,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               park_row(st, lane, acc);
               epi_cold<LNF>(op, b, m, nbase, st, lane, false);
               fetch_row(st, lane, acc);
+              enc_hot = false;
+            }
+            if constexpr (ENC) if (enc_hot) {
+              if (op.flags & EPI_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+              }
+              if (op.flags & EPI_ROWMASK) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] *= enc_keep;
+              }
             }
             if (it == 0 && tr0) ETRACE(2);
             if ((op.flags & EPI_ROWSTATS) && mv) {          // LayerNorm statistics of this row for the consumer GEMM
@@ -891,12 +907,12 @@ static int sm_count() {
   return n;
 }
 
-template <int BN_, bool LNF, bool XF>
+template <int BN_, bool LNF, bool XF, bool ENC = false>
 static int launch_bn(const GemmOp& op, cudaStream_t st) {
   using Cfg = TileCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN_, LNF, XF, ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cannot set %d B dynamic smem: %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
@@ -905,7 +921,7 @@ static int launch_bn(const GemmOp& op, cudaStream_t st) {
   int grid = (XF && op.xmode) ? tiles : (tiles < sm_count() ? tiles : sm_count());
   dim3 cluster(1, 1, 1);
   if (XF && op.xmode && op.ksplit > 1) { grid = tiles * op.ksplit; cluster.x = (unsigned)op.ksplit; }   // split-K: the CTAs of a cluster share a tile
-  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, LNF, XF>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, cluster, op);
+  cudaError_t e = launch_kc(gemm_tc_kernel<BN_, LNF, XF, ENC>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, cluster, op);
   if (e != cudaSuccess) { set_error("gemm_tc launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -921,6 +937,12 @@ void plan_gemm(GemmOp& op) {
 int launch_gemm_tc(const GemmOp& op, cudaStream_t st) {
   if (op.N % 128) { set_error("gemm_tc: packed N=%d is not a multiple of 128", op.N); return -1; }
   const bool lnf = (op.flags & EPI_LNFOLD) != 0;
+  if (op.flags & (EPI_RELU | EPI_ROWMASK)) {
+    if (lnf || op.xmode || op.bn != 64 || (op.flags & EPI_GEGLU)) { set_error("gemm_tc: ReLU / row-mask epilogues need a plain 64-wide tile"); return -1; }
+    if ((op.flags & EPI_ROWMASK) && !op.rowmask) { set_error("gemm_tc: EPI_ROWMASK without a mask"); return -1; }
+    if (op.nkb_total <= 0) { set_error("gemm_tc: empty K"); return -1; }
+    return launch_bn<64, false, false, true>(op, st);
+  }
   if (op.xmode) {
     if (lnf || op.bn != 64 || op.nxs < 1 || op.nxs > kMaxXSeg) { set_error("gemm_tc: panel mode needs a plain 64-wide tile and 1..%d segments", kMaxXSeg); return -1; }
     if (op.pre == nullptr) { set_error("gemm_tc: panel mode without GroupNorm parameters"); return -1; }
