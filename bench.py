@@ -217,6 +217,71 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+PRE_CFG = {"phoneme_encoder": dict(in_channels=256, hidden_channels=256, out_channels=256, n_layers=6, p_dropout=0.2),
+           "prompt_encoder": dict(in_channels=100, hidden_channels=256, out_channels=256, n_layers=6, p_dropout=0.2)}     # reference config.json:27-49
+
+
+def pre_flops(Bn, Tn, Sn, H=256, L=6, k=9):
+    """Algorithmic FLOPs of Pre_model.infer: per frame and layer QKV + out-proj + k-tap conv-FFN (C -> 4C) + FFN out, the
+    attention products, and the two k=1 ConvLayers of each encoder."""
+    per_layer = 2 * H * 3 * H + 2 * H * H + 2 * H * 4 * H * k + 2 * 4 * H * H
+    enc = lambda n, cin: Bn * n * (L * per_layer + 2 * cin * H + 2 * H * H) + Bn * L * 4 * n * n * H
+    return enc(Tn, 256) + enc(Sn, 100)
+
+
+def bench_pre_model(unet, dev, hin, nfe, with_cpu):
+    from ns2vc_b200 import api
+    from ns2vc_b200.pre_model import Pre_model
+    from ns2vc_b200.synth import make_pre_inputs, make_pre_state_dict
+    pre = Pre_model(PRE_CFG)
+    sd = make_pre_state_dict(PRE_CFG, 0)
+    pre.load_state_dict(sd)
+    pre = pre.to(dev).eval()
+    pin = make_pre_inputs(B, T, S, seed=5)
+    pin_h = {k: v.pin_memory() for k, v in pin.items()}
+    data = (pin["c"].to(dev), pin["refer"].to(dev), None, None, None, pin["lengths"].to(dev), pin["refer_lengths"].to(dev), None)
+    for _ in range(3):
+        pre.infer(data)
+    torch.cuda.synchronize(dev)
+    K = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pre.infer(data)
+    e1.record(); torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / K
+    fl = pre_flops(B, T, S)
+    peaks = read_peaks()
+    res = {"workload": f"Pre_model.infer (ref_enc + PromptEncoder + PhoneEncoder, 34.9M params) at B={B}, T={T}, S={S}, device-resident inputs",
+           "ms_per_call": ms, "utterances_per_s": B / (ms / 1e3), "launches_per_call": pre.launch_count(), "algorithmic_gflop": fl / 1e9,
+           "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_tensor_peak": fl / (ms * 1e-3) / 1e12 / peaks["tflops"]}
+    # whole device pipeline through the public API: host (pinned) features in, host latents out, copies inside the timed region
+    def run():
+        return api.sample_from_features(pre, unet, hin["x"], pin_h["c"], pin_h["refer"], pin_h["lengths"], pin_h["refer_lengths"], steps=nfe, device=dev).cpu()
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        run()
+    e1.record(); torch.cuda.synchronize(dev)
+    mp = e0.elapsed_time(e1) / 2
+    res["pipeline_e2e"] = {"what": f"api.sample_from_features: Pre_model.infer + {nfe}-NFE DPM-Solver++(2M) sampling, pinned host features in, host latents out",
+                           "ms_per_run": mp, "value": B * nfe / (mp / 1e3), "unit": UNIT, "pre_model_share": ms / mp}
+    if with_cpu:
+        from oracle import pre_model_oracle as po                # CPU baseline leg: the oracle port of the reference's CPU path
+        torch.set_num_threads(min(host_threads(), 32))
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            po.pre_model_infer(sd, pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], 6, 6)
+            dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"ms_per_call": 1e3 * dt, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "one Pre_model.infer at the same shape through the oracle port of the reference's CPU PyTorch path"}
+    del pre
+    return res
+
+
 def ncu_traffic(kernel):
     """Average DRAM bytes per launch of `kernel` from the committed ncu launch list (profiles/)."""
     p = os.path.join(REPO, "profiles", "r02_traffic.json")
@@ -433,6 +498,12 @@ def main():
             del c3s
         except Exception as e:                                   # the extra key must never cost the headline line
             out["cfg3"] = {"error": repr(e)}
+        # ---- the condition encoders (Pre_model.infer, the step BEFORE the denoiser: SURVEY.md 8(f) rank 1) at the cfg2 shape,
+        # and the whole device pipeline (encoders + 50-NFE sampling) through the public API with host buffers
+        try:
+            out["pre_model"] = bench_pre_model(unet, dev, hin, nfe, world == 1)
+        except Exception as e:
+            out["pre_model"] = {"error": repr(e)}
         if world == 1:
             threads = best_thread_count()
             nf = 3

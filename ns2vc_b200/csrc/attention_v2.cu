@@ -429,9 +429,9 @@ template <int DHP, int PB>
 int launch_v2(const AttnOp& op, cudaStream_t st) {
   if (op.bias) {
     if (ceil_div(op.Tk, kKeys) * kKeys > ACfg<DHP, PB, true, true>::kBiasKeys) { set_error("attention v2: %d biased keys exceed the staged-bias capacity", op.Tk); return -1; }
-    return p_fp16() ? launch_v2b<DHP, PB, true, true>(op, st) : launch_v2b<DHP, PB, true, false>(op, st);
+    return (p_fp16() && !op.p_split) ? launch_v2b<DHP, PB, true, true>(op, st) : launch_v2b<DHP, PB, true, false>(op, st);
   }
-  return p_fp16() ? launch_v2b<DHP, PB, false, true>(op, st) : launch_v2b<DHP, PB, false, false>(op, st);
+  return (p_fp16() && !op.p_split) ? launch_v2b<DHP, PB, false, true>(op, st) : launch_v2b<DHP, PB, false, false>(op, st);
 }
 
 int natural_pb(int dh) { return dh == 16 ? 32 : dh == 32 ? 64 : 128; }

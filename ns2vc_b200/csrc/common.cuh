@@ -242,6 +242,8 @@ struct AttnOp {
   int q_c0, k_c0, v_c0;
   int v2;                         // 1: launch the v2 kernel (needs dh % 16 == 0 and encode_attn_tmaps())
   int pb;                         // byte width of the Q/K/V TMA boxes = shared-memory row pitch (32 / 64 / 128)
+  int p_split;                    // 1: softmax weights as a bf16 hi/lo split whatever NS2VC_ATTN_P says (V must then be a bf16 split too).  The
+                                  // condition encoders attend over a few dozen keys: the 2^-12 rounding of fp16 weights does not average out there
   TMap tm[6];                     // q hi, q lo (box pb x 128 rows), k hi, k lo, v hi, v lo (box pb x 64 rows)
 };
 int launch_attention(const AttnOp& op, cudaStream_t st, bool simt_debug);

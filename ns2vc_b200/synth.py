@@ -55,6 +55,41 @@ def make_state_dict(cfg: UNetConfig, seed: int = 0, perturb_norms: bool = True) 
     return sd
 
 
+def make_pre_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic `Pre_model` weights keyed by parameter name: norms 1 + 0.1 N(0,1) / 0.1 N(0,1), everything else
+    U(-b, b) with b = fan_in^-1/2 (ConvTBC weights [k, c_in, c_out]: fan_in = k c_in)."""
+    from .pre_model import pre_param_shapes
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape in pre_param_shapes(cfg).items():
+        g = torch.Generator().manual_seed(_seed_for(name, seed))
+        owner, leaf = name.rsplit(".", 1)
+        if len(shape) == 1 and "norm" in owner.rsplit(".", 1)[-1]:
+            t = (1.0 if leaf == "weight" else 0.0) + 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in (shape[1:] if len(shape) > 1 else shape):
+                fan_in *= d
+            if name.endswith("conv.weight") and len(shape) == 3 and "spk_proj" not in name:
+                fan_in = shape[0] * shape[1]
+            t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(max(fan_in, 1))
+        sd[name] = t.to(torch.float32).contiguous()
+    return sd
+
+
+def make_pre_inputs(B: int, T: int, S: int, content_ch: int = 256, ragged: bool = False, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic `Pre_model.infer` inputs: c ~ N(0,1) [B, 256, T] (ContentVec features), refer ~ N(0,1) [B, 100, S] (mel prompt)."""
+    g = torch.Generator().manual_seed(seed + 11)
+    c = torch.randn((B, content_ch, T), generator=g)
+    refer = torch.randn((B, 100, S), generator=g)
+    if ragged:
+        lengths = torch.tensor([max(1, T - 37 * (i % 8)) for i in range(B)], dtype=torch.int64)
+        refer_lengths = torch.tensor([max(1, S - 17 * (i % 8)) for i in range(B)], dtype=torch.int64)
+    else:
+        lengths = torch.full((B,), T, dtype=torch.int64)
+        refer_lengths = torch.full((B,), S, dtype=torch.int64)
+    return dict(c=c, refer=refer, lengths=lengths, refer_lengths=refer_lengths)
+
+
 def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> str:
     h = hashlib.sha256()
     for k in sorted(sd):
