@@ -4,6 +4,7 @@ Drop-in surface (same names as the reference):
     ns2vc_b200.unet.UNet1DConditionModel          <- unet1d/unet_1d_condition.py
     ns2vc_b200.dpm_solver.{NoiseScheduleVP, model_wrapper, DPM_Solver}   <- sampler/dpm_solver.py
     ns2vc_b200.uni_pc.{NoiseScheduleVP, model_wrapper, UniPC}            <- sampler/uni_pc.py
+    ns2vc_b200.pre_model.Pre_model                <- model.py:328-377 (condition encoders; ``install_pre_model(model)``)
 ``ns2vc_b200.install()`` aliases those module paths so the reference's model.py / infer.py import
 them unchanged.
 """
@@ -45,3 +46,14 @@ def install() -> None:
         p = parent(pkg)
         sys.modules[f"{pkg}.{sub}"] = mod
         setattr(p, sub, mod)
+
+
+def install_pre_model(model_module=None) -> None:
+    """Make the reference's ``model.Pre_model`` (defined inside ``model.py`` itself, :328) the B200 implementation: call after
+    ``import model`` and before ``NaturalSpeech2(cfg)`` is constructed (``model.py:445`` looks the class up by its global name)."""
+    from .pre_model import Pre_model
+    if model_module is None:
+        model_module = sys.modules.get("model")
+    if model_module is None or not hasattr(model_module, "Pre_model"):
+        raise RuntimeError("install_pre_model: import the reference's model.py first (or pass the module)")
+    model_module.Pre_model = Pre_model

@@ -26,7 +26,14 @@ def test_reference_model_py_builds_on_our_unet():
         import model as ref_model
         from ns2vc_b200.unet import UNet1DConditionModel
         cfg = json.load(open(os.path.join(REF, "config.json")))
+        ref_pre_keys = {k: tuple(v.shape) for k, v in ref_model.Pre_model(cfg).state_dict().items()}   # the reference's own class
+        ns2vc_b200.install_pre_model(ref_model)
         ns2 = ref_model.NaturalSpeech2(cfg)
+        from ns2vc_b200.pre_model import Pre_model
+        assert isinstance(ns2.pre_model, Pre_model)
+        ours = {k: tuple(v.shape) for k, v in ns2.pre_model.state_dict().items()}
+        assert list(ours.items()) == list(ref_pre_keys.items())          # same keys, order and shapes as the reference's Pre_model
+        assert sum(p.numel() for p in ns2.pre_model.parameters()) == 34923404
         unet = ns2.diff_model.unet
         assert isinstance(unet, UNet1DConditionModel)
         assert sum(p.numel() for p in unet.parameters()) == 66076900

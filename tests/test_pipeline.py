@@ -1,0 +1,59 @@
+"""The whole device pipeline - ``NaturalSpeech2.sample`` of the reference up to the vocoder (model.py:605-686): condition encoders
+-> denoiser x DPM-Solver++ (40 steps) / UniPC bh2 (30 steps) - against tests/golden/pipeline.pt, written by the UNMODIFIED
+reference on the shipped configuration (oracle/make_golden_pipeline.py).  CPU: the oracle chain reproduces it; GPU: the product
+(api.sample_from_features: Pre_model.infer + the fused sampling loop, through the C-ABI) within rtol 1e-3 / atol 1e-4."""
+import pytest
+import torch
+
+from ns2vc_b200.arch import ns2vc_denoiser_config
+from ns2vc_b200.synth import linear_betas, make_pre_inputs, make_pre_state_dict, make_state_dict, state_dict_checksum
+
+PRE_CFG = {"phoneme_encoder": dict(in_channels=256, hidden_channels=256, out_channels=256, n_layers=6, p_dropout=0.2),
+           "prompt_encoder": dict(in_channels=100, hidden_channels=256, out_channels=256, n_layers=6, p_dropout=0.2)}
+
+
+def _weights(g):
+    sd_u, sd_p = make_state_dict(ns2vc_denoiser_config(), seed=0), make_pre_state_dict(PRE_CFG, seed=0)
+    assert state_dict_checksum(sd_u) == g["unet_checksum"] and state_dict_checksum(sd_p) == g["pre_checksum"]
+    return sd_u, sd_p
+
+
+def test_oracle_chain_reproduces_the_reference_pipeline(gold):
+    from oracle import pre_model_oracle as po, sampler_oracle, unet_oracle
+    g = gold("pipeline.pt")
+    sd_u, sd_p = _weights(g)
+    k = g["cases"]["unipc"]                                    # (B = 1, 30 NFE: seconds on the CPU; the DPM case runs on the GPU box below)
+    pin = make_pre_inputs(k["B"], k["T"], k["S"], ragged=True, seed=k["seed"])
+    with torch.no_grad():
+        content, prompt = po.pre_model_infer(sd_p, pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], 6, 6)
+        fn = lambda x, t: unet_oracle.denoiser_forward(sd_u, ns2vc_denoiser_config(), x, content, prompt, pin["refer_lengths"], t)
+        got = sampler_oracle.unipc_bh(fn, sampler_oracle.OracleSchedule(linear_betas(1000)), k["xT"], k["steps"], variant="bh2")
+    assert (got - k["mel"]).abs().max().item() <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["dpmsolver", "unipc"])
+def test_device_pipeline_matches_the_reference(gold, method):
+    from ns2vc_b200 import api
+    from ns2vc_b200.pre_model import Pre_model
+    from ns2vc_b200.unet import UNet1DConditionModel
+    g = gold("pipeline.pt")
+    sd_u, sd_p = _weights(g)
+    k = g["cases"][method]
+    unet = UNet1DConditionModel(in_channels=356, out_channels=100, block_out_channels=(128, 256, 384, 512), norm_num_groups=8,
+                                cross_attention_dim=256, attention_head_dim=8, addition_embed_type="text", resnet_time_scale_shift="scale_shift")
+    unet.load_state_dict(sd_u)
+    pre = Pre_model(PRE_CFG)
+    pre.load_state_dict(sd_p)
+    unet, pre = unet.cuda().eval(), pre.cuda().eval()
+    pin = make_pre_inputs(k["B"], k["T"], k["S"], ragged=True, seed=k["seed"])
+    mel = api.sample_from_features(pre, unet, k["xT"], pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], steps=k["steps"],
+                                   method=method, device="cuda").cpu()
+    ref = k["mel"]
+    err = (mel - ref).abs()
+    worst = (err / (1e-4 + 1e-3 * ref.abs())).max().item()
+    assert worst <= 1.0, f"{method}: max_abs={err.max().item():.3e} worst err/tol={worst:.2f}"
+    # a second run replays / re-uses the session and gives the same latents
+    mel2 = api.sample_from_features(pre, unet, k["xT"], pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], steps=k["steps"],
+                                    method=method, device="cuda").cpu()
+    assert torch.equal(mel, mel2)
