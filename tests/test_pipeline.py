@@ -57,3 +57,59 @@ def test_device_pipeline_matches_the_reference(gold, method):
     mel2 = api.sample_from_features(pre, unet, k["xT"], pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], steps=k["steps"],
                                     method=method, device="cuda").cpu()
     assert torch.equal(mel, mel2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["dpmsolver", "unipc"])
+def test_dropin_classes_in_the_reference_call_sequence(gold, method):
+    """The call sequence of ``NaturalSpeech2.sample`` (model.py:620-686) written out with the drop-in classes a patched reference
+    resolves to: ``Pre_model.infer`` -> a ``Diffusion_Encoder.forward``-shaped closure (:403-415: NaN assert,
+    rearranges, cat, mask, ``unet(...).sample``) wrapped by ``model_wrapper`` -> a FRESH ``NoiseScheduleVP`` -> ``DPM_Solver`` /
+    ``UniPC`` ``.sample(...)`` with the reference's arguments.  Same fixture as above."""
+    from ns2vc_b200 import dpm_solver as our_dpm, uni_pc as our_upc
+    from ns2vc_b200.pre_model import Pre_model
+    from ns2vc_b200.unet import UNet1DConditionModel
+    g = gold("pipeline.pt")
+    sd_u, sd_p = _weights(g)
+    k = g["cases"][method]
+    unet = UNet1DConditionModel(in_channels=356, out_channels=100, block_out_channels=(128, 256, 384, 512), norm_num_groups=8,
+                                cross_attention_dim=256, attention_head_dim=8, addition_embed_type="text", resnet_time_scale_shift="scale_shift")
+    unet.load_state_dict(sd_u)
+    pre = Pre_model(PRE_CFG)
+    pre.load_state_dict(sd_p)
+    unet, pre = unet.cuda().eval(), pre.cuda().eval()
+    pin = {n: v.cuda() for n, v in make_pre_inputs(k["B"], k["T"], k["S"], ragged=True, seed=k["seed"]).items()}
+    betas = linear_betas(1000).cuda()
+    calls = []
+
+    def diffusion_encoder_forward(x, data, t):                 # model.py:403-415
+        assert torch.isnan(x).any() == False                   # noqa: E712
+        contentvec, prompt, _contentvec_lengths, prompt_lengths = data
+        prompt = prompt.permute(1, 0, 2)
+        contentvec = contentvec.permute(1, 2, 0)
+        x = torch.cat([x, contentvec], dim=1)
+        prompt_mask = (torch.arange(prompt.size(1), device=x.device).unsqueeze(0) < prompt_lengths.unsqueeze(1)).to(torch.bool)
+        return unet(x, t, prompt, encoder_attention_mask=prompt_mask).sample
+
+    def sample_fun(x, t, data=None):                           # model.py:520-526
+        calls.append(1)
+        return diffusion_encoder_forward(x, data, t)
+
+    with torch.no_grad():
+        data = (pin["c"], pin["refer"], None, 0, 0, pin["lengths"], pin["refer_lengths"], None)
+        content, refer = pre.infer(data, auto_predict_f0=True)
+        audio = k["xT"].cuda()
+        mod = our_dpm if method == "dpmsolver" else our_upc
+        noise_schedule = mod.NoiseScheduleVP(schedule="discrete", betas=betas)
+        model_fn = mod.model_wrapper(sample_fun, noise_schedule, model_type="x_start",
+                                     model_kwargs={"data": (content, refer, pin["lengths"], pin["refer_lengths"])})
+        if method == "dpmsolver":
+            solver = our_dpm.DPM_Solver(model_fn, noise_schedule, algorithm_type="dpmsolver++")
+        else:
+            solver = our_upc.UniPC(model_fn, noise_schedule, variant="bh2")
+        mel = solver.sample(audio, steps=k["steps"], order=2, skip_type="time_uniform", method="multistep").cpu()
+    ref = k["mel"]
+    err = (mel - ref).abs()
+    worst = (err / (1e-4 + 1e-3 * ref.abs())).max().item()
+    assert worst <= 1.0, f"{method}: max_abs={err.max().item():.3e} worst err/tol={worst:.2f}"
+    assert len(calls) == 1                                     # the fused path recognised the closure (one probe call, INTEGRATION.md)
