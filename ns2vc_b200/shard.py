@@ -31,3 +31,16 @@ def gather_latents(local: torch.Tensor, group: Optional[dist.ProcessGroup] = Non
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)
     return out
+
+
+def shard_features(world_size: int, rank: int, *tensors: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    """This rank's utterances of the batch-first inputs of the device pipeline (`api.sample_from_features`: x_T [B, 100, T],
+    c_padded [B, 256, T], refer_padded [B, 100, S], lengths [B], refer_lengths [B]): the condition encoders have no cross-sample op
+    either (per-utterance masks, LayerNorm, attention), so the same contiguous cut applies and no collective is added."""
+    if not tensors:
+        return ()
+    n = tensors[0].shape[0]
+    if any(t.shape[0] != n for t in tensors):
+        raise ValueError("all inputs must share the utterance (first) dimension")
+    lo, hi = shard_bounds(n, world_size, rank)
+    return tuple(t[lo:hi] for t in tensors)

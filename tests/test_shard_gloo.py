@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ns2vc_b200.shard import gather_latents, shard_bounds
+from ns2vc_b200.shard import gather_latents, shard_bounds, shard_features
 
 
 def _fake_sampler(x):                      # independent per utterance, like the denoiser (no cross-sample op)
@@ -22,7 +22,12 @@ def _worker(rank, world, port, q):
         full = torch.randn((6, 5, 17), generator=torch.Generator().manual_seed(3))
         lo, hi = shard_bounds(full.shape[0], world, rank)
         out = gather_latents(_fake_sampler(full[lo:hi]))
-        q.put((rank, torch.equal(out, _fake_sampler(full)), tuple(out.shape)))
+        # the feature inputs of the pipeline (ragged lengths) take the same cut: a per-utterance stand-in for encoders + sampler
+        lengths = torch.tensor([17, 9, 13, 17, 5, 11])
+        x_l, len_l = shard_features(world, rank, full, lengths)
+        masked = lambda x, n: _fake_sampler(x * (torch.arange(x.shape[2])[None, None, :] < n[:, None, None]))
+        out2 = gather_latents(masked(x_l, len_l))
+        q.put((rank, torch.equal(out, _fake_sampler(full)) and torch.equal(out2, masked(full, lengths)), tuple(out.shape)))
     finally:
         dist.destroy_process_group()
 
@@ -51,3 +56,7 @@ def test_shard_bounds_reject_uneven_batches():
         shard_bounds(8, 2, 2)
     x = torch.zeros(2, 3, 4)
     assert gather_latents(x) is x          # no process group: single rank
+    a, b = shard_features(2, 1, torch.arange(8).view(4, 2), torch.arange(4))
+    assert a.tolist() == [[4, 5], [6, 7]] and b.tolist() == [2, 3]
+    with pytest.raises(ValueError):
+        shard_features(2, 0, torch.zeros(4, 1), torch.zeros(3))
