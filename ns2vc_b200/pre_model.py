@@ -184,6 +184,10 @@ class Pre_model(nn.Module):
         if c_padded.dim() != 3 or c_padded.shape[1] != pi:
             raise ValueError(f"c_padded must be [B, {pi}, T], got {tuple(c_padded.shape)}")
         B, _, T = c_padded.shape
+        if refer_padded.dim() == 3 and refer_padded.shape[0] == 1 and B > 1:
+            # one prompt for the whole batch: the reference's encoders broadcast it (`sample()` even cuts a 2-row prompt down to its
+            # first row, model.py:610-611); row-wise that is the same prompt repeated
+            refer_padded = refer_padded.expand(B, -1, -1)
         if refer_padded.dim() != 3 or refer_padded.shape[0] != B or refer_padded.shape[1] != ri:
             raise ValueError(f"refer_padded must be [B, {ri}, S], got {tuple(refer_padded.shape)}")
         S = refer_padded.shape[2]

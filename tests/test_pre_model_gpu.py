@@ -128,3 +128,17 @@ def test_padded_frames_of_the_input_do_not_leak():
     c2[1, :, int(lengths[1]):] = float("nan")
     got_c, got_p = m.infer(data_of(c2, refer, lengths, refer_lengths))
     assert torch.equal(got_c, base_c) and torch.equal(got_p, base_p)
+
+
+def test_one_prompt_broadcast_over_the_batch():
+    """refer_padded with ONE row and B > 1 utterances (what `NaturalSpeech2.sample` produces from a 2-row prompt, model.py:610-611):
+    the reference's modules broadcast it; the oracle does the same."""
+    m, sd = make(FULL, seed=3)
+    c, refer, lengths, refer_lengths = inputs(3, 70, 33, 256, seed=9, dl=21, ds=5)
+    refer1 = refer[:1]
+    with torch.no_grad():
+        ref_c, ref_p = po.pre_model_infer(sd, c, refer1, lengths, refer_lengths, 6, 6)
+    content, prompt = m.infer(data_of(c, refer1, lengths, refer_lengths))
+    assert content.shape == ref_c.shape and prompt.shape == ref_p.shape
+    ok, msg = close(content, ref_c); assert ok, "content " + msg
+    ok, msg = close(prompt, ref_p); assert ok, "prompt " + msg
