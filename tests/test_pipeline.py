@@ -52,6 +52,7 @@ def test_device_pipeline_matches_the_reference(gold, method):
     ref = k["mel"]
     err = (mel - ref).abs()
     worst = (err / (1e-4 + 1e-3 * ref.abs())).max().item()
+    print(f"[pipeline api {method}] max_abs={err.max().item():.3e} worst err/tol={worst:.2f}")
     assert worst <= 1.0, f"{method}: max_abs={err.max().item():.3e} worst err/tol={worst:.2f}"
     # a second run replays / re-uses the session and gives the same latents
     mel2 = api.sample_from_features(pre, unet, k["xT"], pin["c"], pin["refer"], pin["lengths"], pin["refer_lengths"], steps=k["steps"],
@@ -111,5 +112,6 @@ def test_dropin_classes_in_the_reference_call_sequence(gold, method):
     ref = k["mel"]
     err = (mel - ref).abs()
     worst = (err / (1e-4 + 1e-3 * ref.abs())).max().item()
+    print(f"[pipeline drop-in {method}] max_abs={err.max().item():.3e} worst err/tol={worst:.2f}")
     assert worst <= 1.0, f"{method}: max_abs={err.max().item():.3e} worst err/tol={worst:.2f}"
     assert len(calls) == 1                                     # the fused path recognised the closure (one probe call)
