@@ -72,3 +72,23 @@ def test_no_cpu_path():
     data = (torch.zeros(1, 64, 9), torch.zeros(1, 100, 5), None, None, None, torch.tensor([9]), torch.tensor([5]), None)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.infer(data)
+
+
+@pytest.mark.parametrize("hidden,out,lp,lr", [(64, 40, 0, 1), (128, 256, 3, 2), (256, 256, 6, 6), (512, 512, 1, 1)])
+def test_registry_matches_python_over_configurations(hidden, out, lp, lr):
+    cfg = {"phoneme_encoder": dict(in_channels=hidden, hidden_channels=hidden, out_channels=out, n_layers=lp),
+           "prompt_encoder": dict(in_channels=100, hidden_channels=hidden, out_channels=out, n_layers=lr)}
+    m, reg = _registry(cfg)
+    assert reg == pre_param_shapes(cfg)
+    assert sum(p.numel() for p in m.parameters()) == sum(int(torch.tensor(s).prod()) for s in reg.values())
+
+
+def test_bad_configurations_rejected():
+    L = _lib.lib()
+    base = dict(phone_in=64, phone_hidden=64, phone_out=40, phone_layers=1, prompt_in=100, prompt_hidden=64, prompt_out=40, prompt_layers=1,
+                ref_dim=100, ref_heads=1, n_heads=8, ffn_kernel=9)
+    for bad, needle in ((dict(ffn_kernel=8), b"ffn_kernel"), (dict(ffn_kernel=11), b"ffn_kernel"), (dict(phone_hidden=60, phone_in=60), b"hidden width"),
+                        (dict(prompt_in=80), b"ref_dim"), (dict(n_heads=0), b"head")):
+        c = _lib.PreCfg(**{**base, **bad})
+        h = C.c_void_p()
+        assert L.ns2vc_pre_create(C.byref(c), C.byref(h)) != 0 and needle in L.ns2vc_last_error(), (bad, L.ns2vc_last_error())
