@@ -159,7 +159,7 @@ int ns2vc_unet_profile_dump(ns2vc_unet* h, const char* csv_path);   /* one row p
 int ns2vc_unet_profile_reset(ns2vc_unet* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Condition encoders: `Pre_model.infer` (reference model.py:360-377) - the step immediately BEFORE the denoiser
+ * Condition encoders: `Pre_model.infer` (reference model.py:359-377) - the step immediately BEFORE the denoiser
  * (SURVEY.md 8(f) rank 1): ref_enc (TextTimeEmbedding, unet1d/embeddings.py:421-434), PromptEncoder and PhoneEncoder
  * (model.py:98-190: ConvLayer -> n x EncSALayer (operations.py:784-821: LayerNorm, 8-head self-attention with key padding,
  * LayerNorm, k=9 conv-FFN) -> ConvLayer -> LayerNorm), all frames past an utterance's length exactly zero.

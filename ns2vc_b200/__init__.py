@@ -50,7 +50,7 @@ def install() -> None:
 
 def install_pre_model(model_module=None) -> None:
     """Make the reference's ``model.Pre_model`` (defined inside ``model.py`` itself, :328) the B200 implementation: call after
-    ``import model`` and before ``NaturalSpeech2(cfg)`` is constructed (``model.py:445`` looks the class up by its global name)."""
+    ``import model`` and before ``NaturalSpeech2(cfg)`` is constructed (``model.py:451`` looks the class up by its global name)."""
     from .pre_model import Pre_model
     if model_module is None:
         model_module = sys.modules.get("model")

@@ -69,7 +69,7 @@ def sample_latents(unet: UNet1DConditionModel, x_T: torch.Tensor, content_TBC: t
 def sample_from_features(pre_model, unet: UNet1DConditionModel, x_T: torch.Tensor, c_padded: torch.Tensor, refer_padded: torch.Tensor,
                          lengths: torch.Tensor, refer_lengths: torch.Tensor, steps: int = 50, method: str = "dpmsolver",
                          device: Optional[torch.device] = None, out_device: Optional[torch.device] = None) -> torch.Tensor:
-    """The device part of ``NaturalSpeech2.sample`` before the vocoder (reference model.py:612-686): ``pre_model.infer`` (condition
+    """The device part of ``NaturalSpeech2.sample`` before the vocoder (reference model.py:606-686): ``pre_model.infer`` (condition
     encoders) followed by the sampling run.  c_padded [B, 256, T] (ContentVec features), refer_padded [B, 100, S] (mel prompt),
     lengths / refer_lengths [B]; host tensors are copied to the device.  Returns the mel latents [B, 100, T]."""
     dev = torch.device(device) if device is not None else next(unet.parameters()).device

@@ -1,8 +1,8 @@
-// Condition-encoder engine: `Pre_model.infer` of the reference (model.py:360-377) as one launch program per (B, T, S) over the
+// Condition-encoder engine: `Pre_model.infer` of the reference (model.py:359-377) as one launch program per (B, T, S) over the
 // denoiser's own kernels - the tcgen05 3xBF16 GEMM (gemm_tc.cu, ENC instantiation for the ReLU / padding-mask epilogues), the
 // flash attention kernels (key-padding bias), the LayerNorm split - plus the handful of small kernels in pre_kernels.cu.
 //
-//   g            = ref_enc(refer^T)                      TextTimeEmbedding(100, 100, 1)      model.py:340, 364; embeddings.py:421-434
+//   g            = ref_enc(refer^T)                      TextTimeEmbedding(100, 100, 1)      model.py:340, 362; embeddings.py:421-434
 //   audio_prompt = PromptEncoder(refer, refer_lengths)   model.py:173-190
 //   content      = PhoneEncoder(c + spk_proj(g), lengths) model.py:128-148
 //
@@ -371,7 +371,7 @@ int build_program(ns2vc_pre* h, int B, int T, int S, void* ws, size_t* bytes_out
   double* stat_arena = ar.get<double>(stat_doubles);
   double* stat_cur = stat_arena;
   { PLaunch l; l.kind = PLaunch::MEMSET; l.mem = stat_arena; l.mem_bytes = stat_doubles * sizeof(double); prog.push_back(l); }
-  // ---- ref_enc: TextTimeEmbedding over ALL S prompt frames (the reference does not mask them: model.py:364)
+  // ---- ref_enc: TextTimeEmbedding over ALL S prompt frames (the reference does not mask them: model.py:362)
   const int R = c.ref_dim;
   float* rt = ar.get<float>((size_t)B * S * R);
   float* rn = ar.get<float>((size_t)B * S * R);

@@ -2,7 +2,7 @@
 (``TextTimeEmbedding(100, 100, 1)``), ``PromptEncoder`` and ``PhoneEncoder`` (``model.py:98-190``, six
 ``EncSALayer`` each, ``operations.py:784-821``).  It is the step immediately BEFORE the denoiser
 (SURVEY.md §8(f) rank 1): ``NaturalSpeech2.sample`` calls ``self.pre_model.infer(data)`` and hands the two
-results to the sampler (``model.py:612-620``).
+results to the sampler (``model.py:631-633, 666-668``).
 
 Same constructor argument (the ``cfg`` dict with ``phoneme_encoder`` / ``prompt_encoder`` keyword sets), same
 ``state_dict`` key names and shapes (34 923 404 parameters for the shipped configuration, ``demo.ipynb:447``), same

@@ -120,7 +120,7 @@ def test_full_config_vs_oracle_shapes(B, T, S):
 
 def test_padded_frames_of_the_input_do_not_leak():
     """Values (even NaN) in the padded frames of c / refer must not change anything: the reference zero-fills them first
-    (ConvLayer.forward model.py:91-92) - except through ref_enc, which reads ALL prompt frames (model.py:364)."""
+    (ConvLayer.forward model.py:91-92) - except through ref_enc, which reads ALL prompt frames (model.py:362)."""
     m, _ = make(FULL, seed=2)
     c, refer, lengths, refer_lengths = inputs(2, 96, 40, 256, seed=5, dl=31, ds=0)
     base_c, base_p = m.infer(data_of(c, refer, lengths, refer_lengths))
