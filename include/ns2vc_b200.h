@@ -184,7 +184,7 @@ int ns2vc_pre_workspace_bytes(const ns2vc_pre* h, int B, int T, int S, size_t* b
 /* Pre_model.infer:
  *   c [B, phone_in, T] fp32, refer [B, prompt_in, S] fp32 (contiguous), lengths / refer_lengths [B] int64 (device, each >= 1)
  *   -> content [B, T, phone_out], prompt [B, S, prompt_out] fp32 token-major (the reference returns the [T, B, C] / [S, B, C]
- *      views of the same values: model.py:147, 189).                                                                        */
+ *      views of the same values: model.py:145, 189).                                                                        */
 int ns2vc_pre_infer(ns2vc_pre* h, const float* c, const float* refer, const int64_t* lengths, const int64_t* refer_lengths,
                     float* content, float* prompt, int B, int T, int S, void* ws, ns2vc_stream stream);
 /* Diagnostics for the parity tests: per-layer activations (token-major [B, rows, channels]; rows = 1 for the speaker vector). */

@@ -113,8 +113,8 @@ enum EpiFlags : int {
                       //   acc <- rstd_row * (acc - mean_row * ln_g[n]);  bias then carries beta.W + bias   (see engine.cu)
   EPI_ROWSTATS = 512, // accumulate per-row sum / sum-of-squares of the fp32 output (LayerNorm statistics for the consumer)
   // condition encoders (pre_engine.cu; the ENC instantiation of the tcgen05 kernel):
-  EPI_RELU = 1024,    // max(v, 0) after bias / residual              (conv-FFN, reference operations.py:686)
-  EPI_ROWMASK = 2048, // v *= rowmask[m] after everything else         (x * (1 - padding_mask), reference operations.py:812, 820)
+  EPI_RELU = 1024,    // max(v, 0) after bias / residual              (conv-FFN, reference operations.py:689)
+  EPI_ROWMASK = 2048, // v *= rowmask[m] after everything else         (x * (1 - padding_mask), reference operations.py:813, 820)
 };
 
 // One panel segment of a panel-mode GEMM: `ncb` 64-channel blocks of one raw split source

@@ -4,21 +4,21 @@
 //
 //   g            = ref_enc(refer^T)                      TextTimeEmbedding(100, 100, 1)      model.py:340, 362; embeddings.py:421-434
 //   audio_prompt = PromptEncoder(refer, refer_lengths)   model.py:173-190
-//   content      = PhoneEncoder(c + spk_proj(g), lengths) model.py:128-148
+//   content      = PhoneEncoder(c + spk_proj(g), lengths) model.py:125-145
 //
 // Encoder (token-major [B, T, C] throughout; the reference's [T, B, C] is the transposed view of the same values):
-//   x0 = (input) * keep                      -> LayerNorm -> k=1 ConvTBC + bias, * keep                  ConvLayer, model.py:86-96, 137-138
+//   x0 = (input) * keep                      -> LayerNorm -> k=1 ConvTBC + bias, * keep                  ConvLayer, model.py:88-96, 134-135
 //   per layer (EncSALayer, operations.py:798-821):
 //     q|k|v = LN1(x) in_proj^T        LayerNorm FOLDED into the GEMM (gamma in the weights, mean / rstd in the epilogue, row sums
 //                                      accumulated by the producer's epilogue): no LayerNorm kernel
 //     a     = softmax(q k^T dh^-0.5 + key padding bias) v                                                operations.py:412-421
-//     x     = (x + a out_proj^T) * keep                                                                  :811-812
+//     x     = (x + a out_proj^T) * keep                                                                  :812-813
 //     y     = LN2(x)                   explicit (ln_split): the conv-FFN reads NEIGHBOUR rows, whose statistics differ per tap;
 //                                      padded frames of x are zero, so y = beta there - exactly what the reference's FFN sees
 //     f     = relu(k^-0.5 sum_i y[t + off_i] W_i^T + b)   ONE implicit GEMM over 8 row-shifted views (tap 0 of the reference reads
-//                                      the unshifted input, like the centre tap: both weights are summed at load time)      :664-687
-//     x     = (x + f ffn_2^T + b2) * keep                                                                :688-690, 819-820
-//   out = LN(LN_o(x) conv_o + b_o) * keep   (LN_o folded into the k=1 conv; final LayerNorm + mask: ln_mask)  model.py:143-147
+//                                      the unshifted input, like the centre tap: both weights are summed at load time)      :678-684
+//     x     = (x + f ffn_2^T + b2) * keep                                                                :689-691, 819-820
+//   out = LN(LN_o(x) conv_o + b_o) * keep   (LN_o folded into the k=1 conv; final LayerNorm + mask: ln_mask)  model.py:141-144
 #include "common.cuh"
 #include "../../include/ns2vc_b200.h"
 
@@ -394,7 +394,7 @@ int build_program(ns2vc_pre* h, int B, int T, int S, void* ws, size_t* bytes_out
     o.x = rpool; o.x_ld = R; o.M = B; o.K = R; o.W = h->W("ref_enc.proj.weight"); o.bias = h->W("ref_enc.proj.bias"); o.N = R; o.out = rproj; o.out_ld = R; prog.push_back(l); }
   { PLaunch l; l.kind = PLaunch::LN_APPLY; l.a = rproj; l.i0 = R; l.i1 = B; l.i2 = R; l.f0 = 1e-5f; l.b = h->W("ref_enc.norm2.weight"); l.c = h->W("ref_enc.norm2.bias"); l.o = g; l.i3 = R; prog.push_back(l); }
   bld.emit_tap("ref_enc", g, 1, R);
-  // spk_proj: Conv1d(100, hidden, 1) on g [B, 100, 1] (model.py:127, 130)
+  // spk_proj: Conv1d(100, hidden, 1) on g [B, 100, 1] (model.py:123, 127)
   { PLaunch l; l.kind = PLaunch::LINEAR; LinOp& o = l.lin; memset(&o, 0, sizeof(o));
     o.x = g; o.x_ld = R; o.M = B; o.K = R; o.W = h->W("phoneme_encoder.spk_proj.weight"); o.bias = h->W("phoneme_encoder.spk_proj.bias"); o.N = c.phone_hidden; o.out = spk; o.out_ld = c.phone_hidden; prog.push_back(l); }
   build_encoder(bld, h->prompt, S, 2, nullptr, stat_cur);

@@ -47,7 +47,7 @@ int launch_seq_mask(const long long* len, int B, int T, float* keep, float* kbia
   return 0;
 }
 
-// Encoder entry (PhoneEncoder.forward model.py:130-131 + ConvLayer.forward :91-92): [B, C, T] (+ spk[b, c]) -> token-major fp32
+// Encoder entry (PhoneEncoder.forward model.py:127-128 + ConvLayer.forward :92-93): [B, C, T] (+ spk[b, c]) -> token-major fp32
 // [B, T, ld] with padded frames and channels >= C zeroed.  32x32 shared-memory transpose, coalesced on both sides.
 __global__ void enc_input_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ rowbias, const float* __restrict__ keep,
                                  int C, int T, float* __restrict__ out, int ld) {
@@ -78,7 +78,7 @@ int launch_enc_input(const float* x, long long bstride, const float* rowbias, co
   return 0;
 }
 
-// Encoder exit (model.py:144-147): y = LayerNorm(x) * keep; one warp per row, two-pass statistics.
+// Encoder exit (model.py:142-144): y = LayerNorm(x) * keep; one warp per row, two-pass statistics.
 __global__ void __launch_bounds__(256) ln_mask_kernel(const float* __restrict__ x, int ld, int M, int C, float eps, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, const float* __restrict__ keep, float* __restrict__ y, int y_ld) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -166,7 +166,7 @@ int launch_tbc_weight(const float* w, int k, int cin, int cout, float* o, cudaSt
   return 0;
 }
 
-// TransformerFFNLayer first stage (reference operations.py:664-690): k Linear layers over k row shifts of the input, summed,
+// TransformerFFNLayer first stage (reference operations.py:664-692): k Linear layers over k row shifts of the input, summed,
 // times k^-0.5.  With `padded` = the input zero-padded by (k-1)/2 frames on both sides, tap i >= 1 reads padded[t + i], i.e. input
 // row t + i - (k-1)/2; tap 0 reads the UNPADDED input (the reference's `shifted = padded[i:T+i] if i else x`), i.e. row t - the
 // same rows as the centre tap.  Packed here as ONE (k-1)-tap conv weight [F, H, k-1] for the row offsets 1-(k-1)/2 .. (k-1)/2:

@@ -54,7 +54,7 @@ def pre_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
         def last_ln():
             shapes[p + ".layer_norm.weight"] = (cout,); shapes[p + ".layer_norm.bias"] = (cout,)
 
-        if not spk:                     # registration order of the reference modules (model.py:118-127 vs 168-172)
+        if not spk:                     # registration order of the reference modules (model.py:118-123 vs 166-170)
             last_ln()
         shapes[p + ".pre.layer_norm.weight"] = (cin,); shapes[p + ".pre.layer_norm.bias"] = (cin,)
         shapes[p + ".pre.conv.weight"] = (1, cin, H); shapes[p + ".pre.conv.bias"] = (H,)
@@ -91,7 +91,7 @@ class Pre_model(nn.Module):
                 t = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
             elif key.endswith("positional_embedding"):
                 t = torch.randn(shape) / math.sqrt(shape[-1])
-            elif key.endswith("conv.weight") and len(shape) == 3 and "spk_proj" not in key:     # ConvTBC [k, c_in, c_out]: model.py:81-83
+            elif key.endswith("conv.weight") and len(shape) == 3 and "spk_proj" not in key:     # ConvTBC [k, c_in, c_out]: model.py:80-84
                 t = torch.randn(shape) * math.sqrt(4 * 0.8 / (shape[0] * shape[1]))
             elif leaf == "bias":
                 t = torch.zeros(shape)

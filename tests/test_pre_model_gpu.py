@@ -1,7 +1,7 @@
 """Condition encoders on the GPU (`Pre_model.infer`) against fixtures written by the unmodified
 reference (tests/golden/pre_model_*.pt, oracle/make_golden_pre.py) and against the pinned oracle at larger, ragged shapes.
 Through the C-ABI (ns2vc_pre_*).  Tolerance: the north star's rtol 1e-3 / atol 1e-4 vs the CPU fp32 path; frames past an
-utterance's length must be EXACTLY zero (model.py:146-148, 188-190)."""
+utterance's length must be EXACTLY zero (model.py:142-144, 186-188)."""
 import os
 
 import pytest
@@ -120,7 +120,7 @@ def test_full_config_vs_oracle_shapes(B, T, S):
 
 def test_padded_frames_of_the_input_do_not_leak():
     """Values (even NaN) in the padded frames of c / refer must not change anything: the reference zero-fills them first
-    (ConvLayer.forward model.py:91-92) - except through ref_enc, which reads ALL prompt frames (model.py:362)."""
+    (ConvLayer.forward model.py:92-93) - except through ref_enc, which reads ALL prompt frames (model.py:362)."""
     m, _ = make(FULL, seed=2)
     c, refer, lengths, refer_lengths = inputs(2, 96, 40, 256, seed=5, dl=31, ds=0)
     base_c, base_p = m.infer(data_of(c, refer, lengths, refer_lengths))
