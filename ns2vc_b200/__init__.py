@@ -5,6 +5,7 @@ Drop-in surface (same names as the reference):
     ns2vc_b200.dpm_solver.{NoiseScheduleVP, model_wrapper, DPM_Solver}   <- sampler/dpm_solver.py
     ns2vc_b200.uni_pc.{NoiseScheduleVP, model_wrapper, UniPC}            <- sampler/uni_pc.py
     ns2vc_b200.pre_model.Pre_model                <- model.py:328-377 (condition encoders; ``install_pre_model(model)``)
+    ns2vc_b200.frontend.repeat_expand_2d          <- utils.py:482-496 (feature stretch in front of the encoders)
 ``ns2vc_b200.install()`` aliases those module paths so the reference's model.py / infer.py import
 them unchanged.
 """
